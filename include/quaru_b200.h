@@ -1,0 +1,171 @@
+/*
+ * quaru_b200.h -- C ABI of the B200-native state-vector engine behind Quaru's
+ * Register / Operation API (the drop-in boundary).
+ *
+ * The reference (DATX11-22/quaru) has no FFI of its own: its API *is* the Rust
+ * `impl Register` (src/register.rs:39-407).  Each entry point below names the
+ * reference item it replaces; a Rust `register.rs` shim (rust/src/register.rs)
+ * binds exactly these symbols and keeps the reference's method signatures.
+ *
+ * Conventions
+ *   - return 0 = QB_OK; negative = mirror of `OperationError` (register.rs:10-20);
+ *     positive = device/runtime failures that have no reference equivalent (the
+ *     Rust shim panics on them: there is no CPU fallback).
+ *   - complex numbers are interleaved (re, im) doubles = num::Complex<f64> (#[repr(C)]).
+ *   - amplitude index bit q  <->  qubit q (register.rs:47-50).
+ *   - gate matrices are row-major 2^k x 2^k; matrix index bit j <-> targets[j]
+ *     (register.rs:168-173); targets are in arbitrary order, not sorted.
+ *   - every host pointer is borrowed for the duration of the call only.
+ *   - a handle may be used by one thread at a time (`&mut self` in the reference);
+ *     different handles may be used concurrently.
+ *   - qb_apply / qb_apply_all / qb_apply_batch enqueue work (gates are buffered
+ *     and fused into multi-gate passes); every call that returns data
+ *     (measure, probabilities, read, norm, diff) or qb_flush/qb_sync first
+ *     drains the queue.  QB_OPT_FUSION=0 makes every gate its own HBM pass.
+ *   - no exception or panic crosses this boundary.
+ */
+#ifndef QUARU_B200_H
+#define QUARU_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct qb_reg qb_reg;
+
+/* ---- status codes ------------------------------------------------------------------------ */
+#define QB_OK 0
+#define QB_ERR_INVALID_TARGET (-1)     /* OperationError::InvalidTarget(usize)        register.rs:13 */
+#define QB_ERR_INVALID_DIMENSIONS (-2) /* OperationError::InvalidDimensions(r, c)     register.rs:15 */
+#define QB_ERR_INVALID_ARITY (-3)      /* OperationError::InvalidArity(usize)         register.rs:17 */
+#define QB_ERR_INVALID_QUBIT (-4)      /* OperationError::InvalidQubit(usize)         register.rs:19 */
+#define QB_ERR_INVALID_ARGUMENT (-5)   /* NULL pointer / out-of-range index: a Rust panic (index OOB) in the reference */
+#define QB_ERR_CUDA 1
+#define QB_ERR_NCCL 2
+#define QB_ERR_OOM 3
+#define QB_ERR_NO_DEVICE 4
+#define QB_ERR_UNSUPPORTED 5
+
+/* Message / payload (the usize carried by the OperationError variant) of the last failing call
+ * on the calling thread. */
+const char* qb_last_error(void);
+int64_t qb_last_error_payload(void);
+
+/* ---- construction / destruction ---------------------------------------------------------- */
+
+/* Register::new(&[bool]) register.rs:41-56 and Register::from_int(n, k) register.rs:58-63.
+ * The shim folds the bools into basis_index = sum b_q 2^q.  basis_index >= 2^n is the
+ * reference's index-out-of-bounds panic -> QB_ERR_INVALID_ARGUMENT.  Uses the current CUDA
+ * device (cudaGetDevice). */
+int qb_create(uint32_t n, uint64_t basis_index, qb_reg** out);
+
+/* Register::try_from_qubits(&[Array2<c64>]) register.rs:81-102: `qubits` is n x 2 interleaved
+ * c64, qubit i = (qubits[4i..4i+1], qubits[4i+2..4i+3]).  Validates |sum|a|^2 - 1| < 1e-6
+ * (register.rs:107-115) -> QB_ERR_INVALID_QUBIT with payload i. */
+int qb_create_product(const double* qubits, uint32_t n, qb_reg** out);
+
+/* Sharded register: rank `rank` of `world` (power of two) holds amplitudes whose top
+ * log2(world) index bits equal `rank`.  `nccl_unique_id` is the 128-byte ncclUniqueId produced
+ * by qb_nccl_unique_id() on rank 0 and broadcast by the caller (torch.distributed in bench.py).
+ * All subsequent calls on the handle are collective: every rank makes the same calls with the
+ * same arguments.  No reference equivalent (the reference is single-process). */
+int qb_create_sharded(uint32_t n, uint64_t basis_index, int32_t rank, int32_t world,
+                      const void* nccl_unique_id, qb_reg** out);
+int qb_nccl_unique_id(void* out128);
+
+/* #[derive(Clone)] register.rs:23 ; Drop.  qb_destroy(NULL) is a no-op. */
+int qb_clone(qb_reg* src, qb_reg** out);
+void qb_destroy(qb_reg* reg);
+
+/* `*qreg = Register::new(&vec![false; n])` (openqasm.rs:129) without reallocating. */
+int qb_reset(qb_reg* reg, uint64_t basis_index);
+
+/* Register::size() register.rs:404-406 */
+uint32_t qb_num_qubits(const qb_reg* reg);
+
+/* ---- gate application -------------------------------------------------------------------- */
+
+/* Register::apply / try_apply_fast / try_apply (register.rs:134-250).
+ * Validation in the reference's order: smallest duplicate target -> QB_ERR_INVALID_TARGET
+ * (payload = duplicate), first target >= n in `targets` order -> QB_ERR_INVALID_TARGET
+ * (payload = that target).  No unitarity is assumed. */
+int qb_apply(qb_reg* reg, const double* matrix, const uint32_t* targets, uint32_t k);
+
+/* Register::apply_all / try_apply_all (register.rs:259-281): the 2x2 gate on every qubit.
+ * The arity check (InvalidArity) belongs to the shim, which owns the Operation. */
+int qb_apply_all(qb_reg* reg, const double* m2x2);
+
+/* One gate of a batch: the (matrix, targets) payload of `Operation` (operation.rs:49-52). */
+typedef struct qb_gate {
+    const double* matrix;    /* row-major 2^k x 2^k interleaved c64 */
+    const uint32_t* targets; /* k entries */
+    uint32_t k;
+} qb_gate;
+
+/* The gate loop of Register::apply_circuit (register.rs:346-350): validates all gates first
+ * (nothing is applied if any is invalid; payload = offending qubit), then enqueues them. */
+int qb_apply_batch(qb_reg* reg, const qb_gate* gates, uint64_t count);
+
+/* ---- measurement ------------------------------------------------------------------------- */
+
+/* First loop of try_measure (register.rs:303-315): p0/p1 = sum |a_i|^2 by bit `target`.
+ * Deterministic fixed-shape tree reduction (independent of the number of GPUs). */
+int qb_probabilities(qb_reg* reg, uint32_t target, double* p0, double* p1);
+
+/* Register::measure / try_measure (register.rs:291-342).  `u` is the uniform [0,1) draw the
+ * reference takes from thread_rng (register.rs:317-318); the shim supplies it.
+ * outcome = (u > p0); rejected half zeroed; kept half divided by sqrt(p_outcome). */
+int qb_measure(qb_reg* reg, uint32_t target, double u, int32_t* outcome);
+
+/* ---- state access (`pub state`, print_*, PartialEq; register.rs:35, 379-413) -------------- */
+
+/* Copy amplitudes [offset, offset+count) to / from host (2*count doubles).  On a sharded
+ * register the range is in GLOBAL index space; only the part owned by this rank is
+ * transferred (read: the rest of `out` is left untouched). */
+int qb_read_state(qb_reg* reg, uint64_t offset, uint64_t count, double* out);
+int qb_write_state(qb_reg* reg, uint64_t offset, uint64_t count, const double* in);
+
+/* sum |a_i|^2 ; max_i |a_i - b_i| (PartialEq uses < 1e-8, register.rs:411) ; sum |a_i-b_i|^2 */
+int qb_norm2(qb_reg* reg, double* out);
+int qb_max_abs_diff(qb_reg* a, qb_reg* b, double* out);
+int qb_l2_diff2(qb_reg* a, qb_reg* b, double* out);
+
+/* ---- queue / stream control -------------------------------------------------------------- */
+int qb_flush(qb_reg* reg); /* plan + launch everything queued; asynchronous */
+int qb_sync(qb_reg* reg);  /* flush + wait for the handle's stream */
+
+/* CUDA-event stopwatch on the handle's own stream (torch.cuda.Event cannot see it).
+ * start: flush, record; stop: flush, record, synchronize, return elapsed ms. */
+int qb_timer_start(qb_reg* reg);
+int qb_timer_stop(qb_reg* reg, float* ms);
+
+#define QB_OPT_FUSION 1        /* 1 (default): buffer gates and fuse into tile passes; 0: one pass per gate */
+#define QB_OPT_TILE_BITS 2     /* log2 amplitudes per shared-memory tile (default 12) */
+#define QB_OPT_MAX_QUEUE 3     /* auto-flush after this many buffered gates (default 4096) */
+#define QB_OPT_FORCE_PATH 4    /* tests only: 0 auto, 1 generic kernel, 2 tile kernel, 3 streaming kernels */
+int qb_set_option(qb_reg* reg, int32_t option, int64_t value);
+
+#define QB_STAT_KERNEL_LAUNCHES 1 /* kernels launched by this handle since creation */
+#define QB_STAT_PASSES 2          /* state sweeps (HBM read+write passes) */
+#define QB_STAT_GATES 3           /* gates accepted */
+#define QB_STAT_BYTES_MOVED 4     /* physical HBM bytes the launched passes read+wrote (model) */
+#define QB_STAT_SWAP_BYTES 5      /* bytes this rank sent over NVLink in global<->local swaps */
+#define QB_STAT_SWAPS 6           /* number of global<->local exchanges */
+int qb_get_stat(qb_reg* reg, int32_t stat, int64_t* value);
+
+/* ---- planner introspection (host only, no GPU needed) ------------------------------------ */
+/* Plans `count` gates for an n-qubit register with the given tile parameters exactly as
+ * qb_flush would, and writes for each gate the index of the pass it was assigned to
+ * (pass_of_gate[count]) and its position inside the pass (order_in_pass[count]).
+ * Returns the number of passes, or a negative error. */
+int64_t qb_plan_debug(uint32_t n, const qb_gate* gates, uint64_t count, uint32_t tile_bits,
+                      int32_t* pass_of_gate, int32_t* order_in_pass);
+
+const char* qb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QUARU_B200_H */

@@ -1,0 +1,417 @@
+// qb_api.cu -- the extern "C" boundary (include/quaru_b200.h): handle lifetime, argument
+// validation in the reference's order, the gate queue, measurement and state access.
+// Each entry point cites the reference item it stands in for (src/register.rs).
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+
+#include "qb_common.h"
+#include "qb_shard.h"
+
+namespace qb {
+const char* last_error_str();
+int64_t last_error_payload();
+
+// register.rs:146-153 (get_duplicate :418-429 first, then the range check in `targets` order)
+static int validate_targets(uint32_t n, const uint32_t* targets, uint32_t k) {
+    if (k > 0 && !targets) return set_error(QB_ERR_INVALID_ARGUMENT, -1, "targets is NULL");
+    if (k >= 2) {
+        std::vector<uint32_t> s(targets, targets + k);
+        std::sort(s.begin(), s.end());
+        for (uint32_t i = 1; i < k; ++i)
+            if (s[i] == s[i - 1]) return set_error(QB_ERR_INVALID_TARGET, s[i], "InvalidTarget(%u): duplicate target", s[i]);
+    }
+    for (uint32_t j = 0; j < k; ++j)
+        if (targets[j] >= n)
+            return set_error(QB_ERR_INVALID_TARGET, targets[j], "InvalidTarget(%u): register has %u qubits", targets[j], n);
+    return QB_OK;
+}
+
+static int alloc_common(Reg* r) {
+    QB_CUDA(cudaGetDevice(&r->device));
+    QB_CUDA(cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking));
+    QB_CUDA(cudaEventCreate(&r->ev0));
+    QB_CUDA(cudaEventCreate(&r->ev1));
+    QB_CUDA(cudaEventCreateWithFlags(&r->prog_free, cudaEventDisableTiming));
+    const uint64_t n_amps = 1ull << r->n_local;
+    cudaError_t e = cudaMalloc((void**)&r->state, n_amps * sizeof(c64));
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return set_error(e == cudaErrorMemoryAllocation ? QB_ERR_OOM : QB_ERR_CUDA, (int64_t)e,
+                         "cannot allocate %.3f GB for a %u-qubit shard: %s", n_amps * 16.0 / 1e9, r->n_local,
+                         cudaGetErrorString(e));
+    }
+    r->phys_of.resize(r->n);
+    for (uint32_t q = 0; q < r->n; ++q) r->phys_of[q] = q;
+    return QB_OK;
+}
+
+static void free_reg(Reg* r) {
+    if (!r) return;
+    cudaSetDevice(r->device);
+    if (r->stream) cudaStreamSynchronize(r->stream);
+    shard_destroy(r);
+    if (r->state) cudaFree(r->state);
+    if (r->scratch) cudaFree(r->scratch);
+    if (r->partials) cudaFree(r->partials);
+    if (r->dmat) cudaFree(r->dmat);
+    if (r->dprog) cudaFree(r->dprog);
+    if (r->hpin) cudaFreeHost(r->hpin);
+    if (r->ev0) cudaEventDestroy(r->ev0);
+    if (r->ev1) cudaEventDestroy(r->ev1);
+    if (r->prog_free) cudaEventDestroy(r->prog_free);
+    if (r->stream) cudaStreamDestroy(r->stream);
+    delete r;
+}
+
+static int create_impl(uint32_t n, uint64_t basis_index, int rank, int world, const void* uid, qb_reg** out) {
+    if (!out) return set_error(QB_ERR_INVALID_ARGUMENT, -1, "out is NULL");
+    *out = nullptr;
+    if (n > 40) return set_error(QB_ERR_UNSUPPORTED, n, "%u qubits: at most 40 are supported", n);
+    if (n < 64 && basis_index >= (1ull << n))
+        return set_error(QB_ERR_INVALID_ARGUMENT, (int64_t)basis_index,
+                         "basis index %llu out of range for %u qubits (reference: index out of bounds panic, math.rs:46)",
+                         (unsigned long long)basis_index, n);
+    if (world < 1 || (world & (world - 1)) || rank < 0 || rank >= world)
+        return set_error(QB_ERR_INVALID_ARGUMENT, world, "world must be a power of two and 0 <= rank < world");
+    uint32_t g = 0;
+    while ((1 << g) < world) ++g;
+    if (g > n) return set_error(QB_ERR_INVALID_ARGUMENT, world, "%d ranks need at least %u qubits", world, g);
+    Reg* r = new (std::nothrow) Reg();
+    if (!r) return set_error(QB_ERR_OOM, -1, "host allocation failed");
+    r->n = n;
+    r->n_local = n - g;
+    r->rank = rank;
+    r->world = world;
+    int rc = alloc_common(r);
+    if (rc == QB_OK && world > 1) rc = shard_init(r, uid);
+    if (rc == QB_OK) {
+        const uint64_t owner = basis_index >> r->n_local;
+        rc = k_init_basis(r, basis_index & ((1ull << r->n_local) - 1), owner == (uint64_t)rank);
+    }
+    if (rc != QB_OK) { free_reg(r); return rc; }
+    *out = reinterpret_cast<qb_reg*>(r);
+    return QB_OK;
+}
+
+// Launch everything queued.  Fusion on: plan tile passes (qb_tile.cu); off: one kernel per gate.
+static int flush(Reg* r) {
+    if (r->queue.empty()) return QB_OK;
+    QB_CUDA(cudaSetDevice(r->device));
+    std::vector<Gate> gates;
+    gates.swap(r->queue);
+    if (r->world > 1) return shard_run(r, gates);
+    if (r->fusion) return run_fused(r, gates);
+    for (const Gate& g : gates) QB_TRY(k_apply_gate_unfused(r, g));
+    return QB_OK;
+}
+
+int run_local(Reg* r, std::vector<Gate>& gates) {
+    if (r->fusion) return run_fused(r, gates);
+    for (const Gate& g : gates) QB_TRY(k_apply_gate_unfused(r, g));
+    return QB_OK;
+}
+
+static int enqueue(Reg* r, const double* matrix, const uint32_t* targets, uint32_t k) {
+    Gate g;
+    r->st_gates++;
+    if (!classify_gate(matrix, targets, k, &g)) return QB_OK;  // exact identity
+    r->queue.push_back(std::move(g));
+    if (!r->fusion || r->queue.size() >= r->max_queue) return flush(r);
+    return QB_OK;
+}
+
+}  // namespace qb
+
+using namespace qb;
+
+#define REG(p) reinterpret_cast<qb::Reg*>(p)
+#define CHECK_REG(p) \
+    if (!(p)) return qb::set_error(QB_ERR_INVALID_ARGUMENT, -1, "register handle is NULL")
+
+extern "C" {
+
+const char* qb_last_error(void) { return qb::last_error_str(); }
+int64_t qb_last_error_payload(void) { return qb::last_error_payload(); }
+const char* qb_version(void) { return "quaru_b200 0.1 (sm_100a)"; }
+
+int qb_create(uint32_t n, uint64_t basis_index, qb_reg** out) { return create_impl(n, basis_index, 0, 1, nullptr, out); }
+
+int qb_create_sharded(uint32_t n, uint64_t basis_index, int32_t rank, int32_t world, const void* uid, qb_reg** out) {
+    if (world > 1 && !uid) return set_error(QB_ERR_INVALID_ARGUMENT, -1, "nccl_unique_id is NULL");
+    return create_impl(n, basis_index, rank, world, uid, out);
+}
+
+int qb_nccl_unique_id(void* out128) { return shard_unique_id(out128); }
+
+// Register::try_from_qubits (register.rs:81-102)
+int qb_create_product(const double* qubits, uint32_t n, qb_reg** out) {
+    if (!out) return set_error(QB_ERR_INVALID_ARGUMENT, -1, "out is NULL");
+    *out = nullptr;
+    if (n > 0 && !qubits) return set_error(QB_ERR_INVALID_ARGUMENT, -1, "qubits is NULL");
+    for (uint32_t i = 0; i < n; ++i) {  // is_one (register.rs:107-115)
+        double total_prob = -1.0;
+        for (int j = 0; j < 2; ++j) {
+            const double re = qubits[4 * i + 2 * j], im = qubits[4 * i + 2 * j + 1];
+            total_prob += re * re + im * im;
+        }
+        if (!(fabs(total_prob) < 0.000001)) return set_error(QB_ERR_INVALID_QUBIT, i, "InvalidQubit(%u)", i);
+    }
+    int rc = create_impl(n, 0, 0, 1, nullptr, out);
+    if (rc != QB_OK) return rc;
+    rc = k_init_product(REG(*out), qubits);
+    if (rc != QB_OK) { free_reg(REG(*out)); *out = nullptr; }
+    return rc;
+}
+
+int qb_clone(qb_reg* src_, qb_reg** out) {
+    CHECK_REG(src_);
+    if (!out) return set_error(QB_ERR_INVALID_ARGUMENT, -1, "out is NULL");
+    Reg* src = REG(src_);
+    *out = nullptr;
+    if (src->world > 1) return set_error(QB_ERR_UNSUPPORTED, -1, "clone of a sharded register is not supported");
+    QB_TRY(flush(src));
+    int rc = create_impl(src->n, 0, 0, 1, nullptr, out);
+    if (rc != QB_OK) return rc;
+    Reg* dst = REG(*out);
+    dst->fusion = src->fusion; dst->tile_bits = src->tile_bits; dst->max_queue = src->max_queue; dst->force_path = src->force_path;
+    cudaError_t e = cudaMemcpyAsync(dst->state, src->state, sizeof(c64) << src->n_local, cudaMemcpyDeviceToDevice, src->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(src->stream);
+    if (e != cudaSuccess) { free_reg(dst); *out = nullptr; return fail_cuda(e, "clone copy", __FILE__, __LINE__); }
+    return QB_OK;
+}
+
+void qb_destroy(qb_reg* reg) { free_reg(REG(reg)); }
+
+int qb_reset(qb_reg* reg, uint64_t basis_index) {
+    CHECK_REG(reg);
+    Reg* r = REG(reg);
+    if (basis_index >= (1ull << r->n)) return set_error(QB_ERR_INVALID_ARGUMENT, (int64_t)basis_index, "basis index out of range");
+    r->queue.clear();
+    QB_CUDA(cudaSetDevice(r->device));
+    for (uint32_t q = 0; q < r->n; ++q) r->phys_of[q] = q;
+    const uint64_t owner = basis_index >> r->n_local;
+    return k_init_basis(r, basis_index & ((1ull << r->n_local) - 1), owner == (uint64_t)r->rank);
+}
+
+uint32_t qb_num_qubits(const qb_reg* reg) { return reg ? reinterpret_cast<const qb::Reg*>(reg)->n : 0; }
+
+// Register::apply -> try_apply_fast (register.rs:134-191)
+int qb_apply(qb_reg* reg, const double* matrix, const uint32_t* targets, uint32_t k) {
+    CHECK_REG(reg);
+    Reg* r = REG(reg);
+    if (!matrix) return set_error(QB_ERR_INVALID_ARGUMENT, -1, "matrix is NULL");
+    QB_TRY(validate_targets(r->n, targets, k));
+    return enqueue(r, matrix, targets, k);
+}
+
+// Register::try_apply_all (register.rs:267-281) == the 2x2 gate on every qubit
+int qb_apply_all(qb_reg* reg, const double* m2x2) {
+    CHECK_REG(reg);
+    Reg* r = REG(reg);
+    if (!m2x2) return set_error(QB_ERR_INVALID_ARGUMENT, -1, "matrix is NULL");
+    for (uint32_t q = 0; q < r->n; ++q) QB_TRY(enqueue(r, m2x2, &q, 1));
+    return QB_OK;
+}
+
+// gate loop of Register::apply_circuit (register.rs:346-350)
+int qb_apply_batch(qb_reg* reg, const qb_gate* gates, uint64_t count) {
+    CHECK_REG(reg);
+    Reg* r = REG(reg);
+    if (count && !gates) return set_error(QB_ERR_INVALID_ARGUMENT, -1, "gates is NULL");
+    for (uint64_t i = 0; i < count; ++i) {
+        if (!gates[i].matrix) return set_error(QB_ERR_INVALID_ARGUMENT, (int64_t)i, "gate %llu: matrix is NULL", (unsigned long long)i);
+        QB_TRY(validate_targets(r->n, gates[i].targets, gates[i].k));
+    }
+    for (uint64_t i = 0; i < count; ++i) QB_TRY(enqueue(r, gates[i].matrix, gates[i].targets, gates[i].k));
+    return QB_OK;
+}
+
+// first loop of try_measure (register.rs:303-315)
+int qb_probabilities(qb_reg* reg, uint32_t target, double* p0, double* p1) {
+    CHECK_REG(reg);
+    Reg* r = REG(reg);
+    if (!p0 || !p1) return set_error(QB_ERR_INVALID_ARGUMENT, -1, "output pointer is NULL");
+    if (target >= r->n) return set_error(QB_ERR_INVALID_TARGET, target, "InvalidTarget(%u): register has %u qubits", target, r->n);
+    QB_TRY(flush(r));
+    if (r->world > 1) return shard_probabilities(r, target, p0, p1);
+    return k_probabilities(r, (int)target, p0, p1);
+}
+
+// Register::try_measure (register.rs:297-342)
+int qb_measure(qb_reg* reg, uint32_t target, double u, int32_t* outcome) {
+    CHECK_REG(reg);
+    Reg* r = REG(reg);
+    if (!outcome) return set_error(QB_ERR_INVALID_ARGUMENT, -1, "outcome is NULL");
+    double p0, p1;
+    QB_TRY(qb_probabilities(reg, target, &p0, &p1));
+    const int res = u > p0;                    // :321 (strict)
+    const double total = res ? p1 : p0;        // :323
+    *outcome = res;
+    if (r->world > 1) return shard_collapse(r, target, res, total);
+    return k_collapse(r, target, res, total);
+}
+
+int qb_read_state(qb_reg* reg, uint64_t offset, uint64_t count, double* out) {
+    CHECK_REG(reg);
+    Reg* r = REG(reg);
+    const uint64_t N = 1ull << r->n;
+    if (offset > N || count > N - offset) return set_error(QB_ERR_INVALID_ARGUMENT, (int64_t)offset, "range exceeds the state");
+    if (count && !out) return set_error(QB_ERR_INVALID_ARGUMENT, -1, "out is NULL");
+    QB_TRY(flush(r));
+    if (r->world > 1) QB_TRY(shard_canonicalize(r));
+    const uint64_t lo = (uint64_t)r->rank << r->n_local, hi = lo + (1ull << r->n_local);
+    const uint64_t a = std::max(offset, lo), b = std::min(offset + count, hi);
+    if (a < b)
+        QB_CUDA(cudaMemcpyAsync(out + 2 * (a - offset), r->state + (a - lo), (b - a) * sizeof(c64), cudaMemcpyDeviceToHost, r->stream));
+    QB_CUDA(cudaStreamSynchronize(r->stream));
+    return QB_OK;
+}
+
+int qb_write_state(qb_reg* reg, uint64_t offset, uint64_t count, const double* in) {
+    CHECK_REG(reg);
+    Reg* r = REG(reg);
+    const uint64_t N = 1ull << r->n;
+    if (offset > N || count > N - offset) return set_error(QB_ERR_INVALID_ARGUMENT, (int64_t)offset, "range exceeds the state");
+    if (count && !in) return set_error(QB_ERR_INVALID_ARGUMENT, -1, "in is NULL");
+    QB_TRY(flush(r));
+    if (r->world > 1) QB_TRY(shard_canonicalize(r));
+    const uint64_t lo = (uint64_t)r->rank << r->n_local, hi = lo + (1ull << r->n_local);
+    const uint64_t a = std::max(offset, lo), b = std::min(offset + count, hi);
+    if (a < b)
+        QB_CUDA(cudaMemcpyAsync(r->state + (a - lo), in + 2 * (a - offset), (b - a) * sizeof(c64), cudaMemcpyHostToDevice, r->stream));
+    QB_CUDA(cudaStreamSynchronize(r->stream));
+    return QB_OK;
+}
+
+int qb_norm2(qb_reg* reg, double* out) {
+    CHECK_REG(reg);
+    Reg* r = REG(reg);
+    if (!out) return set_error(QB_ERR_INVALID_ARGUMENT, -1, "out is NULL");
+    QB_TRY(flush(r));
+    double p0, p1;
+    if (r->world > 1) QB_TRY(shard_probabilities(r, UINT32_MAX, &p0, &p1));
+    else QB_TRY(k_probabilities(r, -1, &p0, &p1));
+    *out = p0;
+    return QB_OK;
+}
+
+static int diff_impl(qb_reg* a_, qb_reg* b_, double* mx, double* l2) {
+    CHECK_REG(a_);
+    CHECK_REG(b_);
+    Reg *a = REG(a_), *b = REG(b_);
+    if (a->n != b->n || a->world != b->world || a->device != b->device)
+        return set_error(QB_ERR_INVALID_ARGUMENT, -1, "registers differ in size, sharding or device");
+    QB_TRY(flush(a));
+    QB_TRY(flush(b));
+    if (a->world > 1) { QB_TRY(shard_canonicalize(a)); QB_TRY(shard_canonicalize(b)); }
+    double m, l;
+    QB_TRY(k_diff(a, b, &m, &l));
+    if (a->world > 1) QB_TRY(shard_reduce_diff(a, &m, &l));
+    *mx = m;
+    *l2 = l;
+    return QB_OK;
+}
+
+int qb_max_abs_diff(qb_reg* a, qb_reg* b, double* out) {
+    if (!out) return set_error(QB_ERR_INVALID_ARGUMENT, -1, "out is NULL");
+    double l2;
+    return diff_impl(a, b, out, &l2);
+}
+
+int qb_l2_diff2(qb_reg* a, qb_reg* b, double* out) {
+    if (!out) return set_error(QB_ERR_INVALID_ARGUMENT, -1, "out is NULL");
+    double mx;
+    return diff_impl(a, b, &mx, out);
+}
+
+int qb_flush(qb_reg* reg) {
+    CHECK_REG(reg);
+    return flush(REG(reg));
+}
+
+int qb_sync(qb_reg* reg) {
+    CHECK_REG(reg);
+    Reg* r = REG(reg);
+    QB_TRY(flush(r));
+    QB_CUDA(cudaStreamSynchronize(r->stream));
+    return QB_OK;
+}
+
+int qb_timer_start(qb_reg* reg) {
+    CHECK_REG(reg);
+    Reg* r = REG(reg);
+    QB_TRY(flush(r));
+    QB_CUDA(cudaEventRecord(r->ev0, r->stream));
+    return QB_OK;
+}
+
+int qb_timer_stop(qb_reg* reg, float* ms) {
+    CHECK_REG(reg);
+    Reg* r = REG(reg);
+    if (!ms) return set_error(QB_ERR_INVALID_ARGUMENT, -1, "ms is NULL");
+    QB_TRY(flush(r));
+    QB_CUDA(cudaEventRecord(r->ev1, r->stream));
+    QB_CUDA(cudaEventSynchronize(r->ev1));
+    QB_CUDA(cudaEventElapsedTime(ms, r->ev0, r->ev1));
+    return QB_OK;
+}
+
+int qb_set_option(qb_reg* reg, int32_t option, int64_t value) {
+    CHECK_REG(reg);
+    Reg* r = REG(reg);
+    QB_TRY(flush(r));
+    switch (option) {
+        case QB_OPT_FUSION: r->fusion = value != 0; return QB_OK;
+        case QB_OPT_TILE_BITS:
+            if (value < 8 || value > 13) return set_error(QB_ERR_INVALID_ARGUMENT, value, "tile bits must be in [8, 13]");
+            r->tile_bits = (uint32_t)value;
+            return QB_OK;
+        case QB_OPT_MAX_QUEUE:
+            if (value < 1) return set_error(QB_ERR_INVALID_ARGUMENT, value, "max queue must be >= 1");
+            r->max_queue = (uint64_t)value;
+            return QB_OK;
+        case QB_OPT_FORCE_PATH:
+            if (value < 0 || value > 3) return set_error(QB_ERR_INVALID_ARGUMENT, value, "force path must be in [0, 3]");
+            r->force_path = (int)value;
+            return QB_OK;
+    }
+    return set_error(QB_ERR_INVALID_ARGUMENT, option, "unknown option %d", option);
+}
+
+int qb_get_stat(qb_reg* reg, int32_t stat, int64_t* value) {
+    CHECK_REG(reg);
+    Reg* r = REG(reg);
+    if (!value) return set_error(QB_ERR_INVALID_ARGUMENT, -1, "value is NULL");
+    switch (stat) {
+        case QB_STAT_KERNEL_LAUNCHES: *value = r->st_launches; return QB_OK;
+        case QB_STAT_PASSES: *value = r->st_passes; return QB_OK;
+        case QB_STAT_GATES: *value = r->st_gates; return QB_OK;
+        case QB_STAT_BYTES_MOVED: *value = r->st_bytes; return QB_OK;
+        case QB_STAT_SWAP_BYTES: *value = r->st_swap_bytes; return QB_OK;
+        case QB_STAT_SWAPS: *value = r->st_swaps; return QB_OK;
+    }
+    return set_error(QB_ERR_INVALID_ARGUMENT, stat, "unknown stat %d", stat);
+}
+
+int64_t qb_plan_debug(uint32_t n, const qb_gate* gates, uint64_t count, uint32_t tile_bits, int32_t* pass_of_gate,
+                      int32_t* order_in_pass) {
+    if (count && (!gates || !pass_of_gate || !order_in_pass)) return set_error(QB_ERR_INVALID_ARGUMENT, -1, "NULL argument");
+    std::vector<Gate> gs;
+    std::vector<int64_t> src;
+    for (uint64_t i = 0; i < count; ++i) {
+        int rc = validate_targets(n, gates[i].targets, gates[i].k);
+        if (rc != QB_OK) return rc;
+        pass_of_gate[i] = -1;
+        order_in_pass[i] = -1;
+        Gate g;
+        if (!classify_gate(gates[i].matrix, gates[i].targets, gates[i].k, &g)) continue;
+        g.tag = (int64_t)i;
+        gs.push_back(std::move(g));
+    }
+    return plan_debug(n, gs, tile_bits, pass_of_gate, order_in_pass);
+}
+
+}  // extern "C"

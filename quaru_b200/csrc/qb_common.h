@@ -1,0 +1,112 @@
+// qb_common.h -- internal types shared by the engine's translation units.
+//
+// The engine replaces the state engine of the reference (src/register.rs): the state vector
+// lives in HBM as 2^n double2 (= num::Complex<f64>) and every Register method becomes one or
+// more sm_100a kernels.  Nothing here is visible through the C ABI (include/quaru_b200.h).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/quaru_b200.h"
+
+namespace qb {
+
+typedef double2 c64;  // {x = re, y = im}; layout-identical to num::Complex<f64>
+
+// ---- thread-local error record (qb_last_error / qb_last_error_payload) -----------------------
+int set_error(int code, int64_t payload, const char* fmt, ...);
+int fail_cuda(cudaError_t e, const char* what, const char* file, int line);
+
+#define QB_CUDA(expr)                                                               \
+    do {                                                                            \
+        cudaError_t _e = (expr);                                                    \
+        if (_e != cudaSuccess) return qb::fail_cuda(_e, #expr, __FILE__, __LINE__); \
+    } while (0)
+
+#define QB_TRY(expr)                  \
+    do {                              \
+        int _rc = (expr);             \
+        if (_rc != QB_OK) return _rc; \
+    } while (0)
+
+// ---- gate model --------------------------------------------------------------------------------
+// Structure the planner detects in the dense matrix an `Operation` carries (operation.rs:49-52).
+enum GateKind : uint8_t {
+    GK_DENSE = 0,  // general 2^k x 2^k block on `targets`, applied where all ctrl_mask bits are 1
+    GK_DIAG = 1,   // diagonal on `targets` (RZ, phase, CZ, cnz, Grover oracle/diffuser, QFT phases)
+};
+
+struct Gate {
+    uint32_t k = 0;                 // arity after control extraction (may be 0 for a pure masked phase)
+    std::vector<uint32_t> targets;  // PHYSICAL bit positions; matrix bit j <-> targets[j]
+    std::vector<c64> matrix;        // GK_DENSE: 2^k x 2^k row-major; GK_DIAG: 2^k diagonal entries
+    uint64_t ctrl_mask = 0;         // bits that must all be 1 for the gate to act (extracted controls)
+    GateKind kind = GK_DENSE;
+    int64_t tag = -1;               // caller's index of the gate (planner introspection)
+    uint64_t target_mask() const {
+        uint64_t m = 0;
+        for (uint32_t t : targets) m |= 1ull << t;
+        return m;
+    }
+    uint64_t qubit_mask() const { return target_mask() | ctrl_mask; }
+};
+
+// Analyse a raw (matrix, targets) payload (already validated): pull out control qubits (bits on
+// which the matrix is the identity whenever the bit is 0), detect diagonal structure.
+// Returns false if the gate is exactly the identity (nothing to do).
+bool classify_gate(const double* matrix, const uint32_t* targets, uint32_t k, Gate* out);
+
+// ---- the handle ----------------------------------------------------------------------------------
+struct Shard;  // multi-GPU state (qb_shard.cu)
+
+struct Reg {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    uint32_t n = 0;        // logical qubits
+    uint32_t n_local = 0;  // index bits held by this rank (== n on one GPU)
+    c64* state = nullptr;  // 2^n_local amplitudes
+    c64* scratch = nullptr;  // lazily allocated second buffer (out-of-place generic path only)
+    double2* partials = nullptr;  // reduction workspace
+    size_t partials_len = 0;
+    c64* dmat = nullptr;  // device arena for large matrices / diagonals / offset tables
+    size_t dmat_bytes = 0;
+    void* hpin = nullptr;  // pinned host staging for pass programs
+    size_t hpin_bytes = 0;
+    void* dprog = nullptr;  // device copy of the pass program
+    cudaEvent_t prog_free = nullptr;  // recorded after the last kernel that reads dprog/hpin
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<Gate> queue;  // gates accepted but not yet launched
+    // options
+    int fusion = 1;
+    uint32_t tile_bits = 12;
+    uint64_t max_queue = 4096;
+    int force_path = 0;
+    // stats
+    int64_t st_launches = 0, st_passes = 0, st_gates = 0, st_bytes = 0, st_swap_bytes = 0, st_swaps = 0;
+    // sharding
+    int rank = 0, world = 1;
+    Shard* shard = nullptr;
+    std::vector<uint32_t> phys_of;  // logical qubit -> physical bit position
+};
+
+// ---- kernels' host launchers (qb_kernels.cu) -------------------------------------------------------
+int k_init_basis(Reg* r, uint64_t local_index, bool owned);
+int k_init_product(Reg* r, const double* qubits_host);
+int k_apply_gate_unfused(Reg* r, const Gate& g);  // one gate = at most one sweep over the shard
+int k_probabilities(Reg* r, int target_phys /* -1: everything into p0 */, double* p0, double* p1);
+int k_collapse(Reg* r, uint32_t target_phys, int outcome, double total_prob);
+int k_scale_or_zero_all(Reg* r, bool keep, double total_prob);  // measured qubit is a rank bit
+int k_diff(Reg* a, Reg* b, double* max_abs, double* l2sq);
+int ensure_dmat(Reg* r, size_t bytes);
+
+// ---- fused tile passes (qb_tile.cu) ----------------------------------------------------------------
+int run_fused(Reg* r, std::vector<Gate>& gates);  // plan + launch; consumes `gates`
+int run_local(Reg* r, std::vector<Gate>& gates);  // fused or unfused according to r->fusion (qb_api.cu)
+int64_t plan_debug(uint32_t n, std::vector<Gate>& gates, uint32_t tile_bits, int32_t* pass_of_gate,
+                   int32_t* order_in_pass);
+
+}  // namespace qb

@@ -1,0 +1,21 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def engine():
+    """The CUDA engine; building it is part of __graft_entry__.build()."""
+    import __graft_entry__ as ge
+    ge.build(verbose=False)
+    import quaru_b200
+    return quaru_b200
