@@ -1,13 +1,336 @@
-// qb_tile.cu -- fused tile passes (placeholder: one kernel per gate until the tile kernel lands).
+// qb_tile.cu -- fused tile passes: many gates per HBM sweep.
+//
+// The reference applies one gate per full traversal of the state (src/register.rs:160-188, plus a
+// clone at :155).  Here queued gates are planned into PASSES.  A pass picks a set of T index bits
+// (the low `lc` bits, contiguous in memory, plus up to T-5 arbitrary high bits); every CTA stages
+// one 2^T-amplitude tile of the state in shared memory (coalesced >= 512-byte segments), applies
+// every gate of the pass whose dense target bits lie inside the tile, and writes the tile back:
+// one read and one write of the state for the whole group of gates.
+//   * control qubits never have to be in the tile: a control on a non-tile bit is a per-tile
+//     predicate on the tile's base address;
+//   * diagonal gates never constrain the tile either: their non-tile bits select a sub-table.
+// The pass program travels in kernel-parameter (constant-bank) space, so there is no device
+// allocation or copy per pass.
+#include <string.h>
+
+#include <algorithm>
+
 #include "qb_common.h"
+#include "qb_device.cuh"
+
 namespace qb {
-int run_fused(Reg* r, std::vector<Gate>& gates) {
-    for (const Gate& g : gates) QB_TRY(k_apply_gate_unfused(r, g));
+
+// ------------------------------------------------------------------------------------------------
+// device-side program
+// ------------------------------------------------------------------------------------------------
+enum TileOpType : uint8_t { TOP_DENSE1 = 0, TOP_DENSE2 = 1, TOP_DIAG = 2 };
+
+struct TileOp {
+    uint8_t type;
+    uint8_t k;         // DIAG: number of index bits (<= 3)
+    uint8_t b[3];      // DENSE: local bit of matrix bit j; DIAG: local bit, or 0x80 | global position (outer bit)
+    uint8_t pad[3];
+    uint32_t lctrl;    // controls inside the tile (local bit mask)
+    uint32_t mat;      // offset of the matrix / diagonal in `mats` (c64 units)
+    uint64_t octrl;    // controls outside the tile (global bit mask, tested against the tile base)
+};
+static_assert(sizeof(TileOp) == 24, "TileOp layout");
+
+template <int NOPS, int NMAT>
+struct PassProgram {
+    uint32_t tile_bits;  // T' = min(T, n_local)
+    uint32_t lc;         // contiguous low bits
+    uint32_t h;          // high tile bits (T' = lc + h)
+    uint32_t n_ops;
+    uint8_t hp[8];       // ascending global positions of the high tile bits
+    TileOp ops[NOPS];
+    c64 mats[NMAT];
+};
+typedef PassProgram<16, 112> PassSmall;    // <= 4 KB of parameter space
+typedef PassProgram<160, 1280> PassLarge;  // ~24 KB (CUDA >= 12.1 allows 32,764 bytes)
+
+constexpr int TILE_THREADS = 256;
+
+// ------------------------------------------------------------------------------------------------
+// K2: the tile-pass kernel
+// ------------------------------------------------------------------------------------------------
+template <class Prog>
+__global__ void __launch_bounds__(TILE_THREADS) k2_tile_pass(c64* __restrict__ st, const __grid_constant__ Prog prog) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    c64* tile = reinterpret_cast<c64*>(smem_raw);
+    __shared__ uint64_t seg_off[128];
+
+    const uint32_t T = prog.tile_bits, lc = prog.lc, h = prog.h;
+    const uint32_t tile_n = 1u << T;
+    const uint32_t tid = threadIdx.x;
+
+    // base address of this tile: deposit blockIdx into the non-tile bit positions
+    uint64_t base = (uint64_t)blockIdx.x << lc;
+    for (uint32_t j = 0; j < h; ++j) base = insert_zero_bit(base, prog.hp[j]);
+    if (tid < (1u << h)) {
+        uint64_t o = 0;
+        for (uint32_t j = 0; j < h; ++j) o |= (uint64_t)((tid >> j) & 1) << prog.hp[j];
+        seg_off[tid] = o;
+    }
+    __syncthreads();
+    const uint32_t lmask = (1u << lc) - 1;
+
+    // ---- stage the tile: consecutive threads read consecutive amplitudes (>= 512 B per warp) ----
+#pragma unroll 8
+    for (uint32_t l = tid; l < tile_n; l += TILE_THREADS)
+        tile[l] = ld128(st + (base + (l & lmask) + seg_off[l >> lc]));
+    __syncthreads();
+
+    // ---- apply the pass program in shared memory ---------------------------------------------
+    for (uint32_t oi = 0; oi < prog.n_ops; ++oi) {
+        const TileOp& op = prog.ops[oi];
+        if ((base & op.octrl) != op.octrl) continue;  // uniform per CTA
+        const uint32_t lctrl = op.lctrl;
+        if (op.type == TOP_DENSE1) {
+            const uint32_t b = op.b[0];
+            const c64 m00 = prog.mats[op.mat + 0], m01 = prog.mats[op.mat + 1];
+            const c64 m10 = prog.mats[op.mat + 2], m11 = prog.mats[op.mat + 3];
+#pragma unroll 4
+            for (uint32_t p = tid; p < (tile_n >> 1); p += TILE_THREADS) {
+                const uint32_t l0 = (uint32_t)insert_zero_bit(p, b);
+                if ((l0 & lctrl) != lctrl) continue;
+                const uint32_t l1 = l0 | (1u << b);
+                const c64 a0 = tile[l0], a1 = tile[l1];
+                tile[l0] = cmul2(m00, a0, m01, a1);
+                tile[l1] = cmul2(m10, a0, m11, a1);
+            }
+        } else if (op.type == TOP_DENSE2) {
+            const uint32_t b0 = op.b[0], b1 = op.b[1];
+            const uint32_t lo = b0 < b1 ? b0 : b1, hi = b0 < b1 ? b1 : b0;
+            const c64* M = prog.mats + op.mat;
+            for (uint32_t p = tid; p < (tile_n >> 2); p += TILE_THREADS) {
+                const uint32_t l00 = (uint32_t)insert_zero_bit(insert_zero_bit(p, lo), hi);
+                if ((l00 & lctrl) != lctrl) continue;
+                const uint32_t i1 = l00 | (1u << b0), i2 = l00 | (1u << b1), i3 = i1 | (1u << b1);
+                const c64 a0 = tile[l00], a1 = tile[i1], a2 = tile[i2], a3 = tile[i3];
+                c64 r0 = cmul2(M[0], a0, M[1], a1);   r0 = cfma(M[2], a2, r0);   r0 = cfma(M[3], a3, r0);
+                c64 r1 = cmul2(M[4], a0, M[5], a1);   r1 = cfma(M[6], a2, r1);   r1 = cfma(M[7], a3, r1);
+                c64 r2 = cmul2(M[8], a0, M[9], a1);   r2 = cfma(M[10], a2, r2);  r2 = cfma(M[11], a3, r2);
+                c64 r3 = cmul2(M[12], a0, M[13], a1); r3 = cfma(M[14], a2, r3);  r3 = cfma(M[15], a3, r3);
+                tile[l00] = r0; tile[i1] = r1; tile[i2] = r2; tile[i3] = r3;
+            }
+        } else {  // TOP_DIAG, k <= 3 index bits, each local or outer
+            uint32_t oidx = 0;
+            uint32_t lb[3] = {0, 0, 0};
+            uint32_t lsel = 0;  // which matrix bits are local
+            for (uint32_t j = 0; j < op.k; ++j) {
+                const uint32_t bj = op.b[j];
+                if (bj & 0x80) oidx |= (uint32_t)((base >> (bj & 0x7f)) & 1) << j;
+                else { lb[j] = bj; lsel |= 1u << j; }
+            }
+            const c64* D = prog.mats + op.mat;
+            // the (at most 8) factors this tile can see, resolved to registers (uniform loads)
+            c64 f[8];
+#pragma unroll
+            for (uint32_t x = 0; x < 8; ++x) f[x] = D[(oidx | (x & lsel)) & ((1u << op.k) - 1)];
+#pragma unroll 4
+            for (uint32_t l = tid; l < tile_n; l += TILE_THREADS) {
+                if ((l & lctrl) != lctrl) continue;
+                const uint32_t x = (((l >> lb[0]) & 1) | (((l >> lb[1]) & 1) << 1) | (((l >> lb[2]) & 1) << 2)) & lsel;
+                const c64 lo4 = (x & 2) ? ((x & 1) ? f[3] : f[2]) : ((x & 1) ? f[1] : f[0]);
+                const c64 hi4 = (x & 2) ? ((x & 1) ? f[7] : f[6]) : ((x & 1) ? f[5] : f[4]);
+                tile[l] = cmul((x & 4) ? hi4 : lo4, tile[l]);
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- write the tile back ---------------------------------------------------------------------
+#pragma unroll 8
+    for (uint32_t l = tid; l < tile_n; l += TILE_THREADS)
+        st128(st + (base + (l & lmask) + seg_off[l >> lc]), tile[l]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// planner
+// ------------------------------------------------------------------------------------------------
+struct PlannedPass {
+    std::vector<uint32_t> tile_pos;  // ascending global positions of the tile bits
+    uint32_t lc = 0;
+    std::vector<size_t> gate_idx;    // indices into the gate list, in execution order
+    bool unfused = false;            // a single gate the tile kernel cannot take
+};
+
+constexpr uint32_t MIN_LC = 5;       // >= 512-byte contiguous segments
+constexpr uint32_t MAX_DIAG_K = 3;
+
+static bool tile_supported(const Gate& g) {
+    if (g.kind == GK_DIAG) return g.k <= MAX_DIAG_K;
+    return g.k >= 1 && g.k <= 2;
+}
+
+// Greedy list scheduling.  Gates are scanned in program order; a gate joins the current pass if no
+// earlier unscheduled gate shares a qubit with it (so program order is preserved per qubit) and its
+// dense target bits fit the tile; otherwise its qubits become blocked for the rest of this pass.
+static void plan_passes(const std::vector<Gate>& gates, uint32_t n_local, uint32_t T_opt, int max_ops, int max_mats,
+                        std::vector<PlannedPass>* out) {
+    const uint32_t T = std::min(T_opt, n_local);
+    const uint32_t lc_min = std::min(MIN_LC, T);
+    const uint32_t h_max = std::min<uint32_t>(T - lc_min, 7);
+    std::vector<char> done(gates.size(), 0);
+    size_t first = 0, remaining = gates.size();
+    while (remaining) {
+        while (done[first]) ++first;
+        PlannedPass pass;
+        uint64_t high = 0;  // chosen high tile bits (positions >= lc_min)
+        uint32_t nh = 0;
+        uint64_t blocked = 0;
+        int n_ops = 0, n_mats = 0;
+        for (size_t i = first; i < gates.size(); ++i) {
+            if (done[i]) continue;
+            const Gate& g = gates[i];
+            const uint64_t qm = g.qubit_mask();
+            if (qm & blocked) { blocked |= qm; continue; }
+            bool ok = tile_supported(g);
+            uint64_t need = 0;
+            if (ok && g.kind == GK_DENSE) {
+                for (uint32_t t : g.targets)
+                    if (t >= lc_min && !((high >> t) & 1)) need |= 1ull << t;
+                if (nh + (uint32_t)__builtin_popcountll(need) > h_max) ok = false;
+            }
+            const int mats = (int)g.matrix.size();
+            if (ok && (n_ops + 1 > max_ops || n_mats + mats > max_mats)) ok = false;
+            if (!ok) { blocked |= qm; continue; }
+            high |= need;
+            nh += (uint32_t)__builtin_popcountll(need);
+            n_ops++;
+            n_mats += mats;
+            pass.gate_idx.push_back(i);
+            done[i] = 1;
+            --remaining;
+        }
+        if (pass.gate_idx.empty()) {  // the first remaining gate cannot go through the tile kernel
+            pass.unfused = true;
+            pass.gate_idx.push_back(first);
+            done[first] = 1;
+            --remaining;
+            out->push_back(std::move(pass));
+            continue;
+        }
+        // tile = lowest lc bits + the chosen high bits that are not already among them
+        uint32_t lc = T - nh;
+        for (;;) {
+            uint32_t above = 0;
+            for (uint32_t b = lc; b < 64; ++b) above += (uint32_t)((high >> b) & 1);
+            if (lc + above == T) break;
+            lc = T - above;
+        }
+        pass.lc = lc;
+        for (uint32_t b = 0; b < lc; ++b) pass.tile_pos.push_back(b);
+        for (uint32_t b = lc; b < 64; ++b)
+            if ((high >> b) & 1) pass.tile_pos.push_back(b);
+        out->push_back(std::move(pass));
+    }
+}
+
+template <class Prog>
+static bool encode_pass(const std::vector<Gate>& gates, const PlannedPass& pass, Prog* prog) {
+    const uint32_t T = (uint32_t)pass.tile_pos.size();
+    prog->tile_bits = T;
+    prog->lc = pass.lc;
+    prog->h = T - pass.lc;
+    for (uint32_t j = 0; j < prog->h; ++j) prog->hp[j] = (uint8_t)pass.tile_pos[pass.lc + j];
+    int8_t local_of[64];
+    uint64_t tile_mask = 0;
+    for (int b = 0; b < 64; ++b) local_of[b] = -1;
+    for (uint32_t j = 0; j < T; ++j) { local_of[pass.tile_pos[j]] = (int8_t)j; tile_mask |= 1ull << pass.tile_pos[j]; }
+    uint32_t n_ops = 0, n_mats = 0;
+    for (size_t gi : pass.gate_idx) {
+        const Gate& g = gates[gi];
+        TileOp op;
+        memset(&op, 0, sizeof(op));
+        op.k = (uint8_t)g.k;
+        op.mat = n_mats;
+        op.octrl = g.ctrl_mask & ~tile_mask;
+        uint32_t lctrl = 0;
+        for (uint64_t m = g.ctrl_mask & tile_mask; m; m &= m - 1) lctrl |= 1u << local_of[__builtin_ctzll(m)];
+        op.lctrl = lctrl;
+        if (g.kind == GK_DIAG) {
+            op.type = TOP_DIAG;
+            for (uint32_t j = 0; j < g.k; ++j) {
+                const uint32_t t = g.targets[j];
+                op.b[j] = local_of[t] >= 0 ? (uint8_t)local_of[t] : (uint8_t)(0x80 | t);
+            }
+        } else {
+            op.type = g.k == 1 ? TOP_DENSE1 : TOP_DENSE2;
+            for (uint32_t j = 0; j < g.k; ++j) {
+                if (local_of[g.targets[j]] < 0) return false;  // planner bug guard
+                op.b[j] = (uint8_t)local_of[g.targets[j]];
+            }
+        }
+        if (n_ops >= sizeof(prog->ops) / sizeof(TileOp) || n_mats + g.matrix.size() > sizeof(prog->mats) / sizeof(c64))
+            return false;
+        memcpy(prog->mats + n_mats, g.matrix.data(), g.matrix.size() * sizeof(c64));
+        n_mats += (uint32_t)g.matrix.size();
+        prog->ops[n_ops++] = op;
+    }
+    prog->n_ops = n_ops;
+    return true;
+}
+
+template <class Prog>
+static int launch_pass(Reg* r, const Prog& prog) {
+    const size_t smem = sizeof(c64) << prog.tile_bits;
+    static bool attr_set = false;
+    if (!attr_set) {
+        QB_CUDA(cudaFuncSetAttribute(k2_tile_pass<Prog>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 << 13));
+        attr_set = true;
+    }
+    const uint64_t tiles = 1ull << (r->n_local - prog.tile_bits);
+    if (tiles > 0x7fffffffull) return set_error(QB_ERR_UNSUPPORTED, (int64_t)tiles, "too many tiles for one grid");
+    k2_tile_pass<Prog><<<(unsigned)tiles, TILE_THREADS, smem, r->stream>>>(r->state, prog);
+    QB_CUDA(cudaGetLastError());
+    r->st_launches++;
+    r->st_passes++;
+    r->st_bytes += (int64_t)(32ull << r->n_local);
     return QB_OK;
 }
-int64_t plan_debug(uint32_t, std::vector<Gate>& gates, uint32_t, int32_t* pass_of_gate, int32_t* order_in_pass) {
-    int64_t p = 0;
-    for (const Gate& g : gates) { pass_of_gate[g.tag] = (int32_t)p++; order_in_pass[g.tag] = 0; }
-    return p;
+
+int run_fused(Reg* r, std::vector<Gate>& gates) {
+    std::vector<PlannedPass> passes;
+    const int max_ops = (int)(sizeof(PassLarge::ops) / sizeof(TileOp));
+    const int max_mats = (int)(sizeof(PassLarge::mats) / sizeof(c64));
+    plan_passes(gates, r->n_local, r->tile_bits, max_ops, max_mats, &passes);
+    static PassLarge large;  // host staging (single-threaded per handle; copied by value at launch)
+    for (const PlannedPass& p : passes) {
+        if (p.unfused) {
+            QB_TRY(k_apply_gate_unfused(r, gates[p.gate_idx[0]]));
+            continue;
+        }
+        // a pass with a single gate is cheaper through the streaming kernels (they skip untouched halves)
+        if (p.gate_idx.size() == 1 && r->force_path != 2) {
+            const Gate& g = gates[p.gate_idx[0]];
+            if (g.kind == GK_DIAG || g.k == 1) { QB_TRY(k_apply_gate_unfused(r, g)); continue; }
+        }
+        size_t mats = 0;
+        for (size_t gi : p.gate_idx) mats += gates[gi].matrix.size();
+        if (p.gate_idx.size() <= sizeof(PassSmall::ops) / sizeof(TileOp) && mats <= sizeof(PassSmall::mats) / sizeof(c64)) {
+            PassSmall small;
+            if (!encode_pass(gates, p, &small)) return set_error(QB_ERR_UNSUPPORTED, -1, "internal: pass encoding failed");
+            QB_TRY(launch_pass(r, small));
+        } else {
+            if (!encode_pass(gates, p, &large)) return set_error(QB_ERR_UNSUPPORTED, -1, "internal: pass encoding failed");
+            QB_TRY(launch_pass(r, large));
+        }
+    }
+    return QB_OK;
 }
+
+int64_t plan_debug(uint32_t n, std::vector<Gate>& gates, uint32_t tile_bits, int32_t* pass_of_gate, int32_t* order_in_pass) {
+    std::vector<PlannedPass> passes;
+    plan_passes(gates, n, tile_bits, (int)(sizeof(PassLarge::ops) / sizeof(TileOp)),
+                (int)(sizeof(PassLarge::mats) / sizeof(c64)), &passes);
+    for (size_t p = 0; p < passes.size(); ++p)
+        for (size_t o = 0; o < passes[p].gate_idx.size(); ++o) {
+            const Gate& g = gates[passes[p].gate_idx[o]];
+            if (g.tag >= 0) { pass_of_gate[g.tag] = (int32_t)p; order_in_pass[g.tag] = (int32_t)o; }
+        }
+    return (int64_t)passes.size();
+}
+
 }  // namespace qb

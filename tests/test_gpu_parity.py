@@ -221,10 +221,11 @@ def test_measure_outcomes_and_collapse(engine, n):
 
 
 def test_measure_deterministic_edges(engine):
-    """u > p0 is strict (register.rs:321): on |0> even u = 1-eps gives false; on |1> u = 0 gives true."""
+    """u > p0 is strict (register.rs:321): on |0> even u = 1-eps gives false; on |1> (p0 = 0) the smallest
+    positive u gives true."""
     reg = engine.Register.new([False, True])
     assert reg.measure(0, u=np.nextafter(1.0, 0.0)) is False
-    assert reg.measure(1, u=0.0) is True
+    assert reg.measure(1, u=5e-324) is True
     assert (reg.state == OracleRegister.new([False, True]).state).all()
 
 

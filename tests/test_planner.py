@@ -1,0 +1,83 @@
+"""CPU tests of the host-side planner through the C ABI (qb_plan_debug needs no GPU): the pass assignment must
+keep program order between any two gates that share a qubit, every gate must be scheduled exactly once, and
+fusion must actually reduce the number of passes on the BASELINE circuits."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from tests import circuits
+
+
+def _plan(n, ops, tile_bits=12):
+    from quaru_b200 import _ffi
+    L = _ffi.lib()
+    arr = (_ffi.QbGate * max(len(ops), 1))()
+    keep = []
+    for i, (m, t) in enumerate(ops):
+        mm = np.ascontiguousarray(m, dtype=np.complex128)
+        tt = (ctypes.c_uint32 * max(len(t), 1))(*t)
+        keep += [mm, tt]
+        arr[i].matrix = mm.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+        arr[i].targets = tt
+        arr[i].k = len(t)
+    pass_of = (ctypes.c_int32 * max(len(ops), 1))()
+    order = (ctypes.c_int32 * max(len(ops), 1))()
+    npass = L.qb_plan_debug(n, arr, len(ops), tile_bits, pass_of, order)
+    assert npass >= 0, _ffi.last_error()
+    return npass, list(pass_of)[:len(ops)], list(order)[:len(ops)]
+
+
+def _check_order(ops, pass_of, order):
+    last = {}
+    for i, (m, t) in enumerate(ops):
+        if pass_of[i] < 0:          # exact identity: dropped
+            assert np.array_equal(np.asarray(m), np.eye(len(m)))
+            continue
+        key = (pass_of[i], order[i])
+        for q in t:
+            if q in last:
+                assert last[q] < key, f"gate {i} on qubit {q} scheduled before an earlier gate"
+            last[q] = key
+    keys = [(p, o) for p, o in zip(pass_of, order) if p >= 0]
+    assert len(set(keys)) == len(keys), "two gates share a slot"
+
+
+@pytest.mark.parametrize("n,tile_bits", [(3, 12), (8, 8), (12, 9), (20, 12), (28, 12), (33, 12), (33, 13), (36, 11)])
+def test_plan_preserves_dependencies_random_layers(n, tile_bits):
+    ops = circuits.random_circuit(n, 5, seed=n)
+    npass, pass_of, order = _plan(n, ops, tile_bits)
+    _check_order(ops, pass_of, order)
+    if n >= 8:
+        assert npass < len(ops) / 2
+
+
+@pytest.mark.parametrize("n", [5, 12, 24, 33])
+def test_plan_qft(n):
+    ops = circuits.qft_circuit(n)
+    npass, pass_of, order = _plan(n, ops)
+    _check_order(ops, pass_of, order)
+    assert npass <= 2 * n      # the reference would sweep the state len(ops) ~ n^2/2 times
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_plan_mixed(seed):
+    n = 4 + 3 * seed
+    ops = circuits.mixed_circuit(n, 200, seed)
+    npass, pass_of, order = _plan(n, ops, 8 + seed % 5)
+    _check_order(ops, pass_of, order)
+
+
+def test_plan_rejects_invalid_targets():
+    from quaru_b200 import _ffi
+    with pytest.raises(AssertionError):
+        _plan(3, [(np.eye(4), [0, 3])])
+    assert _ffi.last_error()[1] == 3
+    with pytest.raises(AssertionError):
+        _plan(3, [(np.eye(4), [1, 1])])
+    assert _ffi.last_error()[1] == 1
+
+
+def test_identity_gates_are_dropped():
+    npass, pass_of, order = _plan(4, [(np.eye(2), [1]), (np.eye(4), [0, 2])])
+    assert npass == 0 and pass_of == [-1, -1]
