@@ -145,6 +145,7 @@ int qb_timer_stop(qb_reg* reg, float* ms);
 #define QB_OPT_TILE_BITS 2     /* log2 amplitudes per shared-memory tile (default 12) */
 #define QB_OPT_MAX_QUEUE 3     /* auto-flush after this many buffered gates (default 4096) */
 #define QB_OPT_FORCE_PATH 4    /* tests only: 0 auto, 1 generic kernel, 2 tile kernel, 3 streaming kernels */
+#define QB_OPT_PROFILE 5       /* 1: bracket every tile-pass launch with CUDA events (QB_STAT_TILE_NS) */
 int qb_set_option(qb_reg* reg, int32_t option, int64_t value);
 
 #define QB_STAT_KERNEL_LAUNCHES 1 /* kernels launched by this handle since creation */
@@ -153,6 +154,8 @@ int qb_set_option(qb_reg* reg, int32_t option, int64_t value);
 #define QB_STAT_BYTES_MOVED 4     /* physical HBM bytes the launched passes read+wrote (model) */
 #define QB_STAT_SWAP_BYTES 5      /* bytes this rank sent over NVLink in global<->local swaps */
 #define QB_STAT_SWAPS 6           /* number of global<->local exchanges */
+#define QB_STAT_TILE_LAUNCHES 7   /* tile-pass kernel launches (profiled ones when QB_OPT_PROFILE=1) */
+#define QB_STAT_TILE_NS 8         /* summed device time of the profiled tile-pass launches, ns */
 int qb_get_stat(qb_reg* reg, int32_t stat, int64_t* value);
 
 /* ---- planner introspection (host only, no GPU needed) ------------------------------------ */

@@ -17,9 +17,9 @@ QB_ERR_INVALID_QUBIT = -4
 QB_ERR_INVALID_ARGUMENT = -5
 QB_ERR_CUDA, QB_ERR_NCCL, QB_ERR_OOM, QB_ERR_NO_DEVICE, QB_ERR_UNSUPPORTED = 1, 2, 3, 4, 5
 
-QB_OPT_FUSION, QB_OPT_TILE_BITS, QB_OPT_MAX_QUEUE, QB_OPT_FORCE_PATH = 1, 2, 3, 4
+QB_OPT_FUSION, QB_OPT_TILE_BITS, QB_OPT_MAX_QUEUE, QB_OPT_FORCE_PATH, QB_OPT_PROFILE = 1, 2, 3, 4, 5
 (QB_STAT_KERNEL_LAUNCHES, QB_STAT_PASSES, QB_STAT_GATES, QB_STAT_BYTES_MOVED, QB_STAT_SWAP_BYTES,
- QB_STAT_SWAPS) = 1, 2, 3, 4, 5, 6
+ QB_STAT_SWAPS, QB_STAT_TILE_LAUNCHES, QB_STAT_TILE_NS) = 1, 2, 3, 4, 5, 6, 7, 8
 
 
 class QbGate(ctypes.Structure):

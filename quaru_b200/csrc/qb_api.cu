@@ -59,6 +59,7 @@ static void free_reg(Reg* r) {
     if (r->dmat) cudaFree(r->dmat);
     if (r->dprog) cudaFree(r->dprog);
     if (r->hpin) cudaFreeHost(r->hpin);
+    for (cudaEvent_t e : r->tile_events) cudaEventDestroy(e);
     if (r->ev0) cudaEventDestroy(r->ev0);
     if (r->ev1) cudaEventDestroy(r->ev1);
     if (r->prog_free) cudaEventDestroy(r->prog_free);
@@ -373,6 +374,7 @@ int qb_set_option(qb_reg* reg, int32_t option, int64_t value) {
             if (value < 1) return set_error(QB_ERR_INVALID_ARGUMENT, value, "max queue must be >= 1");
             r->max_queue = (uint64_t)value;
             return QB_OK;
+        case QB_OPT_PROFILE: r->profile = value != 0; return QB_OK;
         case QB_OPT_FORCE_PATH:
             if (value < 0 || value > 3) return set_error(QB_ERR_INVALID_ARGUMENT, value, "force path must be in [0, 3]");
             r->force_path = (int)value;
@@ -392,6 +394,8 @@ int qb_get_stat(qb_reg* reg, int32_t stat, int64_t* value) {
         case QB_STAT_BYTES_MOVED: *value = r->st_bytes; return QB_OK;
         case QB_STAT_SWAP_BYTES: *value = r->st_swap_bytes; return QB_OK;
         case QB_STAT_SWAPS: *value = r->st_swaps; return QB_OK;
+        case QB_STAT_TILE_LAUNCHES: QB_TRY(drain_tile_events(r)); *value = r->st_tile_launches; return QB_OK;
+        case QB_STAT_TILE_NS: QB_TRY(drain_tile_events(r)); *value = r->st_tile_ns; return QB_OK;
     }
     return set_error(QB_ERR_INVALID_ARGUMENT, stat, "unknown stat %d", stat);
 }

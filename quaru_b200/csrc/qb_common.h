@@ -85,8 +85,12 @@ struct Reg {
     uint32_t tile_bits = 12;
     uint64_t max_queue = 4096;
     int force_path = 0;
+    int profile = 0;
     // stats
     int64_t st_launches = 0, st_passes = 0, st_gates = 0, st_bytes = 0, st_swap_bytes = 0, st_swaps = 0;
+    int64_t st_tile_launches = 0, st_tile_ns = 0;
+    std::vector<cudaEvent_t> tile_events;  // start/stop pairs of profiled tile launches
+    size_t tile_events_used = 0;
     // sharding
     int rank = 0, world = 1;
     Shard* shard = nullptr;
@@ -104,6 +108,7 @@ int k_diff(Reg* a, Reg* b, double* max_abs, double* l2sq);
 int ensure_dmat(Reg* r, size_t bytes);
 
 // ---- fused tile passes (qb_tile.cu) ----------------------------------------------------------------
+int drain_tile_events(Reg* r);  // fold finished profiling events into st_tile_ns
 int run_fused(Reg* r, std::vector<Gate>& gates);  // plan + launch; consumes `gates`
 int run_local(Reg* r, std::vector<Gate>& gates);  // fused or unfused according to r->fusion (qb_api.cu)
 int64_t plan_debug(uint32_t n, std::vector<Gate>& gates, uint32_t tile_bits, int32_t* pass_of_gate,

@@ -283,11 +283,37 @@ static int launch_pass(Reg* r, const Prog& prog) {
     }
     const uint64_t tiles = 1ull << (r->n_local - prog.tile_bits);
     if (tiles > 0x7fffffffull) return set_error(QB_ERR_UNSUPPORTED, (int64_t)tiles, "too many tiles for one grid");
+    if (r->profile) {
+        if (r->tile_events_used + 2 > 1024) QB_TRY(drain_tile_events(r));
+        while (r->tile_events.size() < r->tile_events_used + 2) {
+            cudaEvent_t e;
+            QB_CUDA(cudaEventCreate(&e));
+            r->tile_events.push_back(e);
+        }
+        QB_CUDA(cudaEventRecord(r->tile_events[r->tile_events_used], r->stream));
+    }
     k2_tile_pass<Prog><<<(unsigned)tiles, TILE_THREADS, smem, r->stream>>>(r->state, prog);
     QB_CUDA(cudaGetLastError());
+    if (r->profile) {
+        QB_CUDA(cudaEventRecord(r->tile_events[r->tile_events_used + 1], r->stream));
+        r->tile_events_used += 2;
+        r->st_tile_launches++;
+    }
     r->st_launches++;
     r->st_passes++;
     r->st_bytes += (int64_t)(32ull << r->n_local);
+    return QB_OK;
+}
+
+int drain_tile_events(Reg* r) {
+    if (!r->tile_events_used) return QB_OK;
+    QB_CUDA(cudaEventSynchronize(r->tile_events[r->tile_events_used - 1]));
+    for (size_t i = 0; i + 1 < r->tile_events_used; i += 2) {
+        float ms = 0.f;
+        QB_CUDA(cudaEventElapsedTime(&ms, r->tile_events[i], r->tile_events[i + 1]));
+        r->st_tile_ns += (int64_t)(ms * 1e6);
+    }
+    r->tile_events_used = 0;
     return QB_OK;
 }
 
