@@ -166,6 +166,14 @@ int qb_get_stat(qb_reg* reg, int32_t stat, int64_t* value);
 int64_t qb_plan_debug(uint32_t n, const qb_gate* gates, uint64_t count, uint32_t tile_bits,
                       int32_t* pass_of_gate, int32_t* order_in_pass);
 
+/* Dry run of the multi-GPU placement logic: the global<->local exchanges rank `rank` of `world` would
+ * perform for this gate list, as a flat int32 list of records [gate index before which the exchange
+ * happens, g', V[0..g') local bit positions, J[0..g') rank-bit indices], and the final logical->physical
+ * placement.  Returns the number of int32 written or a negative error.  Every rank must produce the same
+ * list (tests/test_dist_cpu.py checks this over gloo). */
+int64_t qb_shard_plan_debug(uint32_t n, int32_t world, int32_t rank, const qb_gate* gates, uint64_t count,
+                            int32_t* events, uint64_t capacity, uint32_t* final_phys_of);
+
 const char* qb_version(void);
 
 #ifdef __cplusplus

@@ -67,6 +67,8 @@ SIGNATURES = {
     "qb_timer_stop": (ctypes.c_int, [_reg, ctypes.POINTER(ctypes.c_float)]),
     "qb_set_option": (ctypes.c_int, [_reg, ctypes.c_int32, ctypes.c_int64]),
     "qb_get_stat": (ctypes.c_int, [_reg, ctypes.c_int32, _i64p]),
+    "qb_shard_plan_debug": (ctypes.c_int64, [ctypes.c_uint32, ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(QbGate),
+                                             ctypes.c_uint64, _i32p, ctypes.c_uint64, _u32p]),
     "qb_plan_debug": (ctypes.c_int64, [ctypes.c_uint32, ctypes.POINTER(QbGate), ctypes.c_uint64, ctypes.c_uint32,
                                        _i32p, _i32p]),
 }

@@ -136,6 +136,23 @@ extern "C" {
 
 const char* qb_last_error(void) { return qb::last_error_str(); }
 int64_t qb_last_error_payload(void) { return qb::last_error_payload(); }
+int64_t qb_shard_plan_debug(uint32_t n, int32_t world, int32_t rank, const qb_gate* gates, uint64_t count, int32_t* events,
+                            uint64_t capacity, uint32_t* final_phys_of) {
+    if ((count && !gates) || (capacity && !events)) return set_error(QB_ERR_INVALID_ARGUMENT, -1, "NULL argument");
+    if (world < 1 || (world & (world - 1)) || rank < 0 || rank >= world)
+        return set_error(QB_ERR_INVALID_ARGUMENT, world, "world must be a power of two and 0 <= rank < world");
+    std::vector<Gate> gs;
+    for (uint64_t i = 0; i < count; ++i) {
+        int rc = validate_targets(n, gates[i].targets, gates[i].k);
+        if (rc != QB_OK) return rc;
+        Gate g;
+        if (!classify_gate(gates[i].matrix, gates[i].targets, gates[i].k, &g)) continue;
+        g.tag = (int64_t)i;
+        gs.push_back(std::move(g));
+    }
+    return shard_plan_debug(n, world, rank, gs, events, capacity, final_phys_of);
+}
+
 const char* qb_version(void) { return "quaru_b200 0.1 (sm_100a)"; }
 
 int qb_create(uint32_t n, uint64_t basis_index, qb_reg** out) { return create_impl(n, basis_index, 0, 1, nullptr, out); }

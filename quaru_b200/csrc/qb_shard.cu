@@ -1,12 +1,504 @@
-// qb_shard.cu -- placeholder until the NCCL exchange lands (single-GPU build).
+// qb_shard.cu -- one register sharded over the P = 2^g GPUs of one NVLink/NVSwitch box.
+//
+// No reference equivalent: Quaru is single-process.  Rank r holds the amplitudes
+// whose top g PHYSICAL index bits equal r; a logical->physical qubit placement (Reg::phys_of)
+// decides which logical qubits are currently "global" (rank bits).
+//   * gates whose dense targets are all local run through the single-GPU kernels, no communication;
+//   * controls and diagonal gates on global qubits need no exchange either: the rank's bits are
+//     constants (rank predicate / sub-table of the diagonal);
+//   * a dense target on a global qubit triggers ONE global<->local exchange that swaps every global
+//     qubit that is needed sooner than the local qubit it is traded against (look-ahead over the queued
+//     gates), done as pairwise ncclSend/ncclRecv of contiguous runs through a staging buffer carved
+//     from spare HBM;
+//   * measurement: per-rank (p0, p1) -> ncclAllGather -> the same adjacent-pair tree on every rank.
+// NCCL is bound at run time (dlopen of libnccl.so.2: the copy torch already loaded, else the system's),
+// so a single-GPU process never needs it.
+#include <dlfcn.h>
+#include <math.h>
+#include <nccl.h>
+#include <string.h>
+
+#include <algorithm>
+
 #include "qb_shard.h"
+
 namespace qb {
-int shard_unique_id(void*) { return set_error(QB_ERR_UNSUPPORTED, -1, "sharding not built yet"); }
-int shard_init(Reg*, const void*) { return set_error(QB_ERR_UNSUPPORTED, -1, "sharding not built yet"); }
-void shard_destroy(Reg*) {}
-int shard_run(Reg*, std::vector<Gate>&) { return set_error(QB_ERR_UNSUPPORTED, -1, "sharding not built yet"); }
-int shard_probabilities(Reg*, uint32_t, double*, double*) { return set_error(QB_ERR_UNSUPPORTED, -1, "sharding not built yet"); }
-int shard_collapse(Reg*, uint32_t, int, double) { return set_error(QB_ERR_UNSUPPORTED, -1, "sharding not built yet"); }
-int shard_canonicalize(Reg*) { return QB_OK; }
-int shard_reduce_diff(Reg*, double*, double*) { return QB_OK; }
+
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+static NcclApi g_nccl;
+
+static int load_nccl() {
+    if (g_nccl.handle) return QB_OK;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return set_error(QB_ERR_NCCL, -1, "cannot load libnccl.so.2: %s", dlerror());
+#define QB_SYM(field, name)                                                                       \
+    *(void**)(&g_nccl.field) = dlsym(h, name);                                                    \
+    if (!g_nccl.field) return set_error(QB_ERR_NCCL, -1, "libnccl.so.2 lacks symbol %s", name)
+    QB_SYM(GetUniqueId, "ncclGetUniqueId");
+    QB_SYM(CommInitRank, "ncclCommInitRank");
+    QB_SYM(CommDestroy, "ncclCommDestroy");
+    QB_SYM(Send, "ncclSend");
+    QB_SYM(Recv, "ncclRecv");
+    QB_SYM(AllGather, "ncclAllGather");
+    QB_SYM(GroupStart, "ncclGroupStart");
+    QB_SYM(GroupEnd, "ncclGroupEnd");
+    QB_SYM(GetErrorString, "ncclGetErrorString");
+#undef QB_SYM
+    g_nccl.handle = h;
+    return QB_OK;
+}
+
+#define QB_NCCL(expr)                                                                                     \
+    do {                                                                                                  \
+        ncclResult_t _r = (expr);                                                                         \
+        if (_r != ncclSuccess)                                                                            \
+            return set_error(QB_ERR_NCCL, (int64_t)_r, "NCCL error %d (%s) in %s", (int)_r,               \
+                             g_nccl.GetErrorString ? g_nccl.GetErrorString(_r) : "?", #expr);             \
+    } while (0)
+
+struct Shard {
+    ncclComm_t comm = nullptr;
+    uint32_t g = 0;               // log2(world)
+    c64* staging = nullptr;       // receive staging for exchanges
+    uint64_t staging_amps = 0;
+    double* d_gather = nullptr;   // 2 + 2*world doubles
+    std::vector<uint32_t> logical_at;  // physical position -> logical qubit
+    bool dry = false;                  // planner introspection: record exchanges, move no data
+    std::vector<int32_t> events;       // dry run: [gate index, g', V..., J...] per exchange
+    int64_t cur_gate = -1;
+};
+
+int shard_unique_id(void* out128) {
+    if (!out128) return set_error(QB_ERR_INVALID_ARGUMENT, -1, "out128 is NULL");
+    QB_TRY(load_nccl());
+    ncclUniqueId id;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    QB_NCCL(g_nccl.GetUniqueId(&id));
+    memcpy(out128, &id, 128);
+    return QB_OK;
+}
+
+int shard_init(Reg* r, const void* unique_id) {
+    QB_TRY(load_nccl());
+    Shard* s = new Shard();
+    r->shard = s;
+    while ((1 << s->g) < r->world) ++s->g;
+    ncclUniqueId id;
+    memcpy(&id, unique_id, 128);
+    QB_NCCL(g_nccl.CommInitRank(&s->comm, r->world, id, r->rank));
+    // staging: up to 1/8 of the shard, at most 4 GiB, at most half of what is still free
+    size_t free_b = 0, total_b = 0;
+    QB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    const uint64_t shard_amps = 1ull << r->n_local;
+    uint64_t amps = std::max<uint64_t>(shard_amps >> 3, (uint64_t)(r->world - 1));
+    amps = std::min<uint64_t>(amps, (4ull << 30) / sizeof(c64));
+    while (amps > (uint64_t)r->world && amps * sizeof(c64) > free_b / 2) amps >>= 1;
+    amps = std::max<uint64_t>(amps, (uint64_t)r->world);
+    QB_CUDA(cudaMalloc((void**)&s->staging, amps * sizeof(c64)));
+    s->staging_amps = amps;
+    QB_CUDA(cudaMalloc((void**)&s->d_gather, (2 + 2 * r->world) * sizeof(double)));
+    s->logical_at.resize(r->n);
+    for (uint32_t q = 0; q < r->n; ++q) s->logical_at[q] = q;
+    return QB_OK;
+}
+
+void shard_destroy(Reg* r) {
+    Shard* s = r->shard;
+    if (!s) return;
+    if (s->staging) cudaFree(s->staging);
+    if (s->d_gather) cudaFree(s->d_gather);
+    if (s->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(s->comm);
+    delete s;
+    r->shard = nullptr;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the exchange: swap local physical positions V[i] with rank bits J[i]
+// ------------------------------------------------------------------------------------------------
+static int exchange(Reg* r, std::vector<uint32_t> V, std::vector<uint32_t> J) {
+    Shard* s = r->shard;
+    const uint32_t gp = (uint32_t)V.size();
+    if (!gp) return QB_OK;
+    // sort the pairs by local position
+    std::vector<size_t> ord(gp);
+    for (size_t i = 0; i < gp; ++i) ord[i] = i;
+    std::sort(ord.begin(), ord.end(), [&](size_t a, size_t b) { return V[a] < V[b]; });
+    std::vector<uint32_t> Vs(gp), Js(gp);
+    for (size_t i = 0; i < gp; ++i) { Vs[i] = V[ord[i]]; Js[i] = J[ord[i]]; }
+
+    if (s->dry) {
+        s->events.push_back((int32_t)s->cur_gate);
+        s->events.push_back((int32_t)gp);
+        for (uint32_t v : Vs) s->events.push_back((int32_t)v);
+        for (uint32_t j : Js) s->events.push_back((int32_t)j);
+        for (uint32_t i = 0; i < gp; ++i) {
+            const uint32_t pl = Vs[i], pg = r->n_local + Js[i];
+            const uint32_t ql = s->logical_at[pl], qg = s->logical_at[pg];
+            s->logical_at[pl] = qg; s->logical_at[pg] = ql;
+            r->phys_of[qg] = pl; r->phys_of[ql] = pg;
+        }
+        return QB_OK;
+    }
+    uint32_t mybits = 0;
+    for (uint32_t i = 0; i < gp; ++i) mybits |= ((uint32_t)(r->rank >> Js[i]) & 1u) << i;
+    const uint32_t npeer = (1u << gp) - 1;
+    const uint64_t run_len = 1ull << Vs[0];
+    const uint64_t n_runs = 1ull << (r->n_local - gp - Vs[0]);
+    uint64_t chunk = s->staging_amps / npeer;
+    if (chunk == 0) return set_error(QB_ERR_OOM, -1, "exchange staging buffer too small");
+    uint64_t c2 = 1;
+    while (c2 * 2 <= chunk) c2 *= 2;
+    chunk = std::min(c2, run_len);
+    const uint64_t chunks_per_run = run_len / chunk;
+
+    auto block_off = [&](uint32_t a) {
+        uint64_t o = 0;
+        for (uint32_t i = 0; i < gp; ++i)
+            if ((a >> i) & 1) o |= 1ull << Vs[i];
+        return o;
+    };
+    auto peer_of = [&](uint32_t a) {
+        int p = r->rank;
+        for (uint32_t i = 0; i < gp; ++i) {
+            p &= ~(1 << Js[i]);
+            p |= (int)((a >> i) & 1) << Js[i];
+        }
+        return p;
+    };
+
+    for (uint64_t o = 0; o < n_runs; ++o) {
+        uint64_t base = o << Vs[0];
+        for (uint32_t i = 0; i < gp; ++i) {
+            const uint64_t lo = base & ((1ull << Vs[i]) - 1);
+            base = ((base >> Vs[i]) << (Vs[i] + 1)) | lo;
+        }
+        for (uint64_t c = 0; c < chunks_per_run; ++c) {
+            QB_NCCL(g_nccl.GroupStart());
+            for (uint32_t d = 1; d <= npeer; ++d) {
+                const uint32_t a = mybits ^ d;
+                const uint64_t off = base + block_off(a) + c * chunk;
+                const int peer = peer_of(a);
+                QB_NCCL(g_nccl.Send(r->state + off, chunk * 2, ncclDouble, peer, s->comm, r->stream));
+                QB_NCCL(g_nccl.Recv(s->staging + (uint64_t)(d - 1) * chunk, chunk * 2, ncclDouble, peer, s->comm, r->stream));
+            }
+            QB_NCCL(g_nccl.GroupEnd());
+            for (uint32_t d = 1; d <= npeer; ++d) {
+                const uint32_t a = mybits ^ d;
+                const uint64_t off = base + block_off(a) + c * chunk;
+                QB_CUDA(cudaMemcpyAsync(r->state + off, s->staging + (uint64_t)(d - 1) * chunk, chunk * sizeof(c64),
+                                        cudaMemcpyDeviceToDevice, r->stream));
+            }
+        }
+    }
+    const uint64_t sent = (uint64_t)npeer * (1ull << (r->n_local - gp)) * sizeof(c64);
+    r->st_swap_bytes += (int64_t)sent;
+    r->st_swaps++;
+    // bookkeeping of the placement
+    for (uint32_t i = 0; i < gp; ++i) {
+        const uint32_t pl = Vs[i], pg = r->n_local + Js[i];
+        const uint32_t ql = s->logical_at[pl], qg = s->logical_at[pg];
+        s->logical_at[pl] = qg; s->logical_at[pg] = ql;
+        r->phys_of[qg] = pl; r->phys_of[ql] = pg;
+    }
+    return QB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// mapping a (logical) gate onto this rank's shard
+// ------------------------------------------------------------------------------------------------
+enum MapResult { MAP_LOCAL, MAP_SKIP, MAP_NEEDS_SWAP };
+
+static MapResult map_gate(const Reg* r, const Gate& g, Gate* out) {
+    const uint32_t nl = r->n_local;
+    // controls
+    uint64_t ctrl = 0;
+    for (uint64_t m = g.ctrl_mask; m; m &= m - 1) {
+        const uint32_t p = r->phys_of[__builtin_ctzll(m)];
+        if (p >= nl) {
+            if (!((r->rank >> (p - nl)) & 1)) return MAP_SKIP;  // control is 0 on this rank
+        } else {
+            ctrl |= 1ull << p;
+        }
+    }
+    out->ctrl_mask = ctrl;
+    out->kind = g.kind;
+    out->tag = g.tag;
+    if (g.kind == GK_DENSE) {
+        out->targets.resize(g.k);
+        for (uint32_t j = 0; j < g.k; ++j) {
+            const uint32_t p = r->phys_of[g.targets[j]];
+            if (p >= nl) return MAP_NEEDS_SWAP;
+            out->targets[j] = p;
+        }
+        out->k = g.k;
+        out->matrix = g.matrix;
+        return MAP_LOCAL;
+    }
+    // diagonal: global target bits are fixed by the rank -> sub-table over the local targets
+    std::vector<uint32_t> keep;
+    uint32_t fixed = 0;
+    for (uint32_t j = 0; j < g.k; ++j) {
+        const uint32_t p = r->phys_of[g.targets[j]];
+        if (p >= nl) fixed |= ((uint32_t)(r->rank >> (p - nl)) & 1u) << j;
+        else keep.push_back(j);
+    }
+    out->k = (uint32_t)keep.size();
+    out->targets.resize(out->k);
+    out->matrix.resize(1ull << out->k);
+    for (uint32_t j = 0; j < out->k; ++j) out->targets[j] = r->phys_of[g.targets[keep[j]]];
+    for (uint64_t x = 0; x < (1ull << out->k); ++x) {
+        uint32_t idx = fixed;
+        for (uint32_t j = 0; j < out->k; ++j)
+            if ((x >> j) & 1) idx |= 1u << keep[j];
+        out->matrix[x] = g.matrix[idx];
+    }
+    // a sub-table that is all ones is the identity on this rank
+    bool ident = true;
+    for (const c64& d : out->matrix)
+        if (!(d.x == 1.0 && d.y == 0.0)) { ident = false; break; }
+    return ident ? MAP_SKIP : MAP_LOCAL;
+}
+
+// Chooses and performs the exchange needed before gates[i] (a dense gate with a global target).
+static int swap_for(Reg* r, const std::vector<Gate>& gates, size_t i) {
+    Shard* s = r->shard;
+    const uint32_t nl = r->n_local, n = r->n;
+    const size_t INF = (size_t)-1;
+    // next use as a DENSE target, per logical qubit, from gate i on
+    std::vector<size_t> next_use(n, INF);
+    for (size_t j = gates.size(); j-- > i;)
+        if (gates[j].kind == GK_DENSE)
+            for (uint32_t t : gates[j].targets) next_use[t] = j;
+    // candidates to evict: the top local positions (contiguous runs stay long), widened if needed
+    const uint32_t window = std::min<uint32_t>(nl, 10);
+    std::vector<uint32_t> cand;
+    for (uint32_t p = nl - window; p < nl; ++p) cand.push_back(p);
+    std::sort(cand.begin(), cand.end(), [&](uint32_t a, uint32_t b) {
+        const size_t ua = next_use[s->logical_at[a]], ub = next_use[s->logical_at[b]];
+        if (ua != ub) return ua > ub;  // furthest next use first
+        return a > b;                  // then the highest position (longest runs)
+    });
+    // global qubits ordered by urgency
+    std::vector<uint32_t> globals;
+    for (uint32_t j = 0; j < s->g; ++j) globals.push_back(j);
+    std::sort(globals.begin(), globals.end(), [&](uint32_t a, uint32_t b) {
+        const size_t ua = next_use[s->logical_at[nl + a]], ub = next_use[s->logical_at[nl + b]];
+        if (ua != ub) return ua < ub;
+        return a < b;
+    });
+    std::vector<uint32_t> V, J;
+    size_t ci = 0;
+    for (uint32_t j : globals) {
+        const size_t ug = next_use[s->logical_at[nl + j]];
+        if (ug == INF || ci >= cand.size()) break;
+        const size_t uv = next_use[s->logical_at[cand[ci]]];
+        if (uv <= ug && ug != i) break;        // no gain from trading these two
+        if (uv == i) {                         // the victim itself is needed by this gate: widen the search
+            bool found = false;
+            for (uint32_t p = nl; p-- > 0 && !found;) {
+                if (std::find(V.begin(), V.end(), p) != V.end()) continue;
+                if (next_use[s->logical_at[p]] > i) { V.push_back(p); J.push_back(j); found = true; }
+            }
+            if (!found) return set_error(QB_ERR_UNSUPPORTED, (int64_t)i, "gate touches more qubits than one shard holds");
+            continue;
+        }
+        V.push_back(cand[ci++]);
+        J.push_back(j);
+    }
+    if (V.empty()) return set_error(QB_ERR_UNSUPPORTED, (int64_t)i, "internal: no exchange candidate");
+    return exchange(r, V, J);
+}
+
+int shard_run(Reg* r, std::vector<Gate>& gates) {
+    std::vector<Gate> batch;
+    for (size_t i = 0; i < gates.size(); ++i) {
+        Gate m;
+        MapResult res = map_gate(r, gates[i], &m);
+        if (res == MAP_NEEDS_SWAP) {
+            if (!batch.empty() && !r->shard->dry) QB_TRY(run_local(r, batch));
+            batch.clear();
+            r->shard->cur_gate = gates[i].tag >= 0 ? gates[i].tag : (int64_t)i;
+            QB_TRY(swap_for(r, gates, i));
+            res = map_gate(r, gates[i], &m);
+            if (res == MAP_NEEDS_SWAP) return set_error(QB_ERR_UNSUPPORTED, (int64_t)i, "internal: gate still global after exchange");
+        }
+        if (res == MAP_LOCAL) batch.push_back(std::move(m));
+    }
+    if (!batch.empty() && !r->shard->dry) QB_TRY(run_local(r, batch));
+    return QB_OK;
+}
+
+// Dry run of the placement logic for tests: which exchanges would a rank perform for this gate list?
+int64_t shard_plan_debug(uint32_t n, int world, int rank, std::vector<Gate>& gates, int32_t* events, uint64_t capacity,
+                         uint32_t* final_phys_of) {
+    Reg r;
+    Shard s;
+    r.n = n;
+    r.world = world;
+    r.rank = rank;
+    while ((1 << s.g) < world) ++s.g;
+    if (s.g > n) return set_error(QB_ERR_INVALID_ARGUMENT, world, "more rank bits than qubits");
+    r.n_local = n - s.g;
+    r.phys_of.resize(n);
+    s.logical_at.resize(n);
+    for (uint32_t q = 0; q < n; ++q) r.phys_of[q] = s.logical_at[q] = q;
+    s.dry = true;
+    r.shard = &s;
+    int rc = shard_run(&r, gates);
+    r.shard = nullptr;
+    if (rc != QB_OK) return rc;
+    if (s.events.size() > capacity) return set_error(QB_ERR_INVALID_ARGUMENT, (int64_t)s.events.size(), "event buffer too small");
+    for (size_t i = 0; i < s.events.size(); ++i) events[i] = s.events[i];
+    if (final_phys_of)
+        for (uint32_t q = 0; q < n; ++q) final_phys_of[q] = r.phys_of[q];
+    return (int64_t)s.events.size();
+}
+
+// ------------------------------------------------------------------------------------------------
+// measurement / reductions across ranks
+// ------------------------------------------------------------------------------------------------
+static int allgather2(Reg* r, double a, double b, std::vector<double>* out) {
+    Shard* s = r->shard;
+    double h[2] = {a, b};
+    QB_CUDA(cudaMemcpyAsync(s->d_gather, h, sizeof(h), cudaMemcpyHostToDevice, r->stream));
+    QB_NCCL(g_nccl.AllGather(s->d_gather, s->d_gather + 2, 2, ncclDouble, s->comm, r->stream));
+    out->resize(2 * r->world);
+    QB_CUDA(cudaMemcpyAsync(out->data(), s->d_gather + 2, 2 * r->world * sizeof(double), cudaMemcpyDeviceToHost, r->stream));
+    QB_CUDA(cudaStreamSynchronize(r->stream));
+    return QB_OK;
+}
+
+int shard_probabilities(Reg* r, uint32_t logical_target, double* p0, double* p1) {
+    double a = 0.0, b = 0.0;
+    if (logical_target == UINT32_MAX) {
+        QB_TRY(k_probabilities(r, -1, &a, &b));
+    } else {
+        const uint32_t p = r->phys_of[logical_target];
+        if (p < r->n_local) {
+            QB_TRY(k_probabilities(r, (int)p, &a, &b));
+        } else {
+            double nrm, z;
+            QB_TRY(k_probabilities(r, -1, &nrm, &z));
+            if ((r->rank >> (p - r->n_local)) & 1) b = nrm; else a = nrm;
+        }
+    }
+    std::vector<double> all;
+    QB_TRY(allgather2(r, a, b, &all));
+    // adjacent-pair tree over the rank index: the continuation of the on-device tree
+    std::vector<double> v0(r->world), v1(r->world);
+    for (int i = 0; i < r->world; ++i) { v0[i] = all[2 * i]; v1[i] = all[2 * i + 1]; }
+    for (int len = r->world / 2; len >= 1; len /= 2)
+        for (int i = 0; i < len; ++i) { v0[i] = v0[2 * i] + v0[2 * i + 1]; v1[i] = v1[2 * i] + v1[2 * i + 1]; }
+    *p0 = v0[0];
+    *p1 = v1[0];
+    return QB_OK;
+}
+
+int shard_collapse(Reg* r, uint32_t logical_target, int outcome, double total_prob) {
+    const uint32_t p = r->phys_of[logical_target];
+    if (p < r->n_local) return k_collapse(r, p, outcome, total_prob);
+    const int bit = (r->rank >> (p - r->n_local)) & 1;
+    return k_scale_or_zero_all(r, bit == outcome, total_prob);
+}
+
+int shard_reduce_diff(Reg* r, double* max_abs, double* l2sq) {
+    std::vector<double> all;
+    QB_TRY(allgather2(r, *max_abs, *l2sq, &all));
+    double mx = 0.0, l2 = 0.0;
+    for (int i = 0; i < r->world; ++i) {
+        if (all[2 * i] != all[2 * i] || mx != mx) mx = NAN; else mx = std::max(mx, all[2 * i]);
+        l2 += all[2 * i + 1];
+    }
+    *max_abs = mx;
+    *l2sq = l2;
+    return QB_OK;
+}
+
+// A local bit permutation expressed as SWAP gates on physical positions (fused by the planner).
+static void push_local_swap(std::vector<Gate>* batch, uint32_t pa, uint32_t pb) {
+    Gate g;
+    g.kind = GK_DENSE;
+    g.k = 2;
+    g.targets = {pa, pb};
+    g.matrix.assign(16, make_double2(0.0, 0.0));
+    g.matrix[0] = g.matrix[1 * 4 + 2] = g.matrix[2 * 4 + 1] = g.matrix[15] = make_double2(1.0, 0.0);
+    batch->push_back(std::move(g));
+}
+
+// Restore the identity placement (needed before raw state access).  W = the logical qubits that belong on
+// the rank bits.  (1) local permutation: the top g local positions hold non-W qubits; (2) exchange them with
+// the rank bits: every W qubit is now local; (3) local permutation: top position nl-g+j holds logical nl+j;
+// (4) exchange again: rank bit j holds nl+j; (5) local permutation to the identity.  Steps (1)-(4) are skipped
+// when the rank bits are already home.  Local permutations are SWAP gates, fused by the planner.
+int shard_canonicalize(Reg* r) {
+    Shard* s = r->shard;
+    if (!s) return QB_OK;
+    const uint32_t nl = r->n_local, g = s->g, n = r->n;
+    bool identity = true;
+    for (uint32_t q = 0; q < n; ++q) identity = identity && r->phys_of[q] == q;
+    if (identity || g == 0) return QB_OK;
+    std::vector<Gate> batch;
+    auto local_swap = [&](uint32_t pa, uint32_t pb) {
+        if (pa == pb) return;
+        push_local_swap(&batch, pa, pb);
+        const uint32_t qa = s->logical_at[pa], qb = s->logical_at[pb];
+        s->logical_at[pa] = qb; s->logical_at[pb] = qa;
+        r->phys_of[qa] = pb; r->phys_of[qb] = pa;
+    };
+    auto run_batch = [&]() -> int {
+        if (batch.empty()) return QB_OK;
+        int rc = run_local(r, batch);
+        batch.clear();
+        return rc;
+    };
+    bool home = true;
+    for (uint32_t j = 0; j < g; ++j) home = home && s->logical_at[nl + j] == nl + j;
+    if (!home) {
+        if (nl < 2 * g) return set_error(QB_ERR_UNSUPPORTED, -1, "canonicalize needs n_local >= 2 log2(world)");
+        std::vector<uint32_t> V, J;
+        for (uint32_t j = 0; j < g; ++j) { V.push_back(nl - g + j); J.push_back(j); }
+        // (1)
+        uint32_t below = 0;
+        for (uint32_t p = nl - g; p < nl; ++p) {
+            if (s->logical_at[p] < nl) continue;  // already a non-W qubit
+            while (below < nl - g && s->logical_at[below] >= nl) ++below;
+            local_swap(p, below++);
+        }
+        QB_TRY(run_batch());
+        QB_TRY(exchange(r, V, J));  // (2)
+        // (3)
+        for (uint32_t j = 0; j < g; ++j) {
+            const uint32_t cur = r->phys_of[nl + j];
+            if (cur >= nl) return set_error(QB_ERR_UNSUPPORTED, nl + j, "internal: qubit %u still global", nl + j);
+            local_swap(nl - g + j, cur);
+        }
+        QB_TRY(run_batch());
+        QB_TRY(exchange(r, V, J));  // (4)
+    }
+    // (5)
+    for (uint32_t p = 0; p < nl; ++p) {
+        if (s->logical_at[p] == p) continue;
+        const uint32_t cur = r->phys_of[p];
+        if (cur >= nl) return set_error(QB_ERR_UNSUPPORTED, p, "internal: qubit %u left global", p);
+        local_swap(p, cur);
+    }
+    QB_TRY(run_batch());
+    for (uint32_t q = 0; q < n; ++q)
+        if (r->phys_of[q] != q) return set_error(QB_ERR_UNSUPPORTED, q, "internal: canonicalize failed for qubit %u", q);
+    return QB_OK;
+}
+
 }  // namespace qb
