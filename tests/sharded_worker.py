@@ -1,0 +1,85 @@
+"""Worker for the multi-GPU parity test; launched by tests/test_gpu_sharded.py as
+   python -m torch.distributed.run --nproc-per-node P --master-addr 127.0.0.1 tests/sharded_worker.py
+Every rank builds the same seeded circuit, runs it on its shard and compares its slice (and measurement
+outcomes under a shared uniform stream) with the CPU oracle."""
+import ctypes
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from oracle.oracle import OracleRegister
+from quaru_b200 import Operation, Register, _ffi
+from tests import circuits
+from tests.util import ABS_TOL, L2_TOL
+
+
+def main():
+    rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); local = int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        buf = ctypes.create_string_buffer(128)
+        assert _ffi.lib().qb_nccl_unique_id(buf) == 0, _ffi.last_error()
+        uid = torch.tensor(list(buf.raw), dtype=torch.uint8, device="cuda")
+    dist.broadcast(uid, 0)
+    uid_b = bytes(uid.cpu().tolist())
+    failures = []
+    g = int(np.log2(world))
+
+    def check(name, n, ops, fusion, measure=()):
+        reg = Register.sharded(n, 0, rank, world, uid_b)
+        reg.set_option(_ffi.QB_OPT_FUSION, fusion)
+        ora = OracleRegister.new([False] * n)
+        rng = np.random.default_rng(1234)
+        for m, t in ops:
+            reg.apply(Operation(m, t))
+            ora.apply((m, t))
+        for t in measure:
+            u = float(rng.random())
+            a, b = reg.measure(t, u=u), ora.measure(t, u)
+            if a != b:
+                failures.append(f"{name}: outcome of qubit {t} differs ({a} vs {b})")
+        nl = n - g
+        lo = rank << nl
+        mine = reg.read(0, 1 << n)[lo:lo + (1 << nl)]          # canonicalises the placement first
+        want = ora.state[lo:lo + (1 << nl)]
+        d = np.abs(mine - want)
+        l2 = float(np.sqrt((d * d).sum()))
+        if not (d.max() <= ABS_TOL and l2 <= L2_TOL):
+            failures.append(f"{name}: rank {rank} max|diff| {d.max():.3e} l2 {l2:.3e}")
+        nrm = reg.norm2()
+        if abs(nrm - 1.0) > 1e-10:
+            failures.append(f"{name}: norm2 {nrm}")
+        swaps = reg.stat(_ffi.QB_STAT_SWAPS)
+        reg.close()
+        return swaps
+
+    for n in (2 * g + 2, 10, 14):
+        for fusion in (0, 1):
+            s = check(f"layers n={n} fusion={fusion}", n, circuits.random_circuit(n, 6, seed=n), fusion,
+                      measure=(n - 1, 0, n // 2))
+            check(f"qft n={n} fusion={fusion}", n, circuits.qft_circuit(n), fusion)
+            ops = [o for o in circuits.mixed_circuit(n, 80, seed=7 + n) if len(o[1]) <= n - g]
+            check(f"mixed n={n} fusion={fusion}", n, ops, fusion, measure=(1, n - 1))
+    # a bigger one: 20 qubits, fused, 3 layers
+    check("layers n=20", 20, circuits.random_circuit(20, 3, seed=20), 1, measure=(19,))
+
+    flag = torch.tensor([len(failures)], device="cuda")
+    dist.all_reduce(flag)
+    for f in failures:
+        print(f"[rank {rank}] FAIL {f}", flush=True)
+    if rank == 0:
+        print("SHARDED_OK" if int(flag.item()) == 0 else f"SHARDED_FAILED ({int(flag.item())})", flush=True)
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag.item()) == 0 else 1)
+
+
+if __name__ == "__main__":
+    main()
