@@ -226,7 +226,7 @@ def run_ours(args):
                 raise SystemExit("qb_nccl_unique_id failed: " + _ffi.last_error()[0])
             uid = torch.tensor(list(buf.raw), dtype=torch.uint8, device="cuda")
         dist.broadcast(uid, 0)
-        reg = Register.sharded(n, 0, rank, world, bytes(uid.cpu().tolist()))
+        reg = Register.sharded(n, 0, rank, world, bytes(uid.cpu().tolist()), device=local_rank)
     else:
         reg = Register.new([False] * n)
 

@@ -70,9 +70,11 @@ int qb_create_product(const double* qubits, uint32_t n, qb_reg** out);
  * log2(world) index bits equal `rank`.  `nccl_unique_id` is the 128-byte ncclUniqueId produced
  * by qb_nccl_unique_id() on rank 0 and broadcast by the caller (torch.distributed in bench.py).
  * All subsequent calls on the handle are collective: every rank makes the same calls with the
- * same arguments.  No reference equivalent (the reference is single-process). */
+ * same arguments.  `device` is the CUDA ordinal this rank drives (LOCAL_RANK under torchrun; -1 = the
+ * library's current device -- note the library links its own CUDA runtime, so torch.cuda.set_device does
+ * not change it).  No reference equivalent (the reference is single-process). */
 int qb_create_sharded(uint32_t n, uint64_t basis_index, int32_t rank, int32_t world,
-                      const void* nccl_unique_id, qb_reg** out);
+                      const void* nccl_unique_id, int32_t device, qb_reg** out);
 int qb_nccl_unique_id(void* out128);
 
 /* #[derive(Clone)] register.rs:23 ; Drop.  qb_destroy(NULL) is a no-op. */

@@ -45,7 +45,7 @@ SIGNATURES = {
     "qb_create": (ctypes.c_int, [ctypes.c_uint32, ctypes.c_uint64, _regp]),
     "qb_create_product": (ctypes.c_int, [_dp, ctypes.c_uint32, _regp]),
     "qb_create_sharded": (ctypes.c_int, [ctypes.c_uint32, ctypes.c_uint64, ctypes.c_int32, ctypes.c_int32,
-                                         ctypes.c_void_p, _regp]),
+                                         ctypes.c_void_p, ctypes.c_int32, _regp]),
     "qb_nccl_unique_id": (ctypes.c_int, [ctypes.c_void_p]),
     "qb_clone": (ctypes.c_int, [_reg, _regp]),
     "qb_destroy": (None, [_reg]),

@@ -67,7 +67,7 @@ static void free_reg(Reg* r) {
     delete r;
 }
 
-static int create_impl(uint32_t n, uint64_t basis_index, int rank, int world, const void* uid, qb_reg** out) {
+static int create_impl(uint32_t n, uint64_t basis_index, int rank, int world, const void* uid, int device, qb_reg** out) {
     if (!out) return set_error(QB_ERR_INVALID_ARGUMENT, -1, "out is NULL");
     *out = nullptr;
     if (n > 40) return set_error(QB_ERR_UNSUPPORTED, n, "%u qubits: at most 40 are supported", n);
@@ -80,6 +80,7 @@ static int create_impl(uint32_t n, uint64_t basis_index, int rank, int world, co
     uint32_t g = 0;
     while ((1 << g) < world) ++g;
     if (g > n) return set_error(QB_ERR_INVALID_ARGUMENT, world, "%d ranks need at least %u qubits", world, g);
+    if (device >= 0) QB_CUDA(cudaSetDevice(device));
     Reg* r = new (std::nothrow) Reg();
     if (!r) return set_error(QB_ERR_OOM, -1, "host allocation failed");
     r->n = n;
@@ -129,8 +130,11 @@ static int enqueue(Reg* r, const double* matrix, const uint32_t* targets, uint32
 using namespace qb;
 
 #define REG(p) reinterpret_cast<qb::Reg*>(p)
-#define CHECK_REG(p) \
-    if (!(p)) return qb::set_error(QB_ERR_INVALID_ARGUMENT, -1, "register handle is NULL")
+// every entry point validates the handle and makes its device current (the library's CUDA runtime keeps its
+// own per-thread current device)
+#define CHECK_REG(p)                                                                           \
+    if (!(p)) return qb::set_error(QB_ERR_INVALID_ARGUMENT, -1, "register handle is NULL");    \
+    QB_CUDA(cudaSetDevice(REG(p)->device))
 
 extern "C" {
 
@@ -155,11 +159,12 @@ int64_t qb_shard_plan_debug(uint32_t n, int32_t world, int32_t rank, const qb_ga
 
 const char* qb_version(void) { return "quaru_b200 0.1 (sm_100a)"; }
 
-int qb_create(uint32_t n, uint64_t basis_index, qb_reg** out) { return create_impl(n, basis_index, 0, 1, nullptr, out); }
+int qb_create(uint32_t n, uint64_t basis_index, qb_reg** out) { return create_impl(n, basis_index, 0, 1, nullptr, -1, out); }
 
-int qb_create_sharded(uint32_t n, uint64_t basis_index, int32_t rank, int32_t world, const void* uid, qb_reg** out) {
+int qb_create_sharded(uint32_t n, uint64_t basis_index, int32_t rank, int32_t world, const void* uid, int32_t device,
+                      qb_reg** out) {
     if (world > 1 && !uid) return set_error(QB_ERR_INVALID_ARGUMENT, -1, "nccl_unique_id is NULL");
-    return create_impl(n, basis_index, rank, world, uid, out);
+    return create_impl(n, basis_index, rank, world, uid, device, out);
 }
 
 int qb_nccl_unique_id(void* out128) { return shard_unique_id(out128); }
@@ -177,7 +182,7 @@ int qb_create_product(const double* qubits, uint32_t n, qb_reg** out) {
         }
         if (!(fabs(total_prob) < 0.000001)) return set_error(QB_ERR_INVALID_QUBIT, i, "InvalidQubit(%u)", i);
     }
-    int rc = create_impl(n, 0, 0, 1, nullptr, out);
+    int rc = create_impl(n, 0, 0, 1, nullptr, -1, out);
     if (rc != QB_OK) return rc;
     rc = k_init_product(REG(*out), qubits);
     if (rc != QB_OK) { free_reg(REG(*out)); *out = nullptr; }
@@ -191,7 +196,7 @@ int qb_clone(qb_reg* src_, qb_reg** out) {
     *out = nullptr;
     if (src->world > 1) return set_error(QB_ERR_UNSUPPORTED, -1, "clone of a sharded register is not supported");
     QB_TRY(flush(src));
-    int rc = create_impl(src->n, 0, 0, 1, nullptr, out);
+    int rc = create_impl(src->n, 0, 0, 1, nullptr, src->device, out);
     if (rc != QB_OK) return rc;
     Reg* dst = REG(*out);
     dst->fusion = src->fusion; dst->tile_bits = src->tile_bits; dst->max_queue = src->max_queue; dst->force_path = src->force_path;

@@ -96,11 +96,12 @@ class Register:
             raise RuntimeError("Incorrect input qubits") from e          # register.rs:75
 
     @classmethod
-    def sharded(cls, n, k, rank, world, unique_id, seed=None):
-        """Rank `rank` of a register sharded over `world` GPUs (no reference equivalent)."""
+    def sharded(cls, n, k, rank, world, unique_id, device=-1, seed=None):
+        """Rank `rank` of a register sharded over `world` GPUs, driving CUDA device `device`
+        (no reference equivalent)."""
         h = ctypes.c_void_p()
         buf = ctypes.create_string_buffer(bytes(unique_id), 128)
-        _check(_ffi.lib().qb_create_sharded(n, k, rank, world, buf, ctypes.byref(h)))
+        _check(_ffi.lib().qb_create_sharded(n, k, rank, world, buf, device, ctypes.byref(h)))
         return cls(h, seed)
 
     def clone(self):

@@ -34,7 +34,7 @@ def main():
     g = int(np.log2(world))
 
     def check(name, n, ops, fusion, measure=()):
-        reg = Register.sharded(n, 0, rank, world, uid_b)
+        reg = Register.sharded(n, 0, rank, world, uid_b, device=local)
         reg.set_option(_ffi.QB_OPT_FUSION, fusion)
         ora = OracleRegister.new([False] * n)
         rng = np.random.default_rng(1234)
