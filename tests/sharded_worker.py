@@ -23,18 +23,21 @@ def main():
     rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); local = int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
-    if rank == 0:
-        buf = ctypes.create_string_buffer(128)
-        assert _ffi.lib().qb_nccl_unique_id(buf) == 0, _ffi.last_error()
-        uid = torch.tensor(list(buf.raw), dtype=torch.uint8, device="cuda")
-    dist.broadcast(uid, 0)
-    uid_b = bytes(uid.cpu().tolist())
+    def new_uid():
+        """A ncclUniqueId is single-use: one per communicator, made on rank 0 and broadcast."""
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            buf = ctypes.create_string_buffer(128)
+            assert _ffi.lib().qb_nccl_unique_id(buf) == 0, _ffi.last_error()
+            uid = torch.tensor(list(buf.raw), dtype=torch.uint8, device="cuda")
+        dist.broadcast(uid, 0)
+        return bytes(uid.cpu().tolist())
+
     failures = []
     g = int(np.log2(world))
 
     def check(name, n, ops, fusion, measure=()):
-        reg = Register.sharded(n, 0, rank, world, uid_b, device=local)
+        reg = Register.sharded(n, 0, rank, world, new_uid(), device=local)
         reg.set_option(_ffi.QB_OPT_FUSION, fusion)
         ora = OracleRegister.new([False] * n)
         rng = np.random.default_rng(1234)
