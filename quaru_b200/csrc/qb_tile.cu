@@ -17,6 +17,7 @@
 
 #include "qb_common.h"
 #include "qb_device.cuh"
+#include "qb_tile.h"
 
 namespace qb {
 
@@ -179,13 +180,16 @@ static void plan_passes(const std::vector<Gate>& gates, uint32_t n_local, uint32
         PlannedPass pass;
         uint64_t high = 0;  // chosen high tile bits (positions >= lc_min)
         uint32_t nh = 0;
-        uint64_t blocked = 0;
+        // A gate WRITES its dense target bits and READS its control / diagonal bits.  Two gates commute unless
+        // one writes a bit the other touches (diagonal gates and controls commute among themselves).
+        uint64_t blocked_w = 0, blocked_r = 0;
         int n_ops = 0, n_mats = 0;
         for (size_t i = first; i < gates.size(); ++i) {
             if (done[i]) continue;
             const Gate& g = gates[i];
-            const uint64_t qm = g.qubit_mask();
-            if (qm & blocked) { blocked |= qm; continue; }
+            const uint64_t wm = g.kind == GK_DENSE ? g.target_mask() : 0;
+            const uint64_t rm = g.ctrl_mask | (g.kind == GK_DIAG ? g.target_mask() : 0);
+            if ((wm & (blocked_w | blocked_r)) || (rm & blocked_w)) { blocked_w |= wm; blocked_r |= rm; continue; }
             bool ok = tile_supported(g);
             uint64_t need = 0;
             if (ok && g.kind == GK_DENSE) {
@@ -195,7 +199,7 @@ static void plan_passes(const std::vector<Gate>& gates, uint32_t n_local, uint32
             }
             const int mats = (int)g.matrix.size();
             if (ok && (n_ops + 1 > max_ops || n_mats + mats > max_mats)) ok = false;
-            if (!ok) { blocked |= qm; continue; }
+            if (!ok) { blocked_w |= wm; blocked_r |= rm; continue; }
             high |= need;
             nh += (uint32_t)__builtin_popcountll(need);
             n_ops++;
@@ -283,25 +287,31 @@ static int launch_pass(Reg* r, const Prog& prog) {
     }
     const uint64_t tiles = 1ull << (r->n_local - prog.tile_bits);
     if (tiles > 0x7fffffffull) return set_error(QB_ERR_UNSUPPORTED, (int64_t)tiles, "too many tiles for one grid");
-    if (r->profile) {
-        if (r->tile_events_used + 2 > 1024) QB_TRY(drain_tile_events(r));
-        while (r->tile_events.size() < r->tile_events_used + 2) {
-            cudaEvent_t e;
-            QB_CUDA(cudaEventCreate(&e));
-            r->tile_events.push_back(e);
-        }
-        QB_CUDA(cudaEventRecord(r->tile_events[r->tile_events_used], r->stream));
-    }
+    if (r->profile) QB_TRY(tile_profile_begin(r));
     k2_tile_pass<Prog><<<(unsigned)tiles, TILE_THREADS, smem, r->stream>>>(r->state, prog);
     QB_CUDA(cudaGetLastError());
-    if (r->profile) {
-        QB_CUDA(cudaEventRecord(r->tile_events[r->tile_events_used + 1], r->stream));
-        r->tile_events_used += 2;
-        r->st_tile_launches++;
-    }
+    if (r->profile) QB_TRY(tile_profile_end(r));
     r->st_launches++;
     r->st_passes++;
     r->st_bytes += (int64_t)(32ull << r->n_local);
+    return QB_OK;
+}
+
+int tile_profile_begin(Reg* r) {
+    if (r->tile_events_used + 2 > 1024) QB_TRY(drain_tile_events(r));
+    while (r->tile_events.size() < r->tile_events_used + 2) {
+        cudaEvent_t e;
+        QB_CUDA(cudaEventCreate(&e));
+        r->tile_events.push_back(e);
+    }
+    QB_CUDA(cudaEventRecord(r->tile_events[r->tile_events_used], r->stream));
+    return QB_OK;
+}
+
+int tile_profile_end(Reg* r) {
+    QB_CUDA(cudaEventRecord(r->tile_events[r->tile_events_used + 1], r->stream));
+    r->tile_events_used += 2;
+    r->st_tile_launches++;
     return QB_OK;
 }
 
@@ -329,9 +339,14 @@ int run_fused(Reg* r, std::vector<Gate>& gates) {
             continue;
         }
         // a pass with a single gate is cheaper through the streaming kernels (they skip untouched halves)
-        if (p.gate_idx.size() == 1 && r->force_path != 2) {
+        if (p.gate_idx.size() == 1 && r->force_path != 2 && r->force_path != 4) {
             const Gate& g = gates[p.gate_idx[0]];
             if (g.kind == GK_DIAG || g.k == 1) { QB_TRY(k_apply_gate_unfused(r, g)); continue; }
+        }
+        if (r->force_path != 2) {  // register-blocked kernel for 2^12 tiles; force path 2 pins the shared-memory kernel
+            bool handled = false;
+            QB_TRY(run_pass_v2(r, gates, p.gate_idx, p.tile_pos, p.lc, &handled));
+            if (handled) continue;
         }
         size_t mats = 0;
         for (size_t gi : p.gate_idx) mats += gates[gi].matrix.size();

@@ -1,0 +1,11 @@
+// qb_tile.h -- shared between the two tile-pass kernels (qb_tile.cu: shared-memory interpreter, any tile size;
+// qb_tile2.cu: register-blocked kernel for 2^12-amplitude tiles).
+#pragma once
+#include "qb_common.h"
+
+namespace qb {
+int tile_profile_begin(Reg* r);  // QB_OPT_PROFILE: CUDA-event bracket around one tile launch
+int tile_profile_end(Reg* r);
+int run_pass_v2(Reg* r, const std::vector<Gate>& gates, const std::vector<size_t>& gate_idx,
+                const std::vector<uint32_t>& tile_pos, uint32_t lc, bool* handled);
+}  // namespace qb

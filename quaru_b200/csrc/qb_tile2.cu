@@ -1,0 +1,460 @@
+// qb_tile2.cu -- K2r: register-blocked fused tile pass (the fast path for tiles of 2^12 amplitudes).
+//
+// ncu on the first tile kernel (qb_tile.cu, profiles/r1_ncu_tile_kernel.csv) showed it instruction-issue
+// bound: every gate was one shared-memory round trip with per-amplitude index arithmetic (~57 instructions
+// per amplitude per gate).  Here a CTA still owns one 2^12-amplitude tile per pass, but each of its 256
+// threads keeps 16 amplitudes in REGISTERS, addressed by 4 "register bits" R of the tile index; the other 8
+// tile bits are the thread id.  A pass is a sequence of ROUNDS:
+//   * round 0 loads straight from HBM into registers (R within tile bits 5..11, so a warp still reads 512
+//     contiguous bytes per instruction), the last round stores straight back: a pass whose dense gates touch
+//     at most 4 tile bits never touches shared memory at all;
+//   * between rounds the registers are transposed through a swizzled shared-memory tile (conflict-free
+//     128-bit accesses) into a new choice of R;
+//   * inside a round every gate whose dense target bits are in R is applied to the registers with compile-time
+//     register indices (no index arithmetic per amplitude); controls may be register bits, thread bits or
+//     bits outside the tile; diagonal gates whose bits are all thread/outer bits cost ONE complex multiply per
+//     thread: they accumulate into a per-thread phase that is applied once at the end of the round.
+// Special cases with fewer FP64 instructions: real matrices (H), X (register swap), phase -1 (sign flip).
+#include <string.h>
+
+#include <algorithm>
+
+#include "qb_common.h"
+#include "qb_device.cuh"
+#include "qb_tile.h"
+
+namespace qb {
+
+enum RKind : uint8_t { RK_D1 = 0, RK_X = 1, RK_D2 = 2, RK_PH = 3, RK_DG = 4 };
+enum RFlags : uint8_t { RF_REAL = 1, RF_NEG = 2 };
+
+struct ROp {
+    uint8_t kind;
+    uint8_t a, b;      // register-bit indices of the dense targets (matrix bit 0, matrix bit 1)
+    uint8_t flags;
+    uint16_t rmask;    // controls that are register bits (mask over the 4 register bits)
+    uint16_t tmask;    // controls that are thread bits (mask over the 12 tile-local bits)
+    uint32_t mat;      // offset into mats
+    uint8_t src[3];    // RK_DG: source of index bit i: 0x00|reg bit, 0x40|tile-local bit (thread), 0x80|global bit (outer)
+    uint8_t k;         // RK_DG: number of index bits (1..3)
+    uint64_t omask;    // controls outside the tile (global bit mask)
+};
+static_assert(sizeof(ROp) == 24, "ROp layout");
+
+struct RoundDesc {
+    uint8_t R[4];      // ascending tile-local bits held in registers
+    uint8_t tb[8];     // thread-id bit i <-> tile-local bit tb[i]
+    uint16_t op_begin, op_end;
+    uint8_t has_tph, pad[3];
+};
+
+template <int NOPS, int NMAT, int NROUNDS>
+struct RProgram {
+    uint32_t lc, h, n_rounds, pad;
+    uint8_t hp[8];
+    RoundDesc rounds[NROUNDS];
+    ROp ops[NOPS];
+    c64 mats[NMAT];
+};
+typedef RProgram<24, 160, 8> RProgSmall;      // ~3.4 KB
+typedef RProgram<192, 1200, 48> RProgLarge;   // ~25 KB
+
+constexpr int RT = 12;           // tile bits
+constexpr int RTHREADS = 256;
+
+__device__ __forceinline__ uint32_t swz(uint32_t l) { return l ^ (((l >> 3) ^ (l >> 6) ^ (l >> 9)) & 7u); }
+
+// ---- register-resident gate kernels (compile-time register indices) ---------------------------------
+template <int A>
+__device__ __forceinline__ void r_d1(c64 (&v)[16], const c64* __restrict__ m, uint32_t rmask, bool real) {
+    const c64 m00 = m[0], m01 = m[1], m10 = m[2], m11 = m[3];
+#pragma unroll
+    for (int j0 = 0; j0 < 16; ++j0) {
+        if ((j0 >> A) & 1) continue;
+        const int j1 = j0 | (1 << A);
+        if ((j0 & rmask) != rmask) continue;
+        const c64 a0 = v[j0], a1 = v[j1];
+        if (real) {
+            v[j0] = make_double2(fma(m01.x, a1.x, m00.x * a0.x), fma(m01.x, a1.y, m00.x * a0.y));
+            v[j1] = make_double2(fma(m11.x, a1.x, m10.x * a0.x), fma(m11.x, a1.y, m10.x * a0.y));
+        } else {
+            v[j0] = cmul2(m00, a0, m01, a1);
+            v[j1] = cmul2(m10, a0, m11, a1);
+        }
+    }
+}
+
+template <int A>
+__device__ __forceinline__ void r_x(c64 (&v)[16], uint32_t rmask) {
+#pragma unroll
+    for (int j0 = 0; j0 < 16; ++j0) {
+        if ((j0 >> A) & 1) continue;
+        const int j1 = j0 | (1 << A);
+        if ((j0 & rmask) != rmask) continue;
+        const c64 t = v[j0];
+        v[j0] = v[j1];
+        v[j1] = t;
+    }
+}
+
+template <int A, int B>  // A = register bit of matrix bit 0, B = of matrix bit 1, A != B
+__device__ __forceinline__ void r_d2(c64 (&v)[16], const c64* __restrict__ M, uint32_t rmask) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        if (((j >> A) & 1) || ((j >> B) & 1)) continue;
+        if ((j & rmask) != rmask) continue;
+        const int i1 = j | (1 << A), i2 = j | (1 << B), i3 = i1 | (1 << B);
+        const c64 a0 = v[j], a1 = v[i1], a2 = v[i2], a3 = v[i3];
+        c64 r0 = cmul2(M[0], a0, M[1], a1);   r0 = cfma(M[2], a2, r0);   r0 = cfma(M[3], a3, r0);
+        c64 r1 = cmul2(M[4], a0, M[5], a1);   r1 = cfma(M[6], a2, r1);   r1 = cfma(M[7], a3, r1);
+        c64 r2 = cmul2(M[8], a0, M[9], a1);   r2 = cfma(M[10], a2, r2);  r2 = cfma(M[11], a3, r2);
+        c64 r3 = cmul2(M[12], a0, M[13], a1); r3 = cfma(M[14], a2, r3);  r3 = cfma(M[15], a3, r3);
+        v[j] = r0; v[i1] = r1; v[i2] = r2; v[i3] = r3;
+    }
+}
+
+__device__ __forceinline__ void r_d2_dispatch(c64 (&v)[16], const c64* M, uint32_t a, uint32_t b, uint32_t rmask) {
+    switch (a * 4 + b) {
+        case 0 * 4 + 1: r_d2<0, 1>(v, M, rmask); break;
+        case 0 * 4 + 2: r_d2<0, 2>(v, M, rmask); break;
+        case 0 * 4 + 3: r_d2<0, 3>(v, M, rmask); break;
+        case 1 * 4 + 0: r_d2<1, 0>(v, M, rmask); break;
+        case 1 * 4 + 2: r_d2<1, 2>(v, M, rmask); break;
+        case 1 * 4 + 3: r_d2<1, 3>(v, M, rmask); break;
+        case 2 * 4 + 0: r_d2<2, 0>(v, M, rmask); break;
+        case 2 * 4 + 1: r_d2<2, 1>(v, M, rmask); break;
+        case 2 * 4 + 3: r_d2<2, 3>(v, M, rmask); break;
+        case 3 * 4 + 0: r_d2<3, 0>(v, M, rmask); break;
+        case 3 * 4 + 1: r_d2<3, 1>(v, M, rmask); break;
+        default: r_d2<3, 2>(v, M, rmask); break;
+    }
+}
+
+template <class Prog>
+__global__ void __launch_bounds__(RTHREADS, 2) k2r_tile_pass(c64* __restrict__ st, const __grid_constant__ Prog prog) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    c64* tile = reinterpret_cast<c64*>(smem_raw);
+    const uint32_t tid = threadIdx.x;
+    const uint32_t lc = prog.lc, h = prog.h;
+
+    uint64_t base = (uint64_t)blockIdx.x << lc;
+    for (uint32_t j = 0; j < h; ++j) base = insert_zero_bit(base, prog.hp[j]);
+
+    // tile-local index -> offset from `base` (bit-linear: low lc bits direct, bit lc+i -> global bit hp[i])
+    auto goff = [&](uint32_t x) -> uint64_t {
+        uint64_t o = x & ((1u << lc) - 1u);
+        for (uint32_t i = 0; i < h; ++i) o |= (uint64_t)((x >> (lc + i)) & 1u) << prog.hp[i];
+        return o;
+    };
+
+    c64 v[16];
+    uint32_t tl = 0;          // this thread's tile-local index bits (register bits are 0)
+    uint32_t rb[4];           // 1 << R[i]
+    auto set_mapping = [&](const RoundDesc& rd) {
+        tl = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) tl |= ((tid >> i) & 1u) << rd.tb[i];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) rb[i] = 1u << rd.R[i];
+    };
+    auto roff = [&](int j) -> uint32_t {
+        return ((j & 1) ? rb[0] : 0u) | ((j & 2) ? rb[1] : 0u) | ((j & 4) ? rb[2] : 0u) | ((j & 8) ? rb[3] : 0u);
+    };
+
+    // ---- round 0: HBM -> registers ------------------------------------------------------------------
+    set_mapping(prog.rounds[0]);
+    {
+        const uint64_t gt = base + goff(tl);
+        const uint64_t g0 = goff(rb[0]), g1 = goff(rb[1]), g2 = goff(rb[2]), g3 = goff(rb[3]);
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+            v[j] = ld128(st + (gt + ((j & 1) ? g0 : 0) + ((j & 2) ? g1 : 0) + ((j & 4) ? g2 : 0) + ((j & 8) ? g3 : 0)));
+    }
+
+    for (uint32_t r = 0; r < prog.n_rounds; ++r) {
+        const RoundDesc& rd = prog.rounds[r];
+        if (r > 0) {  // transpose through shared memory into the new register bits
+            const uint32_t s_t = swz(tl);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) tile[s_t ^ swz(roff(j))] = v[j];
+            __syncthreads();
+            set_mapping(rd);
+            const uint32_t s_n = swz(tl);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = tile[s_n ^ swz(roff(j))];
+            __syncthreads();
+        }
+        c64 tph = make_double2(1.0, 0.0);
+        for (uint32_t oi = rd.op_begin; oi < rd.op_end; ++oi) {
+            const ROp& op = prog.ops[oi];
+            if ((base & op.omask) != op.omask) continue;        // uniform per CTA
+            if ((tl & op.tmask) != op.tmask) continue;          // per thread
+            const uint32_t rmask = op.rmask;
+            const c64* M = prog.mats + op.mat;
+            switch (op.kind) {
+                case RK_D1: {
+                    const bool real = op.flags & RF_REAL;
+                    switch (op.a) {
+                        case 0: r_d1<0>(v, M, rmask, real); break;
+                        case 1: r_d1<1>(v, M, rmask, real); break;
+                        case 2: r_d1<2>(v, M, rmask, real); break;
+                        default: r_d1<3>(v, M, rmask, real); break;
+                    }
+                } break;
+                case RK_X:
+                    switch (op.a) {
+                        case 0: r_x<0>(v, rmask); break;
+                        case 1: r_x<1>(v, rmask); break;
+                        case 2: r_x<2>(v, rmask); break;
+                        default: r_x<3>(v, rmask); break;
+                    }
+                    break;
+                case RK_D2: r_d2_dispatch(v, M, op.a, op.b, rmask); break;
+                case RK_PH: {
+                    const c64 d = M[0];
+                    if (rmask == 0) {
+                        tph = cmul(d, tph);
+                    } else if (op.flags & RF_NEG) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if ((j & rmask) == rmask) v[j] = make_double2(-v[j].x, -v[j].y);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if ((j & rmask) == rmask) v[j] = cmul(d, v[j]);
+                    }
+                } break;
+                default: {  // RK_DG: k <= 3 index bits from register / thread / outer bits
+                    uint32_t fixed = 0, regsel = 0, ra[3] = {0, 0, 0};
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) {
+                        if (i >= op.k) break;
+                        const uint32_t s = op.src[i];
+                        if (s & 0x80) fixed |= (uint32_t)((base >> (s & 0x3f)) & 1u) << i;
+                        else if (s & 0x40) fixed |= ((tl >> (s & 0x3f)) & 1u) << i;
+                        else { regsel |= 1u << i; ra[i] = s & 3u; }
+                    }
+                    if (regsel == 0 && rmask == 0) {
+                        tph = cmul(M[fixed], tph);
+                    } else {
+                        c64 f[8];
+#pragma unroll
+                        for (int x = 0; x < 8; ++x) f[x] = M[(fixed | (x & regsel)) & ((1u << op.k) - 1u)];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            if ((j & rmask) != rmask) continue;
+                            const uint32_t x = (((j >> ra[0]) & 1u) | (((j >> ra[1]) & 1u) << 1) | (((j >> ra[2]) & 1u) << 2)) & regsel;
+                            const c64 lo4 = (x & 2) ? ((x & 1) ? f[3] : f[2]) : ((x & 1) ? f[1] : f[0]);
+                            const c64 hi4 = (x & 2) ? ((x & 1) ? f[7] : f[6]) : ((x & 1) ? f[5] : f[4]);
+                            v[j] = cmul((x & 4) ? hi4 : lo4, v[j]);
+                        }
+                    }
+                } break;
+            }
+        }
+        if (rd.has_tph) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = cmul(tph, v[j]);
+        }
+    }
+
+    // ---- last round: registers -> HBM -----------------------------------------------------------------
+    {
+        const uint64_t gt = base + goff(tl);
+        const uint64_t g0 = goff(rb[0]), g1 = goff(rb[1]), g2 = goff(rb[2]), g3 = goff(rb[3]);
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+            st128(st + (gt + ((j & 1) ? g0 : 0) + ((j & 2) ? g1 : 0) + ((j & 4) ? g2 : 0) + ((j & 8) ? g3 : 0)), v[j]);
+    }
+}
+
+// ================================================================================================
+// host: split a pass into rounds and encode it
+// ================================================================================================
+struct LocalOp {
+    const Gate* g;
+    uint32_t dense;  // tile-local bits that are dense targets
+    uint32_t reads;  // tile-local bits that are controls / diagonal index bits
+};
+
+static bool is_real(const Gate& g) {
+    for (const c64& e : g.matrix)
+        if (e.y != 0.0) return false;
+    return true;
+}
+static bool is_x(const Gate& g) {
+    return g.k == 1 && g.matrix[0].x == 0.0 && g.matrix[0].y == 0.0 && g.matrix[3].x == 0.0 && g.matrix[3].y == 0.0 &&
+           g.matrix[1].x == 1.0 && g.matrix[1].y == 0.0 && g.matrix[2].x == 1.0 && g.matrix[2].y == 0.0;
+}
+
+template <class Prog>
+static bool encode_rounds(const std::vector<Gate>& gates, const std::vector<size_t>& gate_idx, const std::vector<uint32_t>& tile_pos,
+                          uint32_t lc, Prog* prog) {
+    const uint32_t T = (uint32_t)tile_pos.size();
+    if (T != RT) return false;
+    int8_t local_of[64];
+    uint64_t tile_mask = 0;
+    for (int b = 0; b < 64; ++b) local_of[b] = -1;
+    for (uint32_t j = 0; j < T; ++j) { local_of[tile_pos[j]] = (int8_t)j; tile_mask |= 1ull << tile_pos[j]; }
+    prog->lc = lc;
+    prog->h = T - lc;
+    for (uint32_t j = 0; j < prog->h; ++j) prog->hp[j] = (uint8_t)tile_pos[lc + j];
+
+    std::vector<LocalOp> ops;
+    for (size_t gi : gate_idx) {
+        const Gate& g = gates[gi];
+        LocalOp lo{&g, 0, 0};
+        for (uint64_t m = g.ctrl_mask & tile_mask; m; m &= m - 1) lo.reads |= 1u << local_of[__builtin_ctzll(m)];
+        for (uint32_t t : g.targets) {
+            if (local_of[t] < 0) { if (g.kind == GK_DENSE) return false; continue; }
+            if (g.kind == GK_DENSE) lo.dense |= 1u << local_of[t]; else lo.reads |= 1u << local_of[t];
+        }
+        ops.push_back(lo);
+    }
+    const size_t max_ops = sizeof(prog->ops) / sizeof(ROp), max_mats = sizeof(prog->mats) / sizeof(c64);
+    const size_t max_rounds = sizeof(prog->rounds) / sizeof(RoundDesc);
+    std::vector<char> done(ops.size(), 0);
+    size_t remaining = ops.size(), n_ops = 0, n_mats = 0, n_rounds = 0;
+    const uint32_t io_allowed = 0xfe0;  // tile bits 5..11: register bits of the HBM-facing rounds
+    auto emit_round = [&](uint32_t R, const std::vector<size_t>& members) -> bool {
+        if (n_rounds >= max_rounds) return false;
+        RoundDesc& rd = prog->rounds[n_rounds];
+        memset(&rd, 0, sizeof(rd));
+        uint32_t ri = 0, reg_of[12];
+        for (uint32_t b = 0; b < RT; ++b) reg_of[b] = 99;
+        for (uint32_t b = 0; b < RT; ++b)
+            if ((R >> b) & 1) { rd.R[ri] = (uint8_t)b; reg_of[b] = ri++; }
+        // thread bits: lanes 0..2 must hit distinct (bit mod 3) classes for conflict-free swizzled accesses;
+        // the HBM-facing rounds have R within 5..11, so taking the free bits in ascending order gives lanes = bits 0..4.
+        std::vector<uint32_t> free_bits;
+        for (uint32_t b = 0; b < RT; ++b)
+            if (!((R >> b) & 1)) free_bits.push_back(b);
+        std::vector<uint32_t> order;
+        bool cls[3] = {false, false, false};
+        for (uint32_t b : free_bits)
+            if (order.size() < 3 && !cls[b % 3]) { order.push_back(b); cls[b % 3] = true; }
+        for (uint32_t b : free_bits)
+            if (std::find(order.begin(), order.end(), b) == order.end()) order.push_back(b);
+        if ((R & ~io_allowed) == 0) order = free_bits;  // bits 0,1,2 first anyway (distinct classes) and lanes = 0..4
+        for (int i = 0; i < 8; ++i) rd.tb[i] = (uint8_t)order[i];
+        rd.op_begin = (uint16_t)n_ops;
+        for (size_t oi : members) {
+            const LocalOp& lo = ops[oi];
+            const Gate& g = *lo.g;
+            if (n_ops >= max_ops || n_mats + g.matrix.size() > max_mats) return false;
+            ROp op;
+            memset(&op, 0, sizeof(op));
+            op.mat = (uint32_t)n_mats;
+            op.omask = g.ctrl_mask & ~tile_mask;
+            for (uint64_t m = g.ctrl_mask & tile_mask; m; m &= m - 1) {
+                const uint32_t lb = (uint32_t)local_of[__builtin_ctzll(m)];
+                if (reg_of[lb] != 99) op.rmask |= (uint16_t)(1u << reg_of[lb]); else op.tmask |= (uint16_t)(1u << lb);
+            }
+            std::vector<c64> mat = g.matrix;
+            if (g.kind == GK_DENSE) {
+                if (g.k == 1) {
+                    op.a = (uint8_t)reg_of[local_of[g.targets[0]]];
+                    if (is_x(g)) op.kind = RK_X;
+                    else { op.kind = RK_D1; if (is_real(g)) op.flags |= RF_REAL; }
+                } else {
+                    op.kind = RK_D2;
+                    op.a = (uint8_t)reg_of[local_of[g.targets[0]]];
+                    op.b = (uint8_t)reg_of[local_of[g.targets[1]]];
+                }
+            } else if (g.k == 0) {
+                op.kind = RK_PH;
+                if (mat[0].x == -1.0 && mat[0].y == 0.0) op.flags |= RF_NEG;
+                if (op.rmask == 0) rd.has_tph = 1;
+            } else {
+                op.kind = RK_DG;
+                op.k = (uint8_t)g.k;
+                bool any_reg = false;
+                for (uint32_t i = 0; i < g.k; ++i) {
+                    const uint32_t t = g.targets[i];
+                    if (local_of[t] < 0) op.src[i] = (uint8_t)(0x80 | t);
+                    else if (reg_of[local_of[t]] != 99) { op.src[i] = (uint8_t)reg_of[local_of[t]]; any_reg = true; }
+                    else op.src[i] = (uint8_t)(0x40 | local_of[t]);
+                }
+                if (!any_reg && op.rmask == 0) rd.has_tph = 1;
+            }
+            memcpy(prog->mats + n_mats, mat.data(), mat.size() * sizeof(c64));
+            n_mats += mat.size();
+            prog->ops[n_ops++] = op;
+        }
+        rd.op_end = (uint16_t)n_ops;
+        ++n_rounds;
+        return true;
+    };
+
+    bool first = true;
+    uint32_t last_R = 0;
+    while (remaining) {
+        uint32_t R = 0, blocked_w = 0, blocked_r = 0;
+        const uint32_t allowed = first ? io_allowed : 0xfffu;
+        std::vector<size_t> members;
+        for (size_t i = 0; i < ops.size(); ++i) {
+            if (done[i]) continue;
+            const LocalOp& lo = ops[i];
+            bool ok = !(lo.dense & (blocked_w | blocked_r)) && !(lo.reads & blocked_w);
+            if (ok && (lo.dense & ~allowed)) ok = false;
+            if (ok && __builtin_popcount(R | lo.dense) > 4) ok = false;
+            if (!ok) { blocked_w |= lo.dense; blocked_r |= lo.reads; continue; }
+            R |= lo.dense;
+            members.push_back(i);
+            done[i] = 1;
+            --remaining;
+        }
+        // fill R up to 4 bits with free bits, highest first (keeps HBM-facing rounds within bits 5..11)
+        for (int b = RT - 1; b >= 0 && __builtin_popcount(R) < 4; --b)
+            if (!((R >> b) & 1) && ((allowed >> b) & 1)) R |= 1u << b;
+        if (!emit_round(R, members)) return false;
+        last_R = R;
+        first = false;
+    }
+    if (n_rounds == 0 || (last_R & ~io_allowed)) {  // the storing round must have its register bits within 5..11
+        if (!emit_round(0xf00, {})) return false;
+    }
+    prog->n_rounds = (uint32_t)n_rounds;
+    return true;
+}
+
+template <class Prog>
+static int launch_rpass(Reg* r, const Prog& prog) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        QB_CUDA(cudaFuncSetAttribute(k2r_tile_pass<Prog>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(c64) << RT)));
+        attr_set = true;
+    }
+    const uint64_t tiles = 1ull << (r->n_local - RT);
+    if (tiles > 0x7fffffffull) return set_error(QB_ERR_UNSUPPORTED, (int64_t)tiles, "too many tiles for one grid");
+    if (r->profile) QB_TRY(tile_profile_begin(r));
+    k2r_tile_pass<Prog><<<(unsigned)tiles, RTHREADS, sizeof(c64) << RT, r->stream>>>(r->state, prog);
+    QB_CUDA(cudaGetLastError());
+    if (r->profile) QB_TRY(tile_profile_end(r));
+    r->st_launches++;
+    r->st_passes++;
+    r->st_bytes += (int64_t)(32ull << r->n_local);
+    return QB_OK;
+}
+
+// returns QB_OK and *handled = true if the pass went through the register-blocked kernel
+int run_pass_v2(Reg* r, const std::vector<Gate>& gates, const std::vector<size_t>& gate_idx, const std::vector<uint32_t>& tile_pos,
+                uint32_t lc, bool* handled) {
+    *handled = false;
+    if (tile_pos.size() != RT || r->n_local < RT) return QB_OK;
+    size_t mats = 0;
+    for (size_t gi : gate_idx) mats += gates[gi].matrix.size();
+    if (gate_idx.size() <= 20 && mats <= 150) {
+        RProgSmall small;
+        if (encode_rounds(gates, gate_idx, tile_pos, lc, &small)) {
+            *handled = true;
+            return launch_rpass(r, small);
+        }
+    }
+    static RProgLarge large;
+    if (!encode_rounds(gates, gate_idx, tile_pos, lc, &large)) return QB_OK;
+    *handled = true;
+    return launch_rpass(r, large);
+}
+
+}  // namespace qb

@@ -85,3 +85,52 @@ def test_large_fused_vs_oracle(engine):
     ops = circuits.random_circuit(n, 2, seed=22)
     reg, ora = _run(engine, n, ops, 2500, batch=True)
     assert_close(reg.state, ora.state)
+
+
+# ---- the register-blocked kernel (2^12 tiles): rounds, thread-phase accumulation, special-cased gates ----------
+@pytest.mark.parametrize("n,depth,seed", [(12, 10, 1), (13, 8, 2), (15, 8, 3), (17, 6, 4), (19, 4, 5)])
+def test_register_blocked_random_layers(engine, n, depth, seed):
+    ops = circuits.random_circuit(n, depth, seed=seed)
+    reg, ora = _run(engine, n, ops, 3000 + n, tile_bits=12, batch=True)
+    assert_close(reg.state, ora.state, f"v2 layers n={n}")
+
+
+@pytest.mark.parametrize("n,seed", [(12, 11), (13, 12), (14, 13), (16, 14), (18, 15)])
+def test_register_blocked_mixed(engine, n, seed):
+    ops = circuits.mixed_circuit(n, 150, seed)
+    reg, ora = _run(engine, n, ops, 3100 + n, tile_bits=12)
+    assert_close(reg.state, ora.state, f"v2 mixed n={n}")
+
+
+def test_register_blocked_single_gate_passes(engine):
+    """Force the tile kernels even for single gates: every choice of register bits / thread bits / outer bits."""
+    n = 15
+    ops = circuits.mixed_circuit(n, 90, 21)
+    reg, ora = _run(engine, n, ops, 3200, tile_bits=12, force=4, max_queue=1)
+    assert_close(reg.state, ora.state)
+
+
+def test_register_blocked_agrees_with_shared_memory_kernel(engine):
+    n = 16
+    ops = circuits.random_circuit(n, 6, seed=8) + circuits.qft_circuit(n)
+    a, ora = _run(engine, n, ops, 3300, tile_bits=12, batch=True)            # register-blocked
+    b, _ = _run(engine, n, ops, 3300, tile_bits=12, force=2, batch=True)     # shared-memory interpreter
+    assert_close(a.state, ora.state)
+    assert_close(b.state, ora.state)
+    assert a.max_abs_diff(b) < 1e-13
+
+
+@pytest.mark.parametrize("n", [12, 14, 17])
+def test_register_blocked_qft_and_diagonals(engine, n):
+    rng = np.random.default_rng(n)
+    ops = circuits.qft_circuit(n)
+    for _ in range(60):          # diagonal-heavy tail: RZ, CZ, controlled phases, 3-qubit diagonals on scrambled bits
+        qs = [int(x) for x in rng.permutation(n)[:3]]
+        d = np.exp(1j * rng.uniform(0, 6.28, size=8))
+        ops.append((np.diag(d), qs))
+        ops.append((np.diag(d[:4]), qs[:2]))
+        ops.append((np.diag(d[:2]), qs[:1]))
+        if rng.random() < 0.3:
+            ops.append(((np.sqrt(0.5) * np.array([[1, 1], [1, -1]])).astype(complex), [qs[2]]))
+    reg, ora = _run(engine, n, ops, 3400 + n, tile_bits=12, batch=True)
+    assert_close(reg.state, ora.state, f"v2 qft+diag n={n}")

@@ -29,16 +29,25 @@ def _plan(n, ops, tile_bits=12):
 
 
 def _check_order(ops, pass_of, order):
-    last = {}
+    """A gate WRITES its dense target qubits and only READS its controls / diagonal qubits.  Program order must
+    be kept between two gates whenever one writes a qubit the other touches (reads commute with reads)."""
+    from tests.test_dist_cpu import _dense_targets
+    last_write, last_touch = {}, {}
     for i, (m, t) in enumerate(ops):
         if pass_of[i] < 0:          # exact identity: dropped
             assert np.array_equal(np.asarray(m), np.eye(len(m)))
             continue
         key = (pass_of[i], order[i])
+        writes = set(_dense_targets(m, t))
         for q in t:
-            if q in last:
-                assert last[q] < key, f"gate {i} on qubit {q} scheduled before an earlier gate"
-            last[q] = key
+            if q in last_write:
+                assert last_write[q] < key, f"gate {i} on qubit {q} scheduled before an earlier write"
+            if q in writes and q in last_touch:
+                assert last_touch[q] < key, f"gate {i} writes qubit {q} before an earlier gate that touches it"
+        for q in t:
+            last_touch[q] = max(last_touch.get(q, key), key)
+            if q in writes:
+                last_write[q] = key
     keys = [(p, o) for p, o in zip(pass_of, order) if p >= 0]
     assert len(set(keys)) == len(keys), "two gates share a slot"
 
