@@ -7,7 +7,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libquaru_b200.so")
+LIB_PATH = os.environ.get("QUARU_B200_LIB") or os.path.join(_HERE, "lib", "libquaru_b200.so")   # env: kernel experiments
 
 QB_OK = 0
 QB_ERR_INVALID_TARGET = -1
@@ -19,7 +19,7 @@ QB_ERR_CUDA, QB_ERR_NCCL, QB_ERR_OOM, QB_ERR_NO_DEVICE, QB_ERR_UNSUPPORTED = 1, 
 
 QB_OPT_FUSION, QB_OPT_TILE_BITS, QB_OPT_MAX_QUEUE, QB_OPT_FORCE_PATH, QB_OPT_PROFILE = 1, 2, 3, 4, 5
 (QB_STAT_KERNEL_LAUNCHES, QB_STAT_PASSES, QB_STAT_GATES, QB_STAT_BYTES_MOVED, QB_STAT_SWAP_BYTES,
- QB_STAT_SWAPS, QB_STAT_TILE_LAUNCHES, QB_STAT_TILE_NS) = 1, 2, 3, 4, 5, 6, 7, 8
+ QB_STAT_SWAPS, QB_STAT_TILE_LAUNCHES, QB_STAT_TILE_NS, QB_STAT_ROUNDS) = 1, 2, 3, 4, 5, 6, 7, 8, 9
 
 
 class QbGate(ctypes.Structure):

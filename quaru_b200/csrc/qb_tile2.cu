@@ -25,11 +25,15 @@
 
 namespace qb {
 
-enum RKind : uint8_t { RK_D1 = 0, RK_X = 1, RK_D2 = 2, RK_PH = 3, RK_DG = 4 };
-enum RFlags : uint8_t { RF_REAL = 1, RF_NEG = 2 };
+// flat op codes: (kind, register bit) combinations are separate switch cases
+enum RCode : uint8_t {
+    RC_D1C = 0, RC_D1R = 4, RC_DG1R = 8,          // + register bit, no control among the register bits
+    RC_D1C_P = 16, RC_D1R_P = 20, RC_DG1R_P = 24,  // + register bit, predicated on rmask
+    RC_D2 = 32, RC_PH_T = 33, RC_PH_NEG = 34, RC_PH_R = 35, RC_DG = 36
+};
 
 struct ROp {
-    uint8_t kind;
+    uint8_t code;      // RCode
     uint8_t a, b;      // register-bit indices of the dense targets (matrix bit 0, matrix bit 1)
     uint8_t flags;
     uint16_t rmask;    // controls that are register bits (mask over the 4 register bits)
@@ -64,36 +68,85 @@ constexpr int RTHREADS = 256;
 
 __device__ __forceinline__ uint32_t swz(uint32_t l) { return l ^ (((l >> 3) ^ (l >> 6) ^ (l >> 9)) & 7u); }
 
+// ---- in-place primitives ----------------------------------------------------------------------------
+// ncu showed that compiler-scheduled updates of the loop-carried register file end every switch case with
+// up to 64 register MOVs (results computed out of place, then copied back): 45 % of all issued instructions.
+// These PTX blocks fix the update ORDER so that every result is written over a value that is already dead,
+// which lets ptxas keep each amplitude in one physical register across the whole op loop.
+__device__ __forceinline__ void ip_cmul(c64& a, const c64 f) {   // a <- f * a
+    asm volatile("{\n\t.reg .f64 t, u;\n\t"
+                 "mul.f64 t, %3, %1;\n\t"            // t = f.y * a.y
+                 "mul.f64 u, %3, %0;\n\t"            // u = f.y * a.x
+                 "neg.f64 t, t;\n\t"
+                 "fma.rn.f64 %0, %2, %0, t;\n\t"     // a.x = f.x * a.x - f.y * a.y
+                 "fma.rn.f64 %1, %2, %1, u;\n\t"     // a.y = f.x * a.y + f.y * a.x
+                 "}" : "+d"(a.x), "+d"(a.y) : "d"(f.x), "d"(f.y));
+}
+__device__ __forceinline__ void ip_pair_real(c64& a0, c64& a1, double p, double q, double r, double s) {
+    // (a0, a1) <- [[p, q], [r, s]] (a0, a1), real matrix
+    asm volatile("{\n\t.reg .f64 t, u;\n\t"
+                 "mul.f64 t, %6, %0;\n\t"            // t = r * a0.x
+                 "mul.f64 u, %6, %1;\n\t"            // u = r * a0.y
+                 "mul.f64 %0, %4, %0;\n\t"           // a0.x = p * a0.x
+                 "mul.f64 %1, %4, %1;\n\t"
+                 "fma.rn.f64 %0, %5, %2, %0;\n\t"    // a0.x += q * a1.x
+                 "fma.rn.f64 %1, %5, %3, %1;\n\t"
+                 "fma.rn.f64 %2, %7, %2, t;\n\t"     // a1.x = s * a1.x + r * a0.x(old)
+                 "fma.rn.f64 %3, %7, %3, u;\n\t"
+                 "}" : "+d"(a0.x), "+d"(a0.y), "+d"(a1.x), "+d"(a1.y) : "d"(p), "d"(q), "d"(r), "d"(s));
+}
+__device__ __forceinline__ void ip_pair_cplx(c64& a0, c64& a1, const c64 m00, const c64 m01, const c64 m10, const c64 m11) {
+    asm volatile("{\n\t.reg .f64 p, q, t, u;\n\t"
+                 "mul.f64 p, %8, %0;\n\t"            // p = m10x*a0x
+                 "mul.f64 q, %8, %1;\n\t"            // q = m10x*a0y
+                 "mul.f64 t, %5, %1;\n\t"            // t = m00y*a0y
+                 "mul.f64 u, %5, %0;\n\t"            // u = m00y*a0x
+                 "fma.rn.f64 q, %9, %0, q;\n\t"      // q += m10y*a0x
+                 "neg.f64 t, t;\n\t"
+                 "fma.rn.f64 p, %13, %1, p;\n\t"     // p -= m10y*a0y
+                 "fma.rn.f64 %0, %4, %0, t;\n\t"     // a0x = m00x*a0x - m00y*a0y
+                 "fma.rn.f64 %1, %4, %1, u;\n\t"     // a0y = m00x*a0y + m00y*a0x
+                 "fma.rn.f64 %0, %6, %2, %0;\n\t"    // a0x += m01x*a1x
+                 "fma.rn.f64 %1, %6, %3, %1;\n\t"    // a0y += m01x*a1y
+                 "fma.rn.f64 %0, %12, %3, %0;\n\t"   // a0x -= m01y*a1y
+                 "fma.rn.f64 %1, %7, %2, %1;\n\t"    // a0y += m01y*a1x
+                 "mul.f64 t, %11, %3;\n\t"           // t = m11y*a1y
+                 "mul.f64 u, %11, %2;\n\t"           // u = m11y*a1x
+                 "fma.rn.f64 %2, %10, %2, p;\n\t"    // a1x = m11x*a1x + p
+                 "fma.rn.f64 %3, %10, %3, q;\n\t"    // a1y = m11x*a1y + q
+                 "sub.f64 %2, %2, t;\n\t"
+                 "add.f64 %3, %3, u;\n\t"
+                 "}" : "+d"(a0.x), "+d"(a0.y), "+d"(a1.x), "+d"(a1.y)
+                     : "d"(m00.x), "d"(m00.y), "d"(m01.x), "d"(m01.y), "d"(m10.x), "d"(m10.y), "d"(m11.x), "d"(m11.y),
+                       "d"(-m01.y), "d"(-m10.y));
+}
+
 // ---- register-resident gate kernels (compile-time register indices) ---------------------------------
-template <int A>
-__device__ __forceinline__ void r_d1(c64 (&v)[16], const c64* __restrict__ m, uint32_t rmask, bool real) {
-    const c64 m00 = m[0], m01 = m[1], m10 = m[2], m11 = m[3];
+// PRED = false is the common case (no control among the register bits): straight-line code, no predicates.
+template <int A, bool REAL, bool PRED>
+__device__ __forceinline__ void r_d1(c64 (&v)[16], const c64* __restrict__ m, uint32_t rmask, bool act) {
+    // a thread whose thread-bit controls are not satisfied applies the identity instead of branching around
+    // the update: a divergent branch here makes the compiler copy the whole register file every iteration
+    c64 m00 = m[0], m01 = m[1], m10 = m[2], m11 = m[3];
+    if (!act) { m00 = make_double2(1.0, 0.0); m01 = make_double2(0.0, 0.0); m10 = m01; m11 = m00; }
 #pragma unroll
     for (int j0 = 0; j0 < 16; ++j0) {
         if ((j0 >> A) & 1) continue;
         const int j1 = j0 | (1 << A);
-        if ((j0 & rmask) != rmask) continue;
-        const c64 a0 = v[j0], a1 = v[j1];
-        if (real) {
-            v[j0] = make_double2(fma(m01.x, a1.x, m00.x * a0.x), fma(m01.x, a1.y, m00.x * a0.y));
-            v[j1] = make_double2(fma(m11.x, a1.x, m10.x * a0.x), fma(m11.x, a1.y, m10.x * a0.y));
-        } else {
-            v[j0] = cmul2(m00, a0, m01, a1);
-            v[j1] = cmul2(m10, a0, m11, a1);
-        }
+        if (PRED && (j0 & rmask) != rmask) continue;
+        if (REAL) ip_pair_real(v[j0], v[j1], m00.x, m01.x, m10.x, m11.x);
+        else ip_pair_cplx(v[j0], v[j1], m00, m01, m10, m11);
     }
 }
 
-template <int A>
-__device__ __forceinline__ void r_x(c64 (&v)[16], uint32_t rmask) {
+// one-qubit diagonal (RZ, phase...) on register bit A: the factor of register j is known at compile time
+template <int A, bool PRED>
+__device__ __forceinline__ void r_dg1(c64 (&v)[16], c64 d0, c64 d1, uint32_t rmask, bool act) {
+    if (!act) { d0 = make_double2(1.0, 0.0); d1 = d0; }
 #pragma unroll
-    for (int j0 = 0; j0 < 16; ++j0) {
-        if ((j0 >> A) & 1) continue;
-        const int j1 = j0 | (1 << A);
-        if ((j0 & rmask) != rmask) continue;
-        const c64 t = v[j0];
-        v[j0] = v[j1];
-        v[j1] = t;
+    for (int j = 0; j < 16; ++j) {
+        if (PRED && (j & rmask) != rmask) continue;
+        ip_cmul(v[j], ((j >> A) & 1) ? d1 : d0);
     }
 }
 
@@ -102,7 +155,7 @@ __device__ __forceinline__ void r_d2(c64 (&v)[16], const c64* __restrict__ M, ui
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
         if (((j >> A) & 1) || ((j >> B) & 1)) continue;
-        if ((j & rmask) != rmask) continue;
+        if (rmask != 0 && (j & rmask) != rmask) continue;
         const int i1 = j | (1 << A), i2 = j | (1 << B), i3 = i1 | (1 << B);
         const c64 a0 = v[j], a1 = v[i1], a2 = v[i2], a3 = v[i3];
         c64 r0 = cmul2(M[0], a0, M[1], a1);   r0 = cfma(M[2], a2, r0);   r0 = cfma(M[3], a3, r0);
@@ -188,43 +241,47 @@ __global__ void __launch_bounds__(RTHREADS, 2) k2r_tile_pass(c64* __restrict__ s
         for (uint32_t oi = rd.op_begin; oi < rd.op_end; ++oi) {
             const ROp& op = prog.ops[oi];
             if ((base & op.omask) != op.omask) continue;        // uniform per CTA
-            if ((tl & op.tmask) != op.tmask) continue;          // per thread
+            const bool act = (tl & op.tmask) == op.tmask;       // per thread; never branched on
             const uint32_t rmask = op.rmask;
             const c64* M = prog.mats + op.mat;
-            switch (op.kind) {
-                case RK_D1: {
-                    const bool real = op.flags & RF_REAL;
-                    switch (op.a) {
-                        case 0: r_d1<0>(v, M, rmask, real); break;
-                        case 1: r_d1<1>(v, M, rmask, real); break;
-                        case 2: r_d1<2>(v, M, rmask, real); break;
-                        default: r_d1<3>(v, M, rmask, real); break;
-                    }
-                } break;
-                case RK_X:
-                    switch (op.a) {
-                        case 0: r_x<0>(v, rmask); break;
-                        case 1: r_x<1>(v, rmask); break;
-                        case 2: r_x<2>(v, rmask); break;
-                        default: r_x<3>(v, rmask); break;
-                    }
+            const c64 one = make_double2(1.0, 0.0);
+            // one flat switch: nested switches would double the register traffic at the joins
+            switch (op.code) {
+#define QB_CASE4(BASE, STMT0, STMT1, STMT2, STMT3) \
+    case BASE + 0: STMT0; break;                  \
+    case BASE + 1: STMT1; break;                  \
+    case BASE + 2: STMT2; break;                  \
+    case BASE + 3: STMT3; break;
+                QB_CASE4(RC_D1C, (r_d1<0, false, false>(v, M, 0, act)), (r_d1<1, false, false>(v, M, 0, act)),
+                         (r_d1<2, false, false>(v, M, 0, act)), (r_d1<3, false, false>(v, M, 0, act)))
+                QB_CASE4(RC_D1R, (r_d1<0, true, false>(v, M, 0, act)), (r_d1<1, true, false>(v, M, 0, act)),
+                         (r_d1<2, true, false>(v, M, 0, act)), (r_d1<3, true, false>(v, M, 0, act)))
+                QB_CASE4(RC_DG1R, (r_dg1<0, false>(v, M[0], M[1], 0, act)), (r_dg1<1, false>(v, M[0], M[1], 0, act)),
+                         (r_dg1<2, false>(v, M[0], M[1], 0, act)), (r_dg1<3, false>(v, M[0], M[1], 0, act)))
+                QB_CASE4(RC_D1C_P, (r_d1<0, false, true>(v, M, rmask, act)), (r_d1<1, false, true>(v, M, rmask, act)),
+                         (r_d1<2, false, true>(v, M, rmask, act)), (r_d1<3, false, true>(v, M, rmask, act)))
+                QB_CASE4(RC_D1R_P, (r_d1<0, true, true>(v, M, rmask, act)), (r_d1<1, true, true>(v, M, rmask, act)),
+                         (r_d1<2, true, true>(v, M, rmask, act)), (r_d1<3, true, true>(v, M, rmask, act)))
+                QB_CASE4(RC_DG1R_P, (r_dg1<0, true>(v, M[0], M[1], rmask, act)), (r_dg1<1, true>(v, M[0], M[1], rmask, act)),
+                         (r_dg1<2, true>(v, M[0], M[1], rmask, act)), (r_dg1<3, true>(v, M[0], M[1], rmask, act)))
+#undef QB_CASE4
+                case RC_D2:
+                    if (act) r_d2_dispatch(v, M, op.a, op.b, rmask);   // rare: controlled 2-qubit dense gates only
                     break;
-                case RK_D2: r_d2_dispatch(v, M, op.a, op.b, rmask); break;
-                case RK_PH: {
-                    const c64 d = M[0];
-                    if (rmask == 0) {
-                        tph = cmul(d, tph);
-                    } else if (op.flags & RF_NEG) {
+                case RC_PH_T: ip_cmul(tph, act ? M[0] : one); break;
+                case RC_PH_NEG: {
+                    const double sgn = act ? -1.0 : 1.0;
 #pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            if ((j & rmask) == rmask) v[j] = make_double2(-v[j].x, -v[j].y);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            if ((j & rmask) == rmask) v[j] = cmul(d, v[j]);
-                    }
+                    for (int j = 0; j < 16; ++j)
+                        if ((j & rmask) == rmask) { v[j].x *= sgn; v[j].y *= sgn; }
                 } break;
-                default: {  // RK_DG: k <= 3 index bits from register / thread / outer bits
+                case RC_PH_R: {
+                    const c64 d = act ? M[0] : one;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if ((j & rmask) == rmask) ip_cmul(v[j], d);
+                } break;
+                default: {  // RC_DG: k <= 3 index bits from register / thread / outer bits
                     uint32_t fixed = 0, regsel = 0, ra[3] = {0, 0, 0};
 #pragma unroll
                     for (int i = 0; i < 3; ++i) {
@@ -235,18 +292,18 @@ __global__ void __launch_bounds__(RTHREADS, 2) k2r_tile_pass(c64* __restrict__ s
                         else { regsel |= 1u << i; ra[i] = s & 3u; }
                     }
                     if (regsel == 0 && rmask == 0) {
-                        tph = cmul(M[fixed], tph);
+                        ip_cmul(tph, act ? M[fixed] : one);
                     } else {
                         c64 f[8];
 #pragma unroll
-                        for (int x = 0; x < 8; ++x) f[x] = M[(fixed | (x & regsel)) & ((1u << op.k) - 1u)];
+                        for (int x = 0; x < 8; ++x) f[x] = act ? M[(fixed | (x & regsel)) & ((1u << op.k) - 1u)] : one;
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
                             if ((j & rmask) != rmask) continue;
                             const uint32_t x = (((j >> ra[0]) & 1u) | (((j >> ra[1]) & 1u) << 1) | (((j >> ra[2]) & 1u) << 2)) & regsel;
                             const c64 lo4 = (x & 2) ? ((x & 1) ? f[3] : f[2]) : ((x & 1) ? f[1] : f[0]);
                             const c64 hi4 = (x & 2) ? ((x & 1) ? f[7] : f[6]) : ((x & 1) ? f[5] : f[4]);
-                            v[j] = cmul((x & 4) ? hi4 : lo4, v[j]);
+                            ip_cmul(v[j], (x & 4) ? hi4 : lo4);
                         }
                     }
                 } break;
@@ -254,7 +311,7 @@ __global__ void __launch_bounds__(RTHREADS, 2) k2r_tile_pass(c64* __restrict__ s
         }
         if (rd.has_tph) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = cmul(tph, v[j]);
+            for (int j = 0; j < 16; ++j) ip_cmul(v[j], tph);
         }
     }
 
@@ -354,19 +411,18 @@ static bool encode_rounds(const std::vector<Gate>& gates, const std::vector<size
             if (g.kind == GK_DENSE) {
                 if (g.k == 1) {
                     op.a = (uint8_t)reg_of[local_of[g.targets[0]]];
-                    if (is_x(g)) op.kind = RK_X;
-                    else { op.kind = RK_D1; if (is_real(g)) op.flags |= RF_REAL; }
+                    const uint8_t pred = op.rmask ? 16 : 0;
+                    op.code = (uint8_t)((is_real(g) ? RC_D1R : RC_D1C) + pred + op.a);
                 } else {
-                    op.kind = RK_D2;
+                    op.code = RC_D2;
                     op.a = (uint8_t)reg_of[local_of[g.targets[0]]];
                     op.b = (uint8_t)reg_of[local_of[g.targets[1]]];
                 }
             } else if (g.k == 0) {
-                op.kind = RK_PH;
-                if (mat[0].x == -1.0 && mat[0].y == 0.0) op.flags |= RF_NEG;
-                if (op.rmask == 0) rd.has_tph = 1;
+                if (op.rmask == 0) { op.code = RC_PH_T; rd.has_tph = 1; }
+                else op.code = (mat[0].x == -1.0 && mat[0].y == 0.0) ? RC_PH_NEG : RC_PH_R;
             } else {
-                op.kind = RK_DG;
+                op.code = RC_DG;
                 op.k = (uint8_t)g.k;
                 bool any_reg = false;
                 for (uint32_t i = 0; i < g.k; ++i) {
@@ -376,6 +432,7 @@ static bool encode_rounds(const std::vector<Gate>& gates, const std::vector<size
                     else op.src[i] = (uint8_t)(0x40 | local_of[t]);
                 }
                 if (!any_reg && op.rmask == 0) rd.has_tph = 1;
+                if (g.k == 1 && any_reg) { op.a = op.src[0]; op.code = (uint8_t)((op.rmask ? RC_DG1R_P : RC_DG1R) + op.a); }
             }
             memcpy(prog->mats + n_mats, mat.data(), mat.size() * sizeof(c64));
             n_mats += mat.size();
@@ -433,6 +490,7 @@ static int launch_rpass(Reg* r, const Prog& prog) {
     if (r->profile) QB_TRY(tile_profile_end(r));
     r->st_launches++;
     r->st_passes++;
+    r->st_rounds += prog.n_rounds;
     r->st_bytes += (int64_t)(32ull << r->n_local);
     return QB_OK;
 }

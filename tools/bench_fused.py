@@ -14,14 +14,15 @@ ops = [Operation(m, t) for m, t in circuits.random_circuit(n, depth, seed=0)]
 reg = Register.new([False] * n)
 reg.set_option(2, tb)
 B = 32.0 * (1 << n)
-for fusion in (1, 0):
+modes = (1,) if (len(sys.argv) > 4 and sys.argv[4] == 'fused') else (1, 0)
+for fusion in modes:
     reg.set_option(1, fusion)
     reg.apply_batch(ops[:len(ops) // depth]); reg.sync()
-    p0, l0, b0 = reg.stat(2), reg.stat(1), reg.stat(4)
+    p0, l0, b0, r0 = reg.stat(2), reg.stat(1), reg.stat(4), reg.stat(9)
     t0 = time.time()
     reg.timer_start(); reg.apply_batch(ops); ms = reg.timer_stop()
     wall = (time.time() - t0) * 1e3
     passes = reg.stat(2) - p0
     print(f"n={n} depth={depth} T={tb} fusion={fusion}: {len(ops)} gates in {ms:.1f} ms (wall {wall:.1f}) = {len(ops) / ms * 1e3:.1f} gates/s, "
-          f"{passes} passes ({ms / passes:.2f} ms/pass), effective {len(ops) * B / ms / 1e6:.0f} GB/s, "
+          f"{passes} passes ({ms / passes:.2f} ms/pass, {reg.stat(9) - r0} rounds), effective {len(ops) * B / ms / 1e6:.0f} GB/s, "
           f"physical {(reg.stat(4) - b0) / ms / 1e6:.0f} GB/s, norm2={reg.norm2():.12f}", flush=True)
