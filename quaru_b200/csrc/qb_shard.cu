@@ -223,6 +223,11 @@ enum MapResult { MAP_LOCAL, MAP_SKIP, MAP_NEEDS_SWAP };
 
 static MapResult map_gate(const Reg* r, const Gate& g, Gate* out) {
     const uint32_t nl = r->n_local;
+    // The exchange decision must be identical on every rank (an exchange is a collective): look at the dense
+    // targets FIRST, and only then at this rank's control bits.
+    if (g.kind == GK_DENSE)
+        for (uint32_t j = 0; j < g.k; ++j)
+            if (r->phys_of[g.targets[j]] >= nl) return MAP_NEEDS_SWAP;
     // controls
     uint64_t ctrl = 0;
     for (uint64_t m = g.ctrl_mask; m; m &= m - 1) {
@@ -238,11 +243,7 @@ static MapResult map_gate(const Reg* r, const Gate& g, Gate* out) {
     out->tag = g.tag;
     if (g.kind == GK_DENSE) {
         out->targets.resize(g.k);
-        for (uint32_t j = 0; j < g.k; ++j) {
-            const uint32_t p = r->phys_of[g.targets[j]];
-            if (p >= nl) return MAP_NEEDS_SWAP;
-            out->targets[j] = p;
-        }
+        for (uint32_t j = 0; j < g.k; ++j) out->targets[j] = r->phys_of[g.targets[j]];
         out->k = g.k;
         out->matrix = g.matrix;
         return MAP_LOCAL;

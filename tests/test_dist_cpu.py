@@ -110,6 +110,23 @@ def test_schedule_replay_matches_oracle(n, world, kind):
         assert len(events) <= 6 + 1, "at most about one exchange per layer is expected"
 
 
+@pytest.mark.parametrize("world", [4, 8])
+def test_controlled_gate_between_rank_bits_keeps_ranks_in_step(world):
+    """A CNOT whose control AND target sit on rank bits: ranks where the control bit is 0 have nothing to do,
+    but the exchange is a collective, so every rank must schedule it (a hang on real GPUs otherwise)."""
+    from oracle import gates as og
+    n = 8
+    g = int(np.log2(world))
+    ops = [og.cnot(n - 1, n - 2), og.hadamard(0), og.to_controlled(og.hadamard(n - 1), n - 2), og.cz(n - 1, n - 2),
+           og.cnx([n - 1, 0], n - 2), og.swap(n - 1, n - g)]
+    per_rank = [_plan_events(n, world, r, ops) for r in range(world)]
+    assert len(per_rank[0][0]) >= 1
+    for ev, ph in per_rank[1:]:
+        assert ev == per_rank[0][0] and ph == per_rank[0][1], "ranks disagree on the exchange schedule"
+    got, want, _ = _replay(n, world, ops, per_rank[0][0], seed=77)
+    assert_close(got, want)
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
