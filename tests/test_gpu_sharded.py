@@ -28,6 +28,6 @@ def test_sharded_matches_oracle(engine, world):
         pytest.skip(f"needs {world} GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(_port()), os.path.join(ROOT, "tests", "sharded_worker.py")]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=240, cwd=ROOT)
     tail = (out.stdout + out.stderr)[-4000:]
     assert out.returncode == 0 and "SHARDED_OK" in out.stdout, tail
