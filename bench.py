@@ -251,6 +251,7 @@ def run_ours(args):
     barrier()
     l0, p0, b0 = reg.stat(_ffi.QB_STAT_KERNEL_LAUNCHES), reg.stat(_ffi.QB_STAT_PASSES), reg.stat(_ffi.QB_STAT_BYTES_MOVED)
     tl0, tn0 = reg.stat(_ffi.QB_STAT_TILE_LAUNCHES), reg.stat(_ffi.QB_STAT_TILE_NS)
+    sb0, sw0 = reg.stat(_ffi.QB_STAT_SWAP_BYTES), reg.stat(_ffi.QB_STAT_SWAPS)
     with ClockSampler(local_rank) as clk:
         barrier()
         reg.timer_start()
@@ -264,6 +265,8 @@ def run_ours(args):
     phys_bytes = reg.stat(_ffi.QB_STAT_BYTES_MOVED) - b0
     tile_launches = reg.stat(_ffi.QB_STAT_TILE_LAUNCHES) - tl0
     tile_ms = (reg.stat(_ffi.QB_STAT_TILE_NS) - tn0) / 1e6
+    swap_bytes_step = (reg.stat(_ffi.QB_STAT_SWAP_BYTES) - sb0) / args.steps
+    swaps_step = (reg.stat(_ffi.QB_STAT_SWAPS) - sw0) / args.steps
     value = n_gates * args.steps / (ms / 1e3)
     clocks = clk.summary()
 
@@ -338,8 +341,15 @@ def run_ours(args):
         "norm2_after": norm2,
     }
     if world > 1:
-        line["nvlink"] = {"swap_bytes_sent_per_gpu_per_step": reg.stat(_ffi.QB_STAT_SWAP_BYTES) / max(1, args.steps + args.warmup + args.steps),
-                          "swaps_total": reg.stat(_ffi.QB_STAT_SWAPS)}
+        # roofline of one step on one GPU: every pass streams the shard once (HBM) and every exchange sends
+        # swap_bytes over NVLink (measured peer copy 770 GB/s per direction, B200_PROFILING.md; 900 nominal)
+        nv_peak = 770.0
+        hbm_s = (passes / args.steps) * per_gpu_bytes / (peak * 1e9)
+        nv_s = swap_bytes_step / (nv_peak * 1e9)
+        line["nvlink"] = {"swap_bytes_sent_per_gpu_per_step": swap_bytes_step, "swaps_per_step": swaps_step,
+                          "peak_GBps_per_direction": nv_peak, "roofline_s_per_step": hbm_s + nv_s,
+                          "roofline_hbm_s": hbm_s, "roofline_nvlink_s": nv_s,
+                          "frac_of_roofline": (hbm_s + nv_s) / (ms / args.steps / 1e3)}
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             try:
