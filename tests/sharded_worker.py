@@ -65,7 +65,7 @@ def main():
         return swaps
 
     quick = world >= 8 or os.environ.get("QB_SHARDED_QUICK") == "1"      # bound the 8-GPU run (GPU-minutes are x8)
-    for n in ((2 * g + 2, 14) if quick else (2 * g + 2, 10, 14)):
+    for n in ((3 * g + 1, 14) if quick else (3 * g + 1, 10, 14)):
         for fusion in ((1,) if quick else (0, 1)):
             s = check(f"layers n={n} fusion={fusion}", n, circuits.random_circuit(n, 6, seed=n), fusion,
                       measure=(n - 1, 0, n // 2))
