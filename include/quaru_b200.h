@@ -42,6 +42,7 @@ typedef struct qb_reg qb_reg;
 #define QB_ERR_INVALID_ARITY (-3)      /* OperationError::InvalidArity(usize)         register.rs:17 */
 #define QB_ERR_INVALID_QUBIT (-4)      /* OperationError::InvalidQubit(usize)         register.rs:19 */
 #define QB_ERR_INVALID_ARGUMENT (-5)   /* NULL pointer / out-of-range index: a Rust panic (index OOB) in the reference */
+#define QB_ERR_QASM (-6)               /* OpenQASMError::OpenQASMParseError (openqasm.rs:27-30); payload = line */
 #define QB_ERR_CUDA 1
 #define QB_ERR_NCCL 2
 #define QB_ERR_OOM 3
@@ -168,6 +169,38 @@ int qb_get_stat(qb_reg* reg, int32_t stat, int64_t* value);
  * Returns the number of passes, or a negative error. */
 int64_t qb_plan_debug(uint32_t n, const qb_gate* gates, uint64_t count, uint32_t tile_bits,
                       int32_t* pass_of_gate, int32_t* order_in_pass);
+
+/* ---- OpenQASM 2.0 front end ------------------------------------------------------------------
+ * Replaces the un-vendored crate the reference parses with (openqasm-parser =^1.0.0, Cargo.toml:21;
+ * call sites src/openqasm.rs:53-54, 73, 91-137): source text -> register declarations + the flat list of
+ * basic operations (gate definitions inlined, register-wide statements broadcast), i.e. what
+ * `OpenQASMProgram::{qregs, cregs, get_basic_operations()}` gives the reference's interpreter loop.
+ * The loop itself (openqasm.rs:73-139) stays on the host side: the Rust `openqasm.rs` is kept as is and
+ * quaru_b200/openqasm.py mirrors it.  U parameters are f32 (BasicOp::U(f32, f32, f32, _)). */
+typedef struct qb_qasm qb_qasm;
+#define QB_QASM_U 0        /* BasicOp::U(theta, phi, lambda, qubit a)       */
+#define QB_QASM_CX 1       /* BasicOp::CX(control a, target b)              */
+#define QB_QASM_MEASURE 2  /* BasicOp::Measure(qubit a, classical bit b)    */
+#define QB_QASM_RESET_Q 3  /* BasicOp::ResetQ(qubit a)                      */
+#define QB_QASM_RESET_C 4  /* BasicOp::ResetC(classical bit a)              */
+typedef struct qb_qasm_op {
+    int32_t kind;
+    float p[3];            /* U: theta, phi, lambda */
+    int32_t reg_a, idx_a;  /* register index (declaration order) and element */
+    int32_t reg_b, idx_b;
+    int32_t cond_creg;     /* `if (creg == cond_val)`: classical register index, or -1 */
+    uint32_t cond_val;
+} qb_qasm_op;
+int qb_qasm_parse(const char* source, qb_qasm** out);  /* QB_ERR_QASM + qb_last_error() on syntax / semantic errors */
+void qb_qasm_free(qb_qasm* prog);
+uint32_t qb_qasm_num_qregs(const qb_qasm* prog);
+uint32_t qb_qasm_num_cregs(const qb_qasm* prog);
+const char* qb_qasm_qreg_name(const qb_qasm* prog, uint32_t i);
+const char* qb_qasm_creg_name(const qb_qasm* prog, uint32_t i);
+uint32_t qb_qasm_qreg_size(const qb_qasm* prog, uint32_t i);
+uint32_t qb_qasm_creg_size(const qb_qasm* prog, uint32_t i);
+uint64_t qb_qasm_num_ops(const qb_qasm* prog);
+const qb_qasm_op* qb_qasm_ops(const qb_qasm* prog);
 
 /* Dry run of the multi-GPU placement logic: the global<->local exchanges rank `rank` of `world` would
  * perform for this gate list, as a flat int32 list of records [gate index before which the exchange

@@ -22,6 +22,16 @@ QB_OPT_FUSION, QB_OPT_TILE_BITS, QB_OPT_MAX_QUEUE, QB_OPT_FORCE_PATH, QB_OPT_PRO
  QB_STAT_SWAPS, QB_STAT_TILE_LAUNCHES, QB_STAT_TILE_NS, QB_STAT_ROUNDS) = 1, 2, 3, 4, 5, 6, 7, 8, 9
 
 
+QB_ERR_QASM = -6
+QB_QASM_U, QB_QASM_CX, QB_QASM_MEASURE, QB_QASM_RESET_Q, QB_QASM_RESET_C = 0, 1, 2, 3, 4
+
+
+class QbQasmOp(ctypes.Structure):
+    _fields_ = [("kind", ctypes.c_int32), ("p", ctypes.c_float * 3), ("reg_a", ctypes.c_int32), ("idx_a", ctypes.c_int32),
+                ("reg_b", ctypes.c_int32), ("idx_b", ctypes.c_int32), ("cond_creg", ctypes.c_int32),
+                ("cond_val", ctypes.c_uint32)]
+
+
 class QbGate(ctypes.Structure):
     _fields_ = [("matrix", ctypes.POINTER(ctypes.c_double)),
                 ("targets", ctypes.POINTER(ctypes.c_uint32)),
@@ -67,6 +77,16 @@ SIGNATURES = {
     "qb_timer_stop": (ctypes.c_int, [_reg, ctypes.POINTER(ctypes.c_float)]),
     "qb_set_option": (ctypes.c_int, [_reg, ctypes.c_int32, ctypes.c_int64]),
     "qb_get_stat": (ctypes.c_int, [_reg, ctypes.c_int32, _i64p]),
+    "qb_qasm_parse": (ctypes.c_int, [ctypes.c_char_p, _regp]),
+    "qb_qasm_free": (None, [_reg]),
+    "qb_qasm_num_qregs": (ctypes.c_uint32, [_reg]),
+    "qb_qasm_num_cregs": (ctypes.c_uint32, [_reg]),
+    "qb_qasm_qreg_name": (ctypes.c_char_p, [_reg, ctypes.c_uint32]),
+    "qb_qasm_creg_name": (ctypes.c_char_p, [_reg, ctypes.c_uint32]),
+    "qb_qasm_qreg_size": (ctypes.c_uint32, [_reg, ctypes.c_uint32]),
+    "qb_qasm_creg_size": (ctypes.c_uint32, [_reg, ctypes.c_uint32]),
+    "qb_qasm_num_ops": (ctypes.c_uint64, [_reg]),
+    "qb_qasm_ops": (ctypes.POINTER(QbQasmOp), [_reg]),
     "qb_shard_plan_debug": (ctypes.c_int64, [ctypes.c_uint32, ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(QbGate),
                                              ctypes.c_uint64, _i32p, ctypes.c_uint64, _u32p]),
     "qb_plan_debug": (ctypes.c_int64, [ctypes.c_uint32, ctypes.POINTER(QbGate), ctypes.c_uint64, ctypes.c_uint32,
