@@ -29,7 +29,7 @@ namespace qb {
 enum RCode : uint8_t {
     RC_D1C = 0, RC_D1R = 4, RC_DG1R = 8,          // + register bit, no control among the register bits
     RC_D1C_P = 16, RC_D1R_P = 20, RC_DG1R_P = 24,  // + register bit, predicated on rmask
-    RC_D2 = 32, RC_PH_T = 33, RC_PH_NEG = 34, RC_PH_R = 35, RC_DG = 36
+    RC_D2 = 32, RC_PH_T = 33, RC_PH_NEG = 34, RC_PH_R = 35, RC_DG = 36, RC_DG1T = 37
 };
 
 struct ROp {
@@ -127,8 +127,8 @@ template <int A, bool REAL, bool PRED>
 __device__ __forceinline__ void r_d1(c64 (&v)[16], const c64* __restrict__ m, uint32_t rmask, bool act) {
     // a thread whose thread-bit controls are not satisfied applies the identity instead of branching around
     // the update: a divergent branch here makes the compiler copy the whole register file every iteration
-    c64 m00 = m[0], m01 = m[1], m10 = m[2], m11 = m[3];
-    if (!act) { m00 = make_double2(1.0, 0.0); m01 = make_double2(0.0, 0.0); m10 = m01; m11 = m00; }
+    (void)act;  // the caller already pointed `m` at the identity (mats[0..3]) for inactive threads
+    const c64 m00 = m[0], m01 = m[1], m10 = m[2], m11 = m[3];
 #pragma unroll
     for (int j0 = 0; j0 < 16; ++j0) {
         if ((j0 >> A) & 1) continue;
@@ -142,7 +142,7 @@ __device__ __forceinline__ void r_d1(c64 (&v)[16], const c64* __restrict__ m, ui
 // one-qubit diagonal (RZ, phase...) on register bit A: the factor of register j is known at compile time
 template <int A, bool PRED>
 __device__ __forceinline__ void r_dg1(c64 (&v)[16], c64 d0, c64 d1, uint32_t rmask, bool act) {
-    if (!act) { d0 = make_double2(1.0, 0.0); d1 = d0; }
+    (void)act;
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
         if (PRED && (j & rmask) != rmask) continue;
@@ -243,7 +243,10 @@ __global__ void __launch_bounds__(RTHREADS, 2) k2r_tile_pass(c64* __restrict__ s
             if ((base & op.omask) != op.omask) continue;        // uniform per CTA
             const bool act = (tl & op.tmask) == op.tmask;       // per thread; never branched on
             const uint32_t rmask = op.rmask;
-            const c64* M = prog.mats + op.mat;
+            // mats[0..3] holds the 2x2 identity (mats[0] = mats[3] = 1): an inactive thread reads its coefficients
+            // from there (per-thread constant-bank index) instead of selecting them register by register
+            const c64* M = prog.mats + (act ? op.mat : 0u);
+            const c64* M1 = prog.mats + (act ? op.mat : 3u);   // for two-entry diagonals: (1, 1)
             const c64 one = make_double2(1.0, 0.0);
             // one flat switch: nested switches would double the register traffic at the joins
             switch (op.code) {
@@ -256,19 +259,19 @@ __global__ void __launch_bounds__(RTHREADS, 2) k2r_tile_pass(c64* __restrict__ s
                          (r_d1<2, false, false>(v, M, 0, act)), (r_d1<3, false, false>(v, M, 0, act)))
                 QB_CASE4(RC_D1R, (r_d1<0, true, false>(v, M, 0, act)), (r_d1<1, true, false>(v, M, 0, act)),
                          (r_d1<2, true, false>(v, M, 0, act)), (r_d1<3, true, false>(v, M, 0, act)))
-                QB_CASE4(RC_DG1R, (r_dg1<0, false>(v, M[0], M[1], 0, act)), (r_dg1<1, false>(v, M[0], M[1], 0, act)),
-                         (r_dg1<2, false>(v, M[0], M[1], 0, act)), (r_dg1<3, false>(v, M[0], M[1], 0, act)))
+                QB_CASE4(RC_DG1R, (r_dg1<0, false>(v, M[0], M1[act ? 1 : 0], 0, act)), (r_dg1<1, false>(v, M[0], M1[act ? 1 : 0], 0, act)),
+                         (r_dg1<2, false>(v, M[0], M1[act ? 1 : 0], 0, act)), (r_dg1<3, false>(v, M[0], M1[act ? 1 : 0], 0, act)))
                 QB_CASE4(RC_D1C_P, (r_d1<0, false, true>(v, M, rmask, act)), (r_d1<1, false, true>(v, M, rmask, act)),
                          (r_d1<2, false, true>(v, M, rmask, act)), (r_d1<3, false, true>(v, M, rmask, act)))
                 QB_CASE4(RC_D1R_P, (r_d1<0, true, true>(v, M, rmask, act)), (r_d1<1, true, true>(v, M, rmask, act)),
                          (r_d1<2, true, true>(v, M, rmask, act)), (r_d1<3, true, true>(v, M, rmask, act)))
-                QB_CASE4(RC_DG1R_P, (r_dg1<0, true>(v, M[0], M[1], rmask, act)), (r_dg1<1, true>(v, M[0], M[1], rmask, act)),
-                         (r_dg1<2, true>(v, M[0], M[1], rmask, act)), (r_dg1<3, true>(v, M[0], M[1], rmask, act)))
+                QB_CASE4(RC_DG1R_P, (r_dg1<0, true>(v, M[0], M1[act ? 1 : 0], rmask, act)), (r_dg1<1, true>(v, M[0], M1[act ? 1 : 0], rmask, act)),
+                         (r_dg1<2, true>(v, M[0], M1[act ? 1 : 0], rmask, act)), (r_dg1<3, true>(v, M[0], M1[act ? 1 : 0], rmask, act)))
 #undef QB_CASE4
                 case RC_D2:
-                    if (act) r_d2_dispatch(v, M, op.a, op.b, rmask);   // rare: controlled 2-qubit dense gates only
+                    if (act) r_d2_dispatch(v, prog.mats + op.mat, op.a, op.b, rmask);   // rare: controlled 2-qubit dense gates only
                     break;
-                case RC_PH_T: ip_cmul(tph, act ? M[0] : one); break;
+                case RC_PH_T: ip_cmul(tph, M[0]); break;
                 case RC_PH_NEG: {
                     const double sgn = act ? -1.0 : 1.0;
 #pragma unroll
@@ -276,34 +279,36 @@ __global__ void __launch_bounds__(RTHREADS, 2) k2r_tile_pass(c64* __restrict__ s
                         if ((j & rmask) == rmask) { v[j].x *= sgn; v[j].y *= sgn; }
                 } break;
                 case RC_PH_R: {
-                    const c64 d = act ? M[0] : one;
+                    const c64 d = M[0];
 #pragma unroll
                     for (int j = 0; j < 16; ++j)
                         if ((j & rmask) == rmask) ip_cmul(v[j], d);
                 } break;
+                case RC_DG1T: {  // one-qubit diagonal (RZ...) on a thread bit or an outer bit: one multiply per thread
+                    const uint32_t s0 = op.src[0];
+                    const uint32_t bit = (s0 & 0x80) ? (uint32_t)((base >> (s0 & 0x3f)) & 1u) : ((tl >> (s0 & 0x3f)) & 1u);
+                    ip_cmul(tph, act ? prog.mats[op.mat + bit] : one);
+                } break;
                 default: {  // RC_DG: k <= 3 index bits from register / thread / outer bits
-                    uint32_t fixed = 0, regsel = 0, ra[3] = {0, 0, 0};
+                    uint32_t fixed = 0, r0 = 0, r1 = 0, r2 = 0;   // r_i: mask over the register index j that feeds index bit i
 #pragma unroll
                     for (int i = 0; i < 3; ++i) {
                         if (i >= op.k) break;
                         const uint32_t s = op.src[i];
                         if (s & 0x80) fixed |= (uint32_t)((base >> (s & 0x3f)) & 1u) << i;
                         else if (s & 0x40) fixed |= ((tl >> (s & 0x3f)) & 1u) << i;
-                        else { regsel |= 1u << i; ra[i] = s & 3u; }
+                        else if (i == 0) r0 = 1u << (s & 3u);
+                        else if (i == 1) r1 = 1u << (s & 3u);
+                        else r2 = 1u << (s & 3u);
                     }
-                    if (regsel == 0 && rmask == 0) {
-                        ip_cmul(tph, act ? M[fixed] : one);
+                    if ((r0 | r1 | r2) == 0 && rmask == 0) {
+                        ip_cmul(tph, act ? prog.mats[op.mat + fixed] : one);
                     } else {
-                        c64 f[8];
-#pragma unroll
-                        for (int x = 0; x < 8; ++x) f[x] = act ? M[(fixed | (x & regsel)) & ((1u << op.k) - 1u)] : one;
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
                             if ((j & rmask) != rmask) continue;
-                            const uint32_t x = (((j >> ra[0]) & 1u) | (((j >> ra[1]) & 1u) << 1) | (((j >> ra[2]) & 1u) << 2)) & regsel;
-                            const c64 lo4 = (x & 2) ? ((x & 1) ? f[3] : f[2]) : ((x & 1) ? f[1] : f[0]);
-                            const c64 hi4 = (x & 2) ? ((x & 1) ? f[7] : f[6]) : ((x & 1) ? f[5] : f[4]);
-                            ip_cmul(v[j], (x & 4) ? hi4 : lo4);
+                            const uint32_t x = fixed | ((j & r0) ? 1u : 0u) | ((j & r1) ? 2u : 0u) | ((j & r2) ? 4u : 0u);
+                            ip_cmul(v[j], act ? prog.mats[op.mat + x] : one);   // per-thread indexed constant load
                         }
                     }
                 } break;
@@ -371,7 +376,9 @@ static bool encode_rounds(const std::vector<Gate>& gates, const std::vector<size
     const size_t max_ops = sizeof(prog->ops) / sizeof(ROp), max_mats = sizeof(prog->mats) / sizeof(c64);
     const size_t max_rounds = sizeof(prog->rounds) / sizeof(RoundDesc);
     std::vector<char> done(ops.size(), 0);
-    size_t remaining = ops.size(), n_ops = 0, n_mats = 0, n_rounds = 0;
+    size_t remaining = ops.size(), n_ops = 0, n_mats = 4, n_rounds = 0;
+    prog->mats[0] = prog->mats[3] = make_double2(1.0, 0.0);
+    prog->mats[1] = prog->mats[2] = make_double2(0.0, 0.0);
     const uint32_t io_allowed = 0xfe0;  // tile bits 5..11: register bits of the HBM-facing rounds
     auto emit_round = [&](uint32_t R, const std::vector<size_t>& members) -> bool {
         if (n_rounds >= max_rounds) return false;
@@ -433,6 +440,7 @@ static bool encode_rounds(const std::vector<Gate>& gates, const std::vector<size
                 }
                 if (!any_reg && op.rmask == 0) rd.has_tph = 1;
                 if (g.k == 1 && any_reg) { op.a = op.src[0]; op.code = (uint8_t)((op.rmask ? RC_DG1R_P : RC_DG1R) + op.a); }
+                if (g.k == 1 && !any_reg && op.rmask == 0) op.code = RC_DG1T;
             }
             memcpy(prog->mats + n_mats, mat.data(), mat.size() * sizeof(c64));
             n_mats += mat.size();
