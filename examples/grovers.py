@@ -3,7 +3,7 @@
 (--target, --list, --statistics; grovers.rs:16-28).  The reference builds the oracle / diffuser as full
 2^n x 2^n diagonal matrices (grovers.rs:181-218), which caps it at ~12 qubits; here the same diagonals are handed
 over for n <= 12 (bit-identical inputs to the reference) and, with --decomposed (or n > 12), as multi-controlled Z
-gates (cnz, operation.rs:520), so that registers far beyond the reference's reach work.
+gates (cnz, operation.rs:520, through qb_apply_controlled: no dense matrix), so that registers far beyond the reference's reach work.
 
     python examples/grovers.py --target 64                  # n = 7, list = 0..127 (BASELINE config C1)
     python examples/grovers.py --target 123456 --qubits 24 --decomposed
@@ -39,7 +39,7 @@ def phase_flip_on(reg, n, index):
     zeros = [q for q in range(n) if not (index >> q) & 1]
     for q in zeros:
         reg.apply(op.not_(q))
-    reg.apply(op.cnz(list(range(1, n)), 0))
+    reg.apply_controlled(op.pauli_z(0), list(range(1, n)))     # cnz without the 2^n x 2^n matrix
     for q in zeros:
         reg.apply(op.not_(q))
 

@@ -96,6 +96,13 @@ uint32_t qb_num_qubits(const qb_reg* reg);
  * (payload = that target).  No unitarity is assumed. */
 int qb_apply(qb_reg* reg, const double* matrix, const uint32_t* targets, uint32_t k);
 
+/* Extension (no reference equivalent): the gate `matrix` on `targets`, applied only where every qubit in
+ * `controls` is 1 -- what operation::to_controlled / cnx / cnz (operation.rs:406, 491, 520) express by building a
+ * 2^(k+c) x 2^(k+c) matrix, without the matrix (a 30-control Z would need 2^62 entries).  Validation as qb_apply over
+ * targets followed by controls. */
+int qb_apply_controlled(qb_reg* reg, const double* matrix, const uint32_t* targets, uint32_t k,
+                        const uint32_t* controls, uint32_t n_controls);
+
 /* Register::apply_all / try_apply_all (register.rs:259-281): the 2x2 gate on every qubit.
  * The arity check (InvalidArity) belongs to the shim, which owns the Operation. */
 int qb_apply_all(qb_reg* reg, const double* m2x2);

@@ -62,6 +62,7 @@ SIGNATURES = {
     "qb_reset": (ctypes.c_int, [_reg, ctypes.c_uint64]),
     "qb_num_qubits": (ctypes.c_uint32, [_reg]),
     "qb_apply": (ctypes.c_int, [_reg, _dp, _u32p, ctypes.c_uint32]),
+    "qb_apply_controlled": (ctypes.c_int, [_reg, _dp, _u32p, ctypes.c_uint32, _u32p, ctypes.c_uint32]),
     "qb_apply_all": (ctypes.c_int, [_reg, _dp]),
     "qb_apply_batch": (ctypes.c_int, [_reg, ctypes.POINTER(QbGate), ctypes.c_uint64]),
     "qb_probabilities": (ctypes.c_int, [_reg, ctypes.c_uint32, _dp, _dp]),

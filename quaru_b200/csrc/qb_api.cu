@@ -230,6 +230,24 @@ int qb_apply(qb_reg* reg, const double* matrix, const uint32_t* targets, uint32_
     return enqueue(r, matrix, targets, k);
 }
 
+int qb_apply_controlled(qb_reg* reg, const double* matrix, const uint32_t* targets, uint32_t k, const uint32_t* controls,
+                        uint32_t n_controls) {
+    CHECK_REG(reg);
+    Reg* r = REG(reg);
+    if (!matrix) return set_error(QB_ERR_INVALID_ARGUMENT, -1, "matrix is NULL");
+    if (n_controls && !controls) return set_error(QB_ERR_INVALID_ARGUMENT, -1, "controls is NULL");
+    std::vector<uint32_t> all(targets, targets + (targets ? k : 0));
+    all.insert(all.end(), controls, controls + n_controls);
+    QB_TRY(validate_targets(r->n, all.data(), (uint32_t)all.size()));
+    Gate g;
+    r->st_gates++;
+    if (!classify_gate(matrix, targets, k, &g)) return QB_OK;
+    for (uint32_t i = 0; i < n_controls; ++i) g.ctrl_mask |= 1ull << controls[i];
+    r->queue.push_back(std::move(g));
+    if (!r->fusion || r->queue.size() >= r->max_queue) return flush(r);
+    return QB_OK;
+}
+
 // Register::try_apply_all (register.rs:267-281) == the 2x2 gate on every qubit
 int qb_apply_all(qb_reg* reg, const double* m2x2) {
     CHECK_REG(reg);

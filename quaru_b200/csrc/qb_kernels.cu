@@ -39,13 +39,13 @@ static unsigned grid_for(uint64_t items, int threads, int per_thread, int ctas_p
 // ================================================================================================
 struct InsertList {
     uint32_t cnt;
-    uint32_t pos[15];
+    uint32_t pos[40];
 };
 
 static InsertList make_inserts(uint64_t mask) {
     InsertList l;
     l.cnt = 0;
-    for (uint32_t b = 0; b < 64 && l.cnt < 15; ++b)
+    for (uint32_t b = 0; b < 64 && l.cnt < 40; ++b)
         if ((mask >> b) & 1) l.pos[l.cnt++] = b;
     return l;
 }
@@ -536,7 +536,6 @@ static int launch_1q(Reg* r, const Gate& g) {
 }
 
 int k_apply_gate_unfused(Reg* r, const Gate& g) {
-    if (g.ctrl_mask && __builtin_popcountll(g.ctrl_mask) > 14) return launch_general(r, g);
     if (r->force_path == 1) {
         if (g.kind == GK_DIAG) {  // the generic kernel takes dense matrices: expand the diagonal
             Gate d = g;

@@ -143,6 +143,18 @@ class Register:
         except OperationError as e:
             raise RuntimeError("Could not apply operation") from e
 
+    def apply_controlled(self, op, controls):
+        """Extension: `op` applied where every qubit in `controls` is 1, without building the
+        2^(k+c) x 2^(k+c) matrix of operation::to_controlled / cnx / cnz."""
+        k = len(op._targets)
+        t = (ctypes.c_uint32 * max(k, 1))(*op._targets)
+        c = (ctypes.c_uint32 * max(len(controls), 1))(*[int(x) for x in controls])
+        try:
+            _check(self._L.qb_apply_controlled(self._h, _dp(op._matrix), t, k, c, len(controls)))
+        except OperationError as e:
+            raise RuntimeError("Could not apply operation") from e
+        return self
+
     def try_apply_all(self, operation):
         """Register::try_apply_all (register.rs:267): InvalidArity unless the operation is unary."""
         if operation.arity() != 1:

@@ -35,6 +35,8 @@ extern "C" {
     pub fn qb_reset(reg: *mut qb_reg, basis_index: u64) -> c_int;
     pub fn qb_num_qubits(reg: *const qb_reg) -> u32;
     pub fn qb_apply(reg: *mut qb_reg, matrix: *const c_double, targets: *const u32, k: u32) -> c_int;
+    pub fn qb_apply_controlled(reg: *mut qb_reg, matrix: *const c_double, targets: *const u32, k: u32,
+                               controls: *const u32, n_controls: u32) -> c_int;
     pub fn qb_apply_all(reg: *mut qb_reg, m2x2: *const c_double) -> c_int;
     pub fn qb_apply_batch(reg: *mut qb_reg, gates: *const qb_gate, count: u64) -> c_int;
     pub fn qb_probabilities(reg: *mut qb_reg, target: u32, p0: *mut c_double, p1: *mut c_double) -> c_int;

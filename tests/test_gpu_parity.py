@@ -272,3 +272,31 @@ def test_larger_registers(engine, n):
     u = float(rng.random())
     assert reg.measure(n - 1, u=u) == ora.measure(n - 1, u)
     assert_close(reg.state, ora.state, f"n={n} collapsed")
+
+
+@pytest.mark.parametrize("fusion", [0, 1])
+def test_apply_controlled_equals_dense_controlled_matrix(engine, fusion):
+    """qb_apply_controlled == the reference's dense construction (to_controlled / cnx / cnz, operation.rs:406-536)."""
+    rng = np.random.default_rng(4)
+    for n in [3, 6, 9, 13]:
+        reg, ora = _pair(engine, n, 1300 + n, fusion=fusion)
+        for _ in range(12):
+            nc = int(rng.integers(1, min(n, 6)))
+            k = int(rng.integers(1, min(n - nc, 2) + 1))
+            qs = [int(x) for x in rng.permutation(n)[:nc + k]]
+            targets, controls = qs[:k], qs[k:]
+            m = random_matrix(k, int(rng.integers(1 << 30)), unitary=True)
+            reg.apply_controlled(engine.Operation(m, targets), controls)
+            big = (m, targets)
+            for c in controls:
+                big = og.to_controlled(big, c)
+            ora.apply(big)
+        # many controls: Z controlled by all other qubits == cnz
+        reg.apply_controlled(engine.operation.pauli_z(0), list(range(1, n)))
+        ora.apply(og.cnz(list(range(1, n)), 0))
+        assert_close(reg.state, ora.state, f"n={n}")
+    reg5 = engine.Register.new([False] * 5)
+    with pytest.raises(RuntimeError, match="Could not apply operation"):
+        reg5.apply_controlled(engine.operation.not_(1), [1])            # control == target
+    with pytest.raises(RuntimeError, match="Could not apply operation"):
+        reg5.apply_controlled(engine.operation.not_(1), [7])
