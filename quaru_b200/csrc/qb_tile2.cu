@@ -29,7 +29,8 @@ namespace qb {
 enum RCode : uint8_t {
     RC_D1C = 0, RC_D1R = 4, RC_DG1R = 8,          // + register bit, no control among the register bits
     RC_D1C_P = 16, RC_D1R_P = 20, RC_DG1R_P = 24,  // + register bit, predicated on rmask
-    RC_D2 = 32, RC_PH_T = 33, RC_PH_NEG = 34, RC_PH_R = 35, RC_DG = 36, RC_DG1T = 37
+    RC_D2 = 32, RC_PH_T = 33, RC_PH_NEG = 34, RC_PH_R = 35, RC_DG = 36, RC_DG1T = 37,
+    RC_H = 40                                      // + register bit: scalar multiple of the Hadamard matrix, uncontrolled
 };
 
 struct ROp {
@@ -119,6 +120,46 @@ __device__ __forceinline__ void ip_pair_cplx(c64& a0, c64& a1, const c64 m00, co
                  "}" : "+d"(a0.x), "+d"(a0.y), "+d"(a1.x), "+d"(a1.y)
                      : "d"(m00.x), "d"(m00.y), "d"(m01.x), "d"(m01.y), "d"(m10.x), "d"(m10.y), "d"(m11.x), "d"(m11.y),
                        "d"(-m01.y), "d"(-m10.y));
+}
+
+__device__ __forceinline__ void ip_pair_h(c64& a0, c64& a1) {
+    // (a0, a1) <- (a0 + a1, a0 - a1): two FP64 instructions per component; the common scalar (1/sqrt 2) of the
+    // Hadamard matrix is deferred into the per-thread phase of the round
+    asm volatile("{\n\t"
+                 "add.f64 %0, %0, %2;\n\t"           // a0.x = a0.x + a1.x
+                 "add.f64 %1, %1, %3;\n\t"
+                 "fma.rn.f64 %2, %2, 0dC000000000000000, %0;\n\t"   // a1.x = (a0.x + a1.x) - 2 a1.x = a0.x - a1.x up to the rounding of the sum
+                 "fma.rn.f64 %3, %3, 0dC000000000000000, %1;\n\t"
+                 "}" : "+d"(a0.x), "+d"(a0.y), "+d"(a1.x), "+d"(a1.y));
+}
+
+template <int A>
+__device__ __forceinline__ void r_h(c64 (&v)[16]) {
+#pragma unroll
+    for (int j0 = 0; j0 < 16; ++j0) {
+        if ((j0 >> A) & 1) continue;
+        ip_pair_h(v[j0], v[j0 | (1 << A)]);
+    }
+}
+
+// phase on the registers whose index contains the (compile-time) mask RM
+template <int RM, bool NEG>
+__device__ __forceinline__ void r_ph(c64 (&v)[16], const c64 d, const double sgn) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        if ((j & RM) != RM) continue;
+        if (NEG) { v[j].x *= sgn; v[j].y *= sgn; } else ip_cmul(v[j], d);
+    }
+}
+template <bool NEG>
+__device__ __forceinline__ void r_ph_dispatch(c64 (&v)[16], uint32_t rmask, const c64 d, const double sgn) {
+    switch (rmask) {
+        case 1: r_ph<1, NEG>(v, d, sgn); break;   case 2: r_ph<2, NEG>(v, d, sgn); break;   case 3: r_ph<3, NEG>(v, d, sgn); break;
+        case 4: r_ph<4, NEG>(v, d, sgn); break;   case 5: r_ph<5, NEG>(v, d, sgn); break;   case 6: r_ph<6, NEG>(v, d, sgn); break;
+        case 7: r_ph<7, NEG>(v, d, sgn); break;   case 8: r_ph<8, NEG>(v, d, sgn); break;   case 9: r_ph<9, NEG>(v, d, sgn); break;
+        case 10: r_ph<10, NEG>(v, d, sgn); break; case 11: r_ph<11, NEG>(v, d, sgn); break; case 12: r_ph<12, NEG>(v, d, sgn); break;
+        case 13: r_ph<13, NEG>(v, d, sgn); break; case 14: r_ph<14, NEG>(v, d, sgn); break; default: r_ph<15, NEG>(v, d, sgn); break;
+    }
 }
 
 // ---- register-resident gate kernels (compile-time register indices) ---------------------------------
@@ -272,18 +313,12 @@ __global__ void __launch_bounds__(RTHREADS, 2) k2r_tile_pass(c64* __restrict__ s
                     if (act) r_d2_dispatch(v, prog.mats + op.mat, op.a, op.b, rmask);   // rare: controlled 2-qubit dense gates only
                     break;
                 case RC_PH_T: ip_cmul(tph, M[0]); break;
-                case RC_PH_NEG: {
-                    const double sgn = act ? -1.0 : 1.0;
-#pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if ((j & rmask) == rmask) { v[j].x *= sgn; v[j].y *= sgn; }
-                } break;
-                case RC_PH_R: {
-                    const c64 d = M[0];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if ((j & rmask) == rmask) ip_cmul(v[j], d);
-                } break;
+                case RC_PH_NEG: r_ph_dispatch<true>(v, rmask, one, act ? -1.0 : 1.0); break;
+                case RC_PH_R: r_ph_dispatch<false>(v, rmask, M[0], 1.0); break;
+                case RC_H + 0: r_h<0>(v); tph.x *= M[0].x; tph.y *= M[0].x; break;   // uncontrolled by construction
+                case RC_H + 1: r_h<1>(v); tph.x *= M[0].x; tph.y *= M[0].x; break;
+                case RC_H + 2: r_h<2>(v); tph.x *= M[0].x; tph.y *= M[0].x; break;
+                case RC_H + 3: r_h<3>(v); tph.x *= M[0].x; tph.y *= M[0].x; break;
                 case RC_DG1T: {  // one-qubit diagonal (RZ...) on a thread bit or an outer bit: one multiply per thread
                     const uint32_t s0 = op.src[0];
                     const uint32_t bit = (s0 & 0x80) ? (uint32_t)((base >> (s0 & 0x3f)) & 1u) : ((tl >> (s0 & 0x3f)) & 1u);
@@ -343,6 +378,11 @@ static bool is_real(const Gate& g) {
     for (const c64& e : g.matrix)
         if (e.y != 0.0) return false;
     return true;
+}
+static bool is_scaled_hadamard(const Gate& g) {   // s * [[1, 1], [1, -1]] with real s (operation::hadamard, operation.rs:350)
+    if (g.k != 1 || !is_real(g)) return false;
+    const double s = g.matrix[0].x;
+    return s != 0.0 && g.matrix[1].x == s && g.matrix[2].x == s && g.matrix[3].x == -s;
 }
 static bool is_x(const Gate& g) {
     return g.k == 1 && g.matrix[0].x == 0.0 && g.matrix[0].y == 0.0 && g.matrix[3].x == 0.0 && g.matrix[3].y == 0.0 &&
@@ -420,6 +460,7 @@ static bool encode_rounds(const std::vector<Gate>& gates, const std::vector<size
                     op.a = (uint8_t)reg_of[local_of[g.targets[0]]];
                     const uint8_t pred = op.rmask ? 16 : 0;
                     op.code = (uint8_t)((is_real(g) ? RC_D1R : RC_D1C) + pred + op.a);
+                    if (is_scaled_hadamard(g) && !op.rmask && !op.tmask && !op.omask) { op.code = (uint8_t)(RC_H + op.a); rd.has_tph = 1; }
                 } else {
                     op.code = RC_D2;
                     op.a = (uint8_t)reg_of[local_of[g.targets[0]]];
