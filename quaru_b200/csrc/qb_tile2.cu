@@ -30,7 +30,9 @@ enum RCode : uint8_t {
     RC_D1C = 0, RC_D1R = 4, RC_DG1R = 8,          // + register bit, no control among the register bits
     RC_D1C_P = 16, RC_D1R_P = 20, RC_DG1R_P = 24,  // + register bit, predicated on rmask
     RC_D2 = 32, RC_PH_T = 33, RC_PH_NEG = 34, RC_PH_R = 35, RC_DG = 36, RC_DG1T = 37,
-    RC_H = 40                                      // + register bit: scalar multiple of the Hadamard matrix, uncontrolled
+    RC_H = 40,                                     // + register bit: scalar multiple of the Hadamard matrix, uncontrolled
+    RC_PH_ACC = 44,                                // phase whose only register-bit control is one bit: accumulate per thread ...
+    RC_PH_FLUSH = 48                               // + register bit: ... and apply the product to the 8 registers with that bit set
 };
 
 struct ROp {
@@ -279,6 +281,7 @@ __global__ void __launch_bounds__(RTHREADS, 2) k2r_tile_pass(c64* __restrict__ s
             __syncthreads();
         }
         c64 tph = make_double2(1.0, 0.0);
+        c64 racc = make_double2(1.0, 0.0);   // running product of a chain of phases controlled by the same register bit
         for (uint32_t oi = rd.op_begin; oi < rd.op_end; ++oi) {
             const ROp& op = prog.ops[oi];
             if ((base & op.omask) != op.omask) continue;        // uniform per CTA
@@ -315,6 +318,11 @@ __global__ void __launch_bounds__(RTHREADS, 2) k2r_tile_pass(c64* __restrict__ s
                 case RC_PH_T: ip_cmul(tph, M[0]); break;
                 case RC_PH_NEG: r_ph_dispatch<true>(v, rmask, one, act ? -1.0 : 1.0); break;
                 case RC_PH_R: r_ph_dispatch<false>(v, rmask, M[0], 1.0); break;
+                case RC_PH_ACC: ip_cmul(racc, M[0]); break;       // M is the identity slot for inactive threads
+                case RC_PH_FLUSH + 0: r_ph<1, false>(v, racc, 1.0); racc = one; break;
+                case RC_PH_FLUSH + 1: r_ph<2, false>(v, racc, 1.0); racc = one; break;
+                case RC_PH_FLUSH + 2: r_ph<4, false>(v, racc, 1.0); racc = one; break;
+                case RC_PH_FLUSH + 3: r_ph<8, false>(v, racc, 1.0); racc = one; break;
                 case RC_H + 0: r_h<0>(v); tph.x *= M[0].x; tph.y *= M[0].x; break;   // uncontrolled by construction
                 case RC_H + 1: r_h<1>(v); tph.x *= M[0].x; tph.y *= M[0].x; break;
                 case RC_H + 2: r_h<2>(v); tph.x *= M[0].x; tph.y *= M[0].x; break;
@@ -486,6 +494,58 @@ static bool encode_rounds(const std::vector<Gate>& gates, const std::vector<size
             memcpy(prog->mats + n_mats, mat.data(), mat.size() * sizeof(c64));
             n_mats += mat.size();
             prog->ops[n_ops++] = op;
+        }
+        // Chains of phases whose only register-bit control is the same single bit b (the controlled-phase cascade
+        // of a QFT: CP(c_i, t) for many c_i) accumulate into one per-thread factor and touch the registers once.
+        // Diagonal ops commute, so only an op that WRITES register bit b ends a chain.
+        {
+            std::vector<ROp> in(prog->ops + rd.op_begin, prog->ops + n_ops), out;
+            auto single_bit = [](const ROp& o) -> int {
+                if ((o.code != RC_PH_R && o.code != RC_PH_NEG) || __builtin_popcount(o.rmask) != 1) return -1;
+                return __builtin_ctz(o.rmask);
+            };
+            auto writes_bit = [](const ROp& o, int b) {
+                const int c = o.code;
+                if (c == RC_D2) return o.a == b || o.b == b;
+                const bool d1 = c < RC_D2 || (c >= RC_H && c < RC_H + 4);
+                return d1 && (c & 3) == b && !(c >= RC_DG1R && c < RC_DG1R + 4) && !(c >= RC_DG1R_P && c < RC_DG1R_P + 4);
+            };
+            // run length of the chain starting at i for bit b
+            auto chain_len = [&](size_t i, int b) {
+                size_t cnt = 0;
+                for (size_t j = i; j < in.size(); ++j) {
+                    if (single_bit(in[j]) == b) ++cnt;
+                    else if (writes_bit(in[j], b)) break;
+                }
+                return cnt;
+            };
+            int cb = -1;
+            auto flush = [&]() {
+                if (cb < 0) return;
+                ROp f;
+                memset(&f, 0, sizeof(f));
+                f.code = (uint8_t)(RC_PH_FLUSH + cb);
+                out.push_back(f);
+                cb = -1;
+            };
+            for (size_t i = 0; i < in.size(); ++i) {
+                const int b = single_bit(in[i]);
+                if (b >= 0 && (cb == b || chain_len(i, b) >= 3)) {
+                    if (cb != b) flush();
+                    cb = b;
+                    ROp a = in[i];
+                    a.code = RC_PH_ACC;   // the -1 of RC_PH_NEG is already the coefficient at `mat`
+                    a.rmask = 0;
+                    out.push_back(a);
+                    continue;
+                }
+                if (cb >= 0 && writes_bit(in[i], cb)) flush();
+                out.push_back(in[i]);
+            }
+            flush();
+            if (rd.op_begin + out.size() > max_ops) return false;
+            n_ops = rd.op_begin;
+            for (const ROp& o : out) prog->ops[n_ops++] = o;
         }
         rd.op_end = (uint16_t)n_ops;
         ++n_rounds;
