@@ -11,15 +11,17 @@
 
 namespace qb {
 
-static int g_num_sms = 0;
-static int num_sms() {
-    if (!g_num_sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-        if (g_num_sms <= 0) g_num_sms = 148;
+static int num_sms() {  // of the current device (every entry point makes the handle's device current)
+    static thread_local int cached_dev = -1, cached = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev != cached_dev) {
+        cached = 0;
+        cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev);
+        if (cached <= 0) cached = 148;
+        cached_dev = dev;
     }
-    return g_num_sms;
+    return cached;
 }
 
 // grid for a grid-stride kernel: enough CTAs to cover `items` with `per_thread` items each, capped

@@ -14,6 +14,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 
 #include "qb_common.h"
 #include "qb_device.cuh"
@@ -280,10 +281,10 @@ static bool encode_pass(const std::vector<Gate>& gates, const PlannedPass& pass,
 template <class Prog>
 static int launch_pass(Reg* r, const Prog& prog) {
     const size_t smem = sizeof(c64) << prog.tile_bits;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static std::atomic<uint64_t> attr_devs{0};  // per-device function attribute (bit d = set on device d)
+    if (!((attr_devs.load() >> (r->device & 63)) & 1)) {
         QB_CUDA(cudaFuncSetAttribute(k2_tile_pass<Prog>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 << 13));
-        attr_set = true;
+        attr_devs.fetch_or(1ull << (r->device & 63));
     }
     const uint64_t tiles = 1ull << (r->n_local - prog.tile_bits);
     if (tiles > 0x7fffffffull) return set_error(QB_ERR_UNSUPPORTED, (int64_t)tiles, "too many tiles for one grid");
@@ -332,7 +333,7 @@ int run_fused(Reg* r, std::vector<Gate>& gates) {
     const int max_ops = (int)(sizeof(PassLarge::ops) / sizeof(TileOp));
     const int max_mats = (int)(sizeof(PassLarge::mats) / sizeof(c64));
     plan_passes(gates, r->n_local, r->tile_bits, max_ops, max_mats, &passes);
-    static PassLarge large;  // host staging (single-threaded per handle; copied by value at launch)
+    static thread_local PassLarge large;  // host staging; thread_local: different handles may run on different threads
     for (const PlannedPass& p : passes) {
         if (p.unfused) {
             QB_TRY(k_apply_gate_unfused(r, gates[p.gate_idx[0]]));

@@ -18,6 +18,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 
 #include "qb_common.h"
 #include "qb_device.cuh"
@@ -586,10 +587,10 @@ static bool encode_rounds(const std::vector<Gate>& gates, const std::vector<size
 
 template <class Prog>
 static int launch_rpass(Reg* r, const Prog& prog) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static std::atomic<uint64_t> attr_devs{0};  // per-device function attribute (bit d = set on device d)
+    if (!((attr_devs.load() >> (r->device & 63)) & 1)) {
         QB_CUDA(cudaFuncSetAttribute(k2r_tile_pass<Prog>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(c64) << RT)));
-        attr_set = true;
+        attr_devs.fetch_or(1ull << (r->device & 63));
     }
     const uint64_t tiles = 1ull << (r->n_local - RT);
     if (tiles > 0x7fffffffull) return set_error(QB_ERR_UNSUPPORTED, (int64_t)tiles, "too many tiles for one grid");
@@ -618,7 +619,7 @@ int run_pass_v2(Reg* r, const std::vector<Gate>& gates, const std::vector<size_t
             return launch_rpass(r, small);
         }
     }
-    static RProgLarge large;
+    static thread_local RProgLarge large;
     if (!encode_rounds(gates, gate_idx, tile_pos, lc, &large)) return QB_OK;
     *handled = true;
     return launch_rpass(r, large);
