@@ -54,12 +54,15 @@ struct RoundDesc {
     uint8_t tb[8];     // thread-id bit i <-> tile-local bit tb[i]
     uint16_t op_begin, op_end;
     uint8_t has_tph, pad[3];
+    uint16_t sro[16];  // swizzled shared-memory offset of register j (host-computed: uniform, ~270 instructions per
+                       // thread and transpose when derived on the device)
 };
 
 template <int NOPS, int NMAT, int NROUNDS>
 struct RProgram {
     uint32_t lc, h, n_rounds, pad;
     uint8_t hp[8];
+    uint64_t gro_first[16], gro_last[16];  // offset from the tile base of register j in the first / last round
     RoundDesc rounds[NROUNDS];
     ROp ops[NOPS];
     c64 mats[NMAT];
@@ -246,39 +249,32 @@ __global__ void __launch_bounds__(RTHREADS, 2) k2r_tile_pass(c64* __restrict__ s
 
     c64 v[16];
     uint32_t tl = 0;          // this thread's tile-local index bits (register bits are 0)
-    uint32_t rb[4];           // 1 << R[i]
     auto set_mapping = [&](const RoundDesc& rd) {
         tl = 0;
 #pragma unroll
         for (int i = 0; i < 8; ++i) tl |= ((tid >> i) & 1u) << rd.tb[i];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) rb[i] = 1u << rd.R[i];
-    };
-    auto roff = [&](int j) -> uint32_t {
-        return ((j & 1) ? rb[0] : 0u) | ((j & 2) ? rb[1] : 0u) | ((j & 4) ? rb[2] : 0u) | ((j & 8) ? rb[3] : 0u);
     };
 
     // ---- round 0: HBM -> registers ------------------------------------------------------------------
     set_mapping(prog.rounds[0]);
     {
         const uint64_t gt = base + goff(tl);
-        const uint64_t g0 = goff(rb[0]), g1 = goff(rb[1]), g2 = goff(rb[2]), g3 = goff(rb[3]);
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-            v[j] = ld128(st + (gt + ((j & 1) ? g0 : 0) + ((j & 2) ? g1 : 0) + ((j & 4) ? g2 : 0) + ((j & 8) ? g3 : 0)));
+        for (int j = 0; j < 16; ++j) v[j] = ld128(st + (gt + prog.gro_first[j]));
     }
 
     for (uint32_t r = 0; r < prog.n_rounds; ++r) {
         const RoundDesc& rd = prog.rounds[r];
         if (r > 0) {  // transpose through shared memory into the new register bits
             const uint32_t s_t = swz(tl);
+            const RoundDesc& prev = prog.rounds[r - 1];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) tile[s_t ^ swz(roff(j))] = v[j];
+            for (int j = 0; j < 16; ++j) tile[s_t ^ prev.sro[j]] = v[j];
             __syncthreads();
             set_mapping(rd);
             const uint32_t s_n = swz(tl);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = tile[s_n ^ swz(roff(j))];
+            for (int j = 0; j < 16; ++j) v[j] = tile[s_n ^ rd.sro[j]];
             __syncthreads();
         }
         c64 tph = make_double2(1.0, 0.0);
@@ -367,10 +363,8 @@ __global__ void __launch_bounds__(RTHREADS, 2) k2r_tile_pass(c64* __restrict__ s
     // ---- last round: registers -> HBM -----------------------------------------------------------------
     {
         const uint64_t gt = base + goff(tl);
-        const uint64_t g0 = goff(rb[0]), g1 = goff(rb[1]), g2 = goff(rb[2]), g3 = goff(rb[3]);
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-            st128(st + (gt + ((j & 1) ? g0 : 0) + ((j & 2) ? g1 : 0) + ((j & 4) ? g2 : 0) + ((j & 8) ? g3 : 0)), v[j]);
+        for (int j = 0; j < 16; ++j) st128(st + (gt + prog.gro_last[j]), v[j]);
     }
 }
 
@@ -450,6 +444,12 @@ static bool encode_rounds(const std::vector<Gate>& gates, const std::vector<size
             if (std::find(order.begin(), order.end(), b) == order.end()) order.push_back(b);
         if ((R & ~io_allowed) == 0) order = free_bits;  // bits 0,1,2 first anyway (distinct classes) and lanes = 0..4
         for (int i = 0; i < 8; ++i) rd.tb[i] = (uint8_t)order[i];
+        for (uint32_t j = 0; j < 16; ++j) {
+            uint32_t l = 0;
+            for (uint32_t i = 0; i < 4; ++i)
+                if ((j >> i) & 1) l |= 1u << rd.R[i];
+            rd.sro[j] = (uint16_t)(l ^ (((l >> 3) ^ (l >> 6) ^ (l >> 9)) & 7u));
+        }
         rd.op_begin = (uint16_t)n_ops;
         for (size_t oi : members) {
             const LocalOp& lo = ops[oi];
@@ -582,6 +582,18 @@ static bool encode_rounds(const std::vector<Gate>& gates, const std::vector<size
         if (!emit_round(0xf00, {})) return false;
     }
     prog->n_rounds = (uint32_t)n_rounds;
+    auto goff_host = [&](uint32_t x) {
+        uint64_t o = x & ((1u << lc) - 1u);
+        for (uint32_t i = 0; i < prog->h; ++i) o |= (uint64_t)((x >> (lc + i)) & 1u) << prog->hp[i];
+        return o;
+    };
+    for (uint32_t j = 0; j < 16; ++j) {
+        uint32_t lf = 0, ll = 0;
+        for (uint32_t i = 0; i < 4; ++i)
+            if ((j >> i) & 1) { lf |= 1u << prog->rounds[0].R[i]; ll |= 1u << prog->rounds[n_rounds - 1].R[i]; }
+        prog->gro_first[j] = goff_host(lf);
+        prog->gro_last[j] = goff_host(ll);
+    }
     return true;
 }
 
