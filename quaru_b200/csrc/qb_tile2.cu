@@ -45,7 +45,7 @@ struct ROp {
     uint32_t mat;      // offset into mats
     uint8_t src[3];    // RK_DG: source of index bit i: 0x00|reg bit, 0x40|tile-local bit (thread), 0x80|global bit (outer)
     uint8_t k;         // RK_DG: number of index bits (1..3)
-    uint64_t omask;    // controls outside the tile (global bit mask)
+    uint64_t omask;    // controls outside the tile, in TILE-INDEX space (bit i = i-th non-tile bit = bit i of blockIdx.x)
 };
 static_assert(sizeof(ROp) == 24, "ROp layout");
 
@@ -281,7 +281,7 @@ __global__ void __launch_bounds__(RTHREADS, 2) k2r_tile_pass(c64* __restrict__ s
         c64 racc = make_double2(1.0, 0.0);   // running product of a chain of phases controlled by the same register bit
         for (uint32_t oi = rd.op_begin; oi < rd.op_end; ++oi) {
             const ROp& op = prog.ops[oi];
-            if ((base & op.omask) != op.omask) continue;        // uniform per CTA
+            if (((uint64_t)blockIdx.x & op.omask) != op.omask) continue;   // uniform per CTA; blockIdx needs no live register
             const bool act = (tl & op.tmask) == op.tmask;       // per thread; never branched on
             const uint32_t rmask = op.rmask;
             // mats[0..3] holds the 2x2 identity (mats[0] = mats[3] = 1): an inactive thread reads its coefficients
@@ -326,7 +326,7 @@ __global__ void __launch_bounds__(RTHREADS, 2) k2r_tile_pass(c64* __restrict__ s
                 case RC_H + 3: r_h<3>(v); tph.x *= M[0].x; tph.y *= M[0].x; break;
                 case RC_DG1T: {  // one-qubit diagonal (RZ...) on a thread bit or an outer bit: one multiply per thread
                     const uint32_t s0 = op.src[0];
-                    const uint32_t bit = (s0 & 0x80) ? (uint32_t)((base >> (s0 & 0x3f)) & 1u) : ((tl >> (s0 & 0x3f)) & 1u);
+                    const uint32_t bit = (s0 & 0x80) ? ((blockIdx.x >> (s0 & 0x3f)) & 1u) : ((tl >> (s0 & 0x3f)) & 1u);
                     ip_cmul(tph, act ? prog.mats[op.mat + bit] : one);
                 } break;
                 default: {  // RC_DG: k <= 3 index bits from register / thread / outer bits
@@ -335,7 +335,7 @@ __global__ void __launch_bounds__(RTHREADS, 2) k2r_tile_pass(c64* __restrict__ s
                     for (int i = 0; i < 3; ++i) {
                         if (i >= op.k) break;
                         const uint32_t s = op.src[i];
-                        if (s & 0x80) fixed |= (uint32_t)((base >> (s & 0x3f)) & 1u) << i;
+                        if (s & 0x80) fixed |= ((blockIdx.x >> (s & 0x3f)) & 1u) << i;
                         else if (s & 0x40) fixed |= ((tl >> (s & 0x3f)) & 1u) << i;
                         else if (i == 0) r0 = 1u << (s & 3u);
                         else if (i == 1) r1 = 1u << (s & 3u);
@@ -405,6 +405,17 @@ static bool encode_rounds(const std::vector<Gate>& gates, const std::vector<size
     prog->h = T - lc;
     for (uint32_t j = 0; j < prog->h; ++j) prog->hp[j] = (uint8_t)tile_pos[lc + j];
 
+    // outer (non-tile) global bit -> its rank among the non-tile bits = its bit position in blockIdx.x
+    int8_t outer_ix[64];
+    {
+        int nx = 0;
+        for (int b = 0; b < 64; ++b) outer_ix[b] = ((tile_mask >> b) & 1) ? (int8_t)-1 : (int8_t)nx++;
+    }
+    auto to_tile_space = [&](uint64_t gmask) {
+        uint64_t o = 0;
+        for (uint64_t m = gmask; m; m &= m - 1) o |= 1ull << outer_ix[__builtin_ctzll(m)];
+        return o;
+    };
     std::vector<LocalOp> ops;
     for (size_t gi : gate_idx) {
         const Gate& g = gates[gi];
@@ -458,7 +469,7 @@ static bool encode_rounds(const std::vector<Gate>& gates, const std::vector<size
             ROp op;
             memset(&op, 0, sizeof(op));
             op.mat = (uint32_t)n_mats;
-            op.omask = g.ctrl_mask & ~tile_mask;
+            op.omask = to_tile_space(g.ctrl_mask & ~tile_mask);
             for (uint64_t m = g.ctrl_mask & tile_mask; m; m &= m - 1) {
                 const uint32_t lb = (uint32_t)local_of[__builtin_ctzll(m)];
                 if (reg_of[lb] != 99) op.rmask |= (uint16_t)(1u << reg_of[lb]); else op.tmask |= (uint16_t)(1u << lb);
@@ -484,7 +495,7 @@ static bool encode_rounds(const std::vector<Gate>& gates, const std::vector<size
                 bool any_reg = false;
                 for (uint32_t i = 0; i < g.k; ++i) {
                     const uint32_t t = g.targets[i];
-                    if (local_of[t] < 0) op.src[i] = (uint8_t)(0x80 | t);
+                    if (local_of[t] < 0) op.src[i] = (uint8_t)(0x80 | outer_ix[t]);
                     else if (reg_of[local_of[t]] != 99) { op.src[i] = (uint8_t)reg_of[local_of[t]]; any_reg = true; }
                     else op.src[i] = (uint8_t)(0x40 | local_of[t]);
                 }
