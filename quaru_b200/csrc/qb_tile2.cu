@@ -33,7 +33,8 @@ enum RCode : uint8_t {
     RC_D2 = 32, RC_PH_T = 33, RC_PH_NEG = 34, RC_PH_R = 35, RC_DG = 36, RC_DG1T = 37,
     RC_H = 40,                                     // + register bit: scalar multiple of the Hadamard matrix, uncontrolled
     RC_PH_ACC = 44,                                // phase whose only register-bit control is one bit: accumulate per thread ...
-    RC_PH_FLUSH = 48                               // + register bit: ... and apply the product to the 8 registers with that bit set
+    RC_PH_FLUSH = 48,                              // + register bit: ... and apply the product to the 8 registers with that bit set
+    RC_TAB = 52, RC_TAB_ACC = 53                   // merged thread-uniform phases: table over <= 4 thread / outer bits -> tph / racc
 };
 
 struct ROp {
@@ -316,6 +317,19 @@ __global__ void __launch_bounds__(RTHREADS, 2) k2r_tile_pass(c64* __restrict__ s
                 case RC_PH_NEG: r_ph_dispatch<true>(v, rmask, one, act ? -1.0 : 1.0); break;
                 case RC_PH_R: r_ph_dispatch<false>(v, rmask, M[0], 1.0); break;
                 case RC_PH_ACC: ip_cmul(racc, M[0]); break;       // M is the identity slot for inactive threads
+                case RC_TAB:
+                case RC_TAB_ACC: {   // host-merged phases: index a table with up to 4 thread / outer bits
+                    const uint32_t sel[4] = {op.src[0], op.src[1], op.src[2], op.b};
+                    uint32_t idx = 0;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        if (i >= op.k) break;
+                        const uint32_t sc = sel[i];
+                        idx |= (((sc & 0x80) ? (blockIdx.x >> (sc & 0x3f)) : (tl >> (sc & 0x3f))) & 1u) << i;
+                    }
+                    const c64 f = prog.mats[op.mat + idx];
+                    if (op.code == RC_TAB) ip_cmul(tph, f); else ip_cmul(racc, f);
+                } break;
                 case RC_PH_FLUSH + 0: r_ph<1, false>(v, racc, 1.0); racc = one; break;
                 case RC_PH_FLUSH + 1: r_ph<2, false>(v, racc, 1.0); racc = one; break;
                 case RC_PH_FLUSH + 2: r_ph<4, false>(v, racc, 1.0); racc = one; break;
@@ -555,9 +569,84 @@ static bool encode_rounds(const std::vector<Gate>& gates, const std::vector<size
                 out.push_back(in[i]);
             }
             flush();
-            if (rd.op_begin + out.size() > max_ops) return false;
+            // Second pass: every thread-uniform phase (RC_PH_T, RC_DG1T, RC_PH_ACC) is a function of a few thread / outer
+            // bits.  They all commute, so they are multiplied together on the host into tables over <= 4 selector bits:
+            // one table op replaces several ops (each op costs ~25 instructions of decode for 4 FP64 instructions of work).
+            struct PhaseFn { std::vector<uint8_t> sel; std::vector<c64> tab; };
+            auto to_phase = [&](const ROp& o, PhaseFn* f) -> bool {
+                if (o.code != RC_PH_T && o.code != RC_PH_ACC && o.code != RC_DG1T) return false;
+                std::vector<uint8_t> ctl;
+                for (uint32_t m = o.tmask; m; m &= m - 1) ctl.push_back((uint8_t)(0x40 | __builtin_ctz(m)));
+                for (uint64_t m = o.omask; m; m &= m - 1) ctl.push_back((uint8_t)(0x80 | __builtin_ctzll(m)));
+                f->sel = ctl;
+                int dsel = -1;
+                if (o.code == RC_DG1T) {
+                    for (size_t i = 0; i < ctl.size(); ++i) if (ctl[i] == o.src[0]) return false;  // cannot happen (validated targets)
+                    dsel = (int)f->sel.size();
+                    f->sel.push_back(o.src[0]);
+                }
+                if (f->sel.size() > 4) return false;
+                const size_t nctl = ctl.size();
+                f->tab.assign(1u << f->sel.size(), make_double2(1.0, 0.0));
+                for (uint32_t x = 0; x < f->tab.size(); ++x) {
+                    if ((x & ((1u << nctl) - 1u)) != ((1u << nctl) - 1u)) continue;   // a control is 0: factor 1
+                    f->tab[x] = dsel < 0 ? prog->mats[o.mat] : prog->mats[o.mat + ((x >> dsel) & 1u)];
+                }
+                return true;
+            };
+            auto merge_into = [&](std::vector<PhaseFn>* tabs, const PhaseFn& f) {
+                for (PhaseFn& t : *tabs) {
+                    std::vector<uint8_t> uni = t.sel;
+                    for (uint8_t sb : f.sel) if (std::find(uni.begin(), uni.end(), sb) == uni.end()) uni.push_back(sb);
+                    if (uni.size() > 4) continue;
+                    std::vector<c64> nt(1u << uni.size());
+                    auto sub = [&](const PhaseFn& g, uint32_t x) {
+                        uint32_t ix = 0;
+                        for (size_t i = 0; i < g.sel.size(); ++i) {
+                            const size_t pos = std::find(uni.begin(), uni.end(), g.sel[i]) - uni.begin();
+                            ix |= ((x >> pos) & 1u) << i;
+                        }
+                        return g.tab[ix];
+                    };
+                    for (uint32_t x = 0; x < nt.size(); ++x) {
+                        const c64 a = sub(t, x), b = sub(f, x);
+                        nt[x] = make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+                    }
+                    t.sel = uni;
+                    t.tab = nt;
+                    return;
+                }
+                tabs->push_back(f);
+            };
+            bool overflow = false;
+            auto emit_tabs = [&](std::vector<PhaseFn>* tabs, uint8_t code, std::vector<ROp>* dst) {
+                for (const PhaseFn& t : *tabs) {
+                    if (n_mats + t.tab.size() > max_mats) { overflow = true; return; }
+                    ROp o;
+                    memset(&o, 0, sizeof(o));
+                    o.code = code;
+                    o.k = (uint8_t)t.sel.size();
+                    for (size_t i = 0; i < t.sel.size(); ++i) { if (i < 3) o.src[i] = t.sel[i]; else o.b = t.sel[i]; }
+                    o.mat = (uint32_t)n_mats;
+                    memcpy(prog->mats + n_mats, t.tab.data(), t.tab.size() * sizeof(c64));
+                    n_mats += t.tab.size();
+                    dst->push_back(o);
+                }
+                tabs->clear();
+            };
+            std::vector<ROp> merged;
+            std::vector<PhaseFn> tph_tabs, acc_tabs;
+            for (const ROp& o : out) {
+                PhaseFn f;
+                if (o.code >= RC_PH_FLUSH && o.code < RC_PH_FLUSH + 4) { emit_tabs(&acc_tabs, RC_TAB_ACC, &merged); merged.push_back(o); continue; }
+                if (!to_phase(o, &f)) { merged.push_back(o); continue; }
+                merge_into(o.code == RC_PH_ACC ? &acc_tabs : &tph_tabs, f);
+            }
+            emit_tabs(&tph_tabs, RC_TAB, &merged);
+            if (overflow || !acc_tabs.empty()) return false;
+            if (rd.op_begin + merged.size() > max_ops) return false;
             n_ops = rd.op_begin;
-            for (const ROp& o : out) prog->ops[n_ops++] = o;
+            for (const ROp& o : merged) prog->ops[n_ops++] = o;
         }
         rd.op_end = (uint16_t)n_ops;
         ++n_rounds;
