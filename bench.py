@@ -155,12 +155,25 @@ def cpu_baseline(n_workload, threads, budget_s=20.0, n_sample=None):
     dt = time.perf_counter() - t0
     gps_sample = done / dt
     gps_scaled = gps_sample / float(1 << (n_workload - n_sample))
+    # the allocation-faithful variant (per-group vectors + matrix clone, register.rs:155-188) on a smaller sample
+    faithful = None
+    try:
+        nf = min(n_sample, 18)
+        regf = orc.OracleRegister.new([False] * nf)
+        opsf = build_circuit(nf, layers=1, seed=0, qft=False)[:12]
+        tf = time.perf_counter()
+        for m, t in opsf:
+            regf.try_apply_fast((m, t), faithful=True)
+        faithful = len(opsf) / (time.perf_counter() - tf) / float(1 << (n_workload - nf))
+    except Exception:
+        pass
     return {"value": gps_scaled, "unit": "gates/s", "cores": threads, "kind": "port",
             "sample": f"{done} gates of the random H/RZ/CNOT/CZ layers at n={n_sample} in {dt:.1f} s "
                       f"({gps_sample:.2f} gates/s there), scaled by 2^-{n_workload - n_sample} to n={n_workload} "
                       f"(cost per gate is linear in 2^n); oracle/quaru_oracle.c try_apply_fast, {threads} OpenMP thread(s); "
                       f"the Rust reference itself is single-threaded and limited to n<=30",
-            "n_sample": n_sample, "gates_per_s_at_sample": gps_sample}
+            "n_sample": n_sample, "gates_per_s_at_sample": gps_sample,
+            "faithful_variant_value": faithful}
 
 
 def run_reference(args):
@@ -319,6 +332,13 @@ def run_ours(args):
                "traffic": None, "targets": targets_1q, "avg_launch_ms": ms_1q, "peak_source": peak_src}
     if roof is None:
         roof = roof_1q
+    try:   # DRAM traffic of the dominant kernel from the committed ncu capture (n = 28; see profiles/README.md)
+        cap = json.load(open(os.path.join(ROOT, "profiles", "r1c_traffic.json")))
+        roof["traffic_capture"] = cap
+        roof["traffic"] = cap["traffic_over_algorithmic"] * per_gpu_bytes
+        roof["traffic_note"] = "per launch, scaled from the n = 28 ncu capture by the algorithmic-byte ratio (measured ratio %.4f)" % cap["traffic_over_algorithmic"]
+    except Exception:
+        pass
 
     line = {
         "metric": "gates/s", "value": value, "unit": "gates/s", "n_gpus": world, "steps": args.steps,
