@@ -279,7 +279,8 @@ __global__ void __launch_bounds__(RTHREADS, 2) k2r_tile_pass(c64* __restrict__ s
             __syncthreads();
         }
         c64 tph = make_double2(1.0, 0.0);
-        c64 racc = make_double2(1.0, 0.0);   // running product of a chain of phases controlled by the same register bit
+        // `tph` doubles as the accumulator of a phase chain on one register bit: the host orders the ops of a round so that
+        // every other writer of tph (merged tables, Hadamard scalars, wide phases) comes after the last RC_PH_FLUSH
         for (uint32_t oi = rd.op_begin; oi < rd.op_end; ++oi) {
             const ROp& op = prog.ops[oi];
             if (((uint64_t)blockIdx.x & op.omask) != op.omask) continue;   // uniform per CTA; blockIdx needs no live register
@@ -316,7 +317,7 @@ __global__ void __launch_bounds__(RTHREADS, 2) k2r_tile_pass(c64* __restrict__ s
                 case RC_PH_T: ip_cmul(tph, M[0]); break;
                 case RC_PH_NEG: r_ph_dispatch<true>(v, rmask, one, act ? -1.0 : 1.0); break;
                 case RC_PH_R: r_ph_dispatch<false>(v, rmask, M[0], 1.0); break;
-                case RC_PH_ACC: ip_cmul(racc, M[0]); break;       // M is the identity slot for inactive threads
+                case RC_PH_ACC: ip_cmul(tph, M[0]); break;        // M is the identity slot for inactive threads
                 case RC_TAB:
                 case RC_TAB_ACC: {   // host-merged phases: index a table with up to 4 thread / outer bits
                     const uint32_t sel[4] = {op.src[0], op.src[1], op.src[2], op.b};
@@ -328,16 +329,16 @@ __global__ void __launch_bounds__(RTHREADS, 2) k2r_tile_pass(c64* __restrict__ s
                         idx |= (((sc & 0x80) ? (blockIdx.x >> (sc & 0x3f)) : (tl >> (sc & 0x3f))) & 1u) << i;
                     }
                     const c64 f = prog.mats[op.mat + idx];
-                    if (op.code == RC_TAB) ip_cmul(tph, f); else ip_cmul(racc, f);
+                    ip_cmul(tph, f);   // RC_TAB_ACC: the chain's flush follows; RC_TAB: applied at the end of the round
                 } break;
-                case RC_PH_FLUSH + 0: r_ph<1, false>(v, racc, 1.0); racc = one; break;
-                case RC_PH_FLUSH + 1: r_ph<2, false>(v, racc, 1.0); racc = one; break;
-                case RC_PH_FLUSH + 2: r_ph<4, false>(v, racc, 1.0); racc = one; break;
-                case RC_PH_FLUSH + 3: r_ph<8, false>(v, racc, 1.0); racc = one; break;
-                case RC_H + 0: r_h<0>(v); tph.x *= M[0].x; tph.y *= M[0].x; break;   // uncontrolled by construction
-                case RC_H + 1: r_h<1>(v); tph.x *= M[0].x; tph.y *= M[0].x; break;
-                case RC_H + 2: r_h<2>(v); tph.x *= M[0].x; tph.y *= M[0].x; break;
-                case RC_H + 3: r_h<3>(v); tph.x *= M[0].x; tph.y *= M[0].x; break;
+                case RC_PH_FLUSH + 0: r_ph<1, false>(v, tph, 1.0); tph = one; break;
+                case RC_PH_FLUSH + 1: r_ph<2, false>(v, tph, 1.0); tph = one; break;
+                case RC_PH_FLUSH + 2: r_ph<4, false>(v, tph, 1.0); tph = one; break;
+                case RC_PH_FLUSH + 3: r_ph<8, false>(v, tph, 1.0); tph = one; break;
+                case RC_H + 0: r_h<0>(v); break;   // uncontrolled; the scalar is folded into a table by the host
+                case RC_H + 1: r_h<1>(v); break;
+                case RC_H + 2: r_h<2>(v); break;
+                case RC_H + 3: r_h<3>(v); break;
                 case RC_DG1T: {  // one-qubit diagonal (RZ...) on a thread bit or an outer bit: one multiply per thread
                     const uint32_t s0 = op.src[0];
                     const uint32_t bit = (s0 & 0x80) ? ((blockIdx.x >> (s0 & 0x3f)) & 1u) : ((tl >> (s0 & 0x3f)) & 1u);
@@ -634,14 +635,28 @@ static bool encode_rounds(const std::vector<Gate>& gates, const std::vector<size
                 }
                 tabs->clear();
             };
-            std::vector<ROp> merged;
+            std::vector<ROp> merged, tail;   // tail: unmerged writers of tph, moved behind the last chain flush (they commute)
             std::vector<PhaseFn> tph_tabs, acc_tabs;
+            double h_scalar = 1.0;
+            bool any_h = false;
             for (const ROp& o : out) {
                 PhaseFn f;
                 if (o.code >= RC_PH_FLUSH && o.code < RC_PH_FLUSH + 4) { emit_tabs(&acc_tabs, RC_TAB_ACC, &merged); merged.push_back(o); continue; }
-                if (!to_phase(o, &f)) { merged.push_back(o); continue; }
+                if (o.code >= RC_H && o.code < RC_H + 4) { h_scalar *= prog->mats[o.mat].x; any_h = true; merged.push_back(o); continue; }
+                if (!to_phase(o, &f)) {
+                    const bool writes_tph = o.code == RC_PH_T || o.code == RC_DG1T ||
+                                            (o.code == RC_DG && o.rmask == 0 && !(o.src[0] < 4 && o.k > 0) && !(o.k > 1 && o.src[1] < 4) && !(o.k > 2 && o.src[2] < 4));
+                    (writes_tph ? tail : merged).push_back(o);
+                    continue;
+                }
                 merge_into(o.code == RC_PH_ACC ? &acc_tabs : &tph_tabs, f);
             }
+            if (any_h) {   // the deferred 1/sqrt(2) factors of the round's Hadamards: one constant
+                PhaseFn c;
+                c.tab.assign(1, make_double2(h_scalar, 0.0));
+                merge_into(&tph_tabs, c);
+            }
+            for (const ROp& o : tail) merged.push_back(o);
             emit_tabs(&tph_tabs, RC_TAB, &merged);
             if (overflow || !acc_tabs.empty()) return false;
             if (rd.op_begin + merged.size() > max_ops) return false;
