@@ -475,7 +475,11 @@ static int launch_general(Reg* r, const Gate& g) {
     else QB_GEN(1);
 #undef QB_GEN
     QB_CUDA(cudaGetLastError());
-    std::swap(r->state, r->scratch);
+    if (r->world > 1) {   // peers have mapped r->state (CUDA IPC): keep the pointer, copy the result back
+        QB_CUDA(cudaMemcpyAsync(r->state, r->scratch, n_amps * sizeof(c64), cudaMemcpyDeviceToDevice, r->stream));
+    } else {
+        std::swap(r->state, r->scratch);
+    }
     r->st_launches++;
     r->st_passes++;
     r->st_bytes += (int64_t)(n_amps * 32);

@@ -8,19 +8,24 @@
 //     constants (rank predicate / sub-table of the diagonal);
 //   * a dense target on a global qubit triggers ONE global<->local exchange that swaps every global
 //     qubit that is needed sooner than the local qubit it is traded against (look-ahead over the queued
-//     gates), done as pairwise ncclSend/ncclRecv of contiguous runs through a staging buffer carved
-//     from spare HBM;
+//     gates).  Preferred transport: a PEER-MEMORY kernel -- every rank maps its peers' shards (CUDA IPC) and one
+//     kernel swaps the blocks in place over NVLink/NVSwitch with 256-bit loads/stores on peer pointers, each rank of
+//     a pair handling half of the block (no staging buffer, no extra copy, all peers concurrently), bracketed by two
+//     tiny NCCL all-gathers as barriers.  Fallback (QB_SHARD_TRANSPORT=nccl or IPC unavailable): pairwise
+//     ncclSend/ncclRecv of contiguous runs through a staging buffer carved from spare HBM;
 //   * measurement: per-rank (p0, p1) -> ncclAllGather -> the same adjacent-pair tree on every rank.
 // NCCL is bound at run time (dlopen of libnccl.so.2: the copy torch already loaded, else the system's),
 // so a single-GPU process never needs it.
 #include <dlfcn.h>
 #include <math.h>
 #include <nccl.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
 
 #include "qb_shard.h"
+#include "qb_device.cuh"
 
 namespace qb {
 
@@ -76,6 +81,8 @@ struct Shard {
     uint64_t staging_amps = 0;
     double* d_gather = nullptr;   // 2 + 2*world doubles
     std::vector<uint32_t> logical_at;  // physical position -> logical qubit
+    c64* peer[8] = {nullptr};          // peer-mapped shards (CUDA IPC), index = rank; peer[rank] = own state
+    bool p2p = false;                  // peer-memory exchange available
     bool dry = false;                  // planner introspection: record exchanges, move no data
     std::vector<int32_t> events;       // dry run: [gate index, g', V..., J...] per exchange
     int64_t cur_gate = -1;
@@ -112,12 +119,55 @@ int shard_init(Reg* r, const void* unique_id) {
     QB_CUDA(cudaMalloc((void**)&s->d_gather, (2 + 2 * r->world) * sizeof(double)));
     s->logical_at.resize(r->n);
     for (uint32_t q = 0; q < r->n; ++q) s->logical_at[q] = q;
+    // peer-memory transport: exchange CUDA IPC handles of the shards through NCCL and map every peer's shard
+    const char* tr = getenv("QB_SHARD_TRANSPORT");
+    if (!(tr && !strcmp(tr, "nccl")) && r->world <= 8) {
+        cudaIpcMemHandle_t mine, all[8];
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+        char* dbuf = nullptr;
+        bool ok = cudaIpcGetMemHandle(&mine, r->state) == cudaSuccess && cudaMalloc((void**)&dbuf, 64 * (r->world + 1)) == cudaSuccess;
+        if (ok) {
+            ok = cudaMemcpyAsync(dbuf, &mine, 64, cudaMemcpyHostToDevice, r->stream) == cudaSuccess &&
+                 g_nccl.AllGather(dbuf, dbuf + 64, 64, ncclChar, s->comm, r->stream) == ncclSuccess &&
+                 cudaMemcpyAsync(all, dbuf + 64, 64 * r->world, cudaMemcpyDeviceToHost, r->stream) == cudaSuccess &&
+                 cudaStreamSynchronize(r->stream) == cudaSuccess;
+        }
+        if (dbuf) cudaFree(dbuf);
+        int opened = 0;
+        if (ok) {
+            for (int p = 0; p < r->world; ++p) {
+                if (p == r->rank) { s->peer[p] = r->state; ++opened; continue; }
+                void* ptr = nullptr;
+                if (cudaIpcOpenMemHandle(&ptr, all[p], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) break;
+                s->peer[p] = (c64*)ptr;
+                ++opened;
+            }
+        }
+        cudaGetLastError();   // a failed IPC call must not poison later launches
+        // all ranks must agree on the transport: gather the success flags
+        std::vector<double> flags;
+        double h[2] = {opened == r->world ? 1.0 : 0.0, 0.0};
+        QB_CUDA(cudaMemcpyAsync(s->d_gather, h, sizeof(h), cudaMemcpyHostToDevice, r->stream));
+        QB_NCCL(g_nccl.AllGather(s->d_gather, s->d_gather + 2, 2, ncclDouble, s->comm, r->stream));
+        flags.resize(2 * r->world);
+        QB_CUDA(cudaMemcpyAsync(flags.data(), s->d_gather + 2, 2 * r->world * sizeof(double), cudaMemcpyDeviceToHost, r->stream));
+        QB_CUDA(cudaStreamSynchronize(r->stream));
+        s->p2p = true;
+        for (int p = 0; p < r->world; ++p) s->p2p = s->p2p && flags[2 * p] == 1.0;
+    }
     return QB_OK;
 }
 
 void shard_destroy(Reg* r) {
     Shard* s = r->shard;
     if (!s) return;
+    bool mapped = false;
+    for (int p = 0; p < 8; ++p)
+        if (s->peer[p] && p != r->rank) { cudaIpcCloseMemHandle(s->peer[p]); mapped = true; }
+    if (mapped && s->comm && g_nccl.AllGather) {   // nobody frees its shard before every peer has unmapped it
+        g_nccl.AllGather(s->d_gather, s->d_gather + 2, 2, ncclDouble, s->comm, r->stream);
+        cudaStreamSynchronize(r->stream);
+    }
     if (s->staging) cudaFree(s->staging);
     if (s->d_gather) cudaFree(s->d_gather);
     if (s->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(s->comm);
@@ -126,8 +176,85 @@ void shard_destroy(Reg* r) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// K9: peer-memory exchange kernel.  For every peer p (xor-distance d = 1 .. 2^g'-1) this rank swaps its block
+// a = bits(p) with the peer's block b = bits(me): element e of the block pair is handled by the LOWER rank if e is in
+// the first half of the block and by the higher rank otherwise, so each amplitude is moved exactly once and both
+// directions of every NVLink are loaded equally.  A thread moves two amplitudes per access (256-bit).
+// ------------------------------------------------------------------------------------------------
+struct P2PArgs {
+    c64* peer[8];          // by xor-distance index d-1: the peer's shard
+    uint64_t my_off[8];    // offset of block a (the one I give away) inside my shard, without the run base
+    uint64_t peer_off;     // offset of block b (the one every peer gives me) inside THEIR shard
+    uint8_t lower[8];      // 1 if this rank is the lower rank of the pair
+    uint32_t npeer, gp;
+    uint32_t V[3];         // ascending local bit positions being traded
+    uint32_t log_run;      // log2(run length) = V[0]
+    uint64_t block_amps;   // amplitudes per block = 2^(n_local - gp)
+};
+
+__global__ void __launch_bounds__(256) k9_exchange_p2p(c64* __restrict__ mine, P2PArgs a) {
+    const uint64_t half_vecs = a.block_amps >> 2;                 // 2-amp vectors in half a block
+    const uint64_t total = half_vecs * a.npeer;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += stride) {
+        const uint32_t d = (uint32_t)(w / half_vecs);             // which peer
+        uint64_t e = (w - (uint64_t)d * half_vecs) << 1;          // element inside my half of the block
+        if (!a.lower[d]) e += a.block_amps >> 1;                  // the higher rank takes the second half
+        // element e of a block -> offset: low log_run bits are contiguous, the rest is deposited around the traded bits
+        uint64_t x = e >> a.log_run << a.log_run;
+        const uint64_t within = e - x;
+        for (uint32_t i = 0; i < a.gp; ++i) x = insert_zero_bit(x, a.V[i]);
+        const uint64_t lo = x + within + a.my_off[d], ro = x + within + a.peer_off;
+        c64* rp = a.peer[d];
+        const c64x2 L = ld256(mine + lo), R = ld256(rp + ro);
+        st256(mine + lo, R);
+        st256(rp + ro, L);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // the exchange: swap local physical positions V[i] with rank bits J[i]
 // ------------------------------------------------------------------------------------------------
+static int barrier_all(Reg* r);
+static int exchange_p2p(Reg* r, const std::vector<uint32_t>& Vs, const std::vector<uint32_t>& Js, uint32_t mybits) {
+    Shard* s = r->shard;
+    const uint32_t gp = (uint32_t)Vs.size();
+    P2PArgs a;
+    memset(&a, 0, sizeof(a));
+    a.npeer = (1u << gp) - 1;
+    a.gp = gp;
+    for (uint32_t i = 0; i < gp; ++i) a.V[i] = Vs[i];
+    a.log_run = Vs[0];
+    a.block_amps = 1ull << (r->n_local - gp);
+    auto block_off = [&](uint32_t bits) {
+        uint64_t o = 0;
+        for (uint32_t i = 0; i < gp; ++i)
+            if ((bits >> i) & 1) o |= 1ull << Vs[i];
+        return o;
+    };
+    a.peer_off = block_off(mybits);
+    for (uint32_t d = 1; d <= a.npeer; ++d) {
+        const uint32_t ab = mybits ^ d;
+        int p = r->rank;
+        for (uint32_t i = 0; i < gp; ++i) { p &= ~(1 << Js[i]); p |= (int)((ab >> i) & 1) << Js[i]; }
+        a.peer[d - 1] = s->peer[p];
+        a.my_off[d - 1] = block_off(ab);
+        a.lower[d - 1] = r->rank < p;
+    }
+    if (a.block_amps < 4 || Vs[0] < 1) return -1;  // tiny registers / a traded bit 0 (no 2-amplitude vectors): NCCL path
+    QB_TRY(barrier_all(r));           // every rank has finished the kernels that precede the exchange
+    const uint64_t total = (a.block_amps >> 2) * a.npeer;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, r->device);
+    const unsigned grid = (unsigned)std::min<uint64_t>((total + 255) / 256, (uint64_t)sms * 8);
+    k9_exchange_p2p<<<grid, 256, 0, r->stream>>>(r->state, a);
+    QB_CUDA(cudaGetLastError());
+    r->st_launches++;
+    QB_TRY(barrier_all(r));           // nobody touches its shard before every peer has finished writing into it
+    return QB_OK;
+}
+
+
 static int exchange(Reg* r, std::vector<uint32_t> V, std::vector<uint32_t> J) {
     Shard* s = r->shard;
     const uint32_t gp = (uint32_t)V.size();
@@ -155,6 +282,12 @@ static int exchange(Reg* r, std::vector<uint32_t> V, std::vector<uint32_t> J) {
     uint32_t mybits = 0;
     for (uint32_t i = 0; i < gp; ++i) mybits |= ((uint32_t)(r->rank >> Js[i]) & 1u) << i;
     const uint32_t npeer = (1u << gp) - 1;
+    bool done_p2p = false;
+    if (s->p2p) {
+        int rc = exchange_p2p(r, Vs, Js, mybits);
+        if (rc > 0 || rc < -1) return rc;
+        done_p2p = rc == QB_OK;
+    }
     const uint64_t run_len = 1ull << Vs[0];
     const uint64_t n_runs = 1ull << (r->n_local - gp - Vs[0]);
     uint64_t chunk = s->staging_amps / npeer;
@@ -179,7 +312,7 @@ static int exchange(Reg* r, std::vector<uint32_t> V, std::vector<uint32_t> J) {
         return p;
     };
 
-    for (uint64_t o = 0; o < n_runs; ++o) {
+    for (uint64_t o = 0; o < n_runs && !done_p2p; ++o) {
         uint64_t base = o << Vs[0];
         for (uint32_t i = 0; i < gp; ++i) {
             const uint64_t lo = base & ((1ull << Vs[i]) - 1);
@@ -379,6 +512,12 @@ static int allgather2(Reg* r, double a, double b, std::vector<double>* out) {
     out->resize(2 * r->world);
     QB_CUDA(cudaMemcpyAsync(out->data(), s->d_gather + 2, 2 * r->world * sizeof(double), cudaMemcpyDeviceToHost, r->stream));
     QB_CUDA(cudaStreamSynchronize(r->stream));
+    return QB_OK;
+}
+
+static int barrier_all(Reg* r) {   // stream-ordered barrier across ranks: a two-double all-gather
+    Shard* s = r->shard;
+    QB_NCCL(g_nccl.AllGather(s->d_gather, s->d_gather + 2, 2, ncclDouble, s->comm, r->stream));
     return QB_OK;
 }
 
