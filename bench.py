@@ -367,6 +367,8 @@ def run_ours(args):
         hbm_s = (passes / args.steps) * per_gpu_bytes / (peak * 1e9)
         nv_s = swap_bytes_step / (nv_peak * 1e9)
         line["nvlink"] = {"swap_bytes_sent_per_gpu_per_step": swap_bytes_step, "swaps_per_step": swaps_step,
+                          "transport": "peer-memory kernel (CUDA IPC)" if reg.stat(_ffi.QB_STAT_P2P_EXCHANGES) > 0 else "NCCL send/recv + staging",
+                          "p2p_exchanges_total": reg.stat(_ffi.QB_STAT_P2P_EXCHANGES), "exchanges_total": reg.stat(_ffi.QB_STAT_SWAPS),
                           "peak_GBps_per_direction": nv_peak, "roofline_s_per_step": hbm_s + nv_s,
                           "roofline_hbm_s": hbm_s, "roofline_nvlink_s": nv_s,
                           "frac_of_roofline": (hbm_s + nv_s) / (ms / args.steps / 1e3)}

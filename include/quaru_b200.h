@@ -167,6 +167,7 @@ int qb_set_option(qb_reg* reg, int32_t option, int64_t value);
 #define QB_STAT_TILE_LAUNCHES 7   /* tile-pass kernel launches (profiled ones when QB_OPT_PROFILE=1) */
 #define QB_STAT_TILE_NS 8         /* summed device time of the profiled tile-pass launches, ns */
 #define QB_STAT_ROUNDS 9          /* register rounds executed by the register-blocked tile kernel */
+#define QB_STAT_P2P_EXCHANGES 10  /* exchanges done by the peer-memory kernel (the rest went through NCCL send/recv) */
 int qb_get_stat(qb_reg* reg, int32_t stat, int64_t* value);
 
 /* ---- planner introspection (host only, no GPU needed) ------------------------------------ */

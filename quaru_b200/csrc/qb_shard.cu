@@ -250,6 +250,7 @@ static int exchange_p2p(Reg* r, const std::vector<uint32_t>& Vs, const std::vect
     k9_exchange_p2p<<<grid, 256, 0, r->stream>>>(r->state, a);
     QB_CUDA(cudaGetLastError());
     r->st_launches++;
+    r->st_p2p++;
     QB_TRY(barrier_all(r));           // nobody touches its shard before every peer has finished writing into it
     return QB_OK;
 }
