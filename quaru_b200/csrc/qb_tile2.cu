@@ -34,7 +34,8 @@ enum RCode : uint8_t {
     RC_H = 40,                                     // + register bit: scalar multiple of the Hadamard matrix, uncontrolled
     RC_PH_ACC = 44,                                // phase whose only register-bit control is one bit: accumulate per thread ...
     RC_PH_FLUSH = 48,                              // + register bit: ... and apply the product to the 8 registers with that bit set
-    RC_TAB = 52, RC_TAB_ACC = 53                   // merged thread-uniform phases: table over <= 4 thread / outer bits -> tph / racc
+    RC_TAB = 52, RC_TAB_ACC = 53,                  // merged thread-uniform phases: table over <= 4 thread / outer bits -> tph
+    RC_LAYER = 54                                  // up to four real 2x2 gates, one per register bit, decoded once
 };
 
 struct ROp {
@@ -147,6 +148,26 @@ __device__ __forceinline__ void r_h(c64 (&v)[16]) {
         if ((j0 >> A) & 1) continue;
         ip_pair_h(v[j0], v[j0 | (1 << A)]);
     }
+}
+
+template <int A>
+__device__ __forceinline__ void r_d1r_vals(c64 (&v)[16], double p, double q, double r, double s) {
+#pragma unroll
+    for (int j0 = 0; j0 < 16; ++j0) {
+        if ((j0 >> A) & 1) continue;
+        ip_pair_real(v[j0], v[j0 | (1 << A)], p, q, r, s);
+    }
+}
+
+// one slot of a layer op: a real 2x2 gate on register bit A with its own thread-bit control mask, or a Hadamard
+template <int A>
+__device__ __forceinline__ void r_layer_slot(c64 (&v)[16], uint32_t present, uint32_t hmask, const c64* __restrict__ C, uint32_t tm,
+                                             uint32_t tl) {
+    if (!((present >> A) & 1u)) return;                    // uniform
+    if ((hmask >> A) & 1u) { r_h<A>(v); return; }          // uniform
+    const bool act = (tl & tm) == tm;                      // per thread, never branched on
+    const c64 c0 = C[2 * A], c1 = C[2 * A + 1];
+    r_d1r_vals<A>(v, act ? c0.x : 1.0, act ? c0.y : 0.0, act ? c1.x : 0.0, act ? c1.y : 1.0);
 }
 
 // phase on the registers whose index contains the (compile-time) mask RM
@@ -330,6 +351,14 @@ __global__ void __launch_bounds__(RTHREADS, 2) k2r_tile_pass(c64* __restrict__ s
                     }
                     const c64 f = prog.mats[op.mat + idx];
                     ip_cmul(tph, f);   // RC_TAB_ACC: the chain's flush follows; RC_TAB: applied at the end of the round
+                } break;
+                case RC_LAYER: {   // several dense one-qubit gates decoded once (masks are packed into otherwise unused fields)
+                    const uint32_t present = op.k & 15u, hmask = op.k >> 4;
+                    const c64* C = prog.mats + op.mat;
+                    r_layer_slot<0>(v, present, hmask, C, op.tmask, tl);
+                    r_layer_slot<1>(v, present, hmask, C, op.rmask, tl);
+                    r_layer_slot<2>(v, present, hmask, C, (uint32_t)op.src[0] | ((uint32_t)op.src[1] << 8), tl);
+                    r_layer_slot<3>(v, present, hmask, C, (uint32_t)op.src[2] | ((uint32_t)op.b << 8), tl);
                 } break;
                 case RC_PH_FLUSH + 0: r_ph<1, false>(v, tph, 1.0); tph = one; break;
                 case RC_PH_FLUSH + 1: r_ph<2, false>(v, tph, 1.0); tph = one; break;
@@ -658,6 +687,90 @@ static bool encode_rounds(const std::vector<Gate>& gates, const std::vector<size
             }
             for (const ROp& o : tail) merged.push_back(o);
             emit_tabs(&tph_tabs, RC_TAB, &merged);
+            // Third pass: bundle real one-qubit gates (H, X, real rotations; no register-bit or outer control) on DISTINCT
+            // register bits into layer ops.  A gate may be hoisted into the open layer past ops that do not touch its
+            // register bit (it writes only that bit; nobody writes thread bits inside a round).
+            {
+                auto reg_bits = [](const ROp& o) -> uint32_t {
+                    const int c = o.code;
+                    if (c < RC_D2) return (1u << (c & 3)) | o.rmask;                  // D1C / D1R / DG1R and predicated forms
+                    if (c == RC_D2) return (1u << o.a) | (1u << o.b) | o.rmask;
+                    if (c == RC_PH_NEG || c == RC_PH_R) return o.rmask;
+                    if (c >= RC_PH_FLUSH && c < RC_PH_FLUSH + 4) return 1u << (c - RC_PH_FLUSH);
+                    if (c >= RC_H && c < RC_H + 4) return 1u << (c - RC_H);
+                    if (c == RC_DG) {
+                        uint32_t m = o.rmask;
+                        for (int i = 0; i < o.k && i < 3; ++i) if (o.src[i] < 4) m |= 1u << o.src[i];
+                        return m;
+                    }
+                    return 0;   // PH_T, DG1T, TAB, TAB_ACC, PH_ACC: per-thread phase only
+                };
+                std::vector<ROp> packed;
+                int open = -1;            // index in `packed` of the open layer
+                uint32_t touched = 0;     // register bits touched by ops appended after the open layer
+                struct Slot { bool used, h; uint16_t tm; c64 c0, c1; };
+                Slot slots[4];
+                auto close_layer = [&]() -> bool {
+                    if (open < 0) return true;
+                    int cnt = 0;
+                    for (int b = 0; b < 4; ++b) cnt += slots[b].used;
+                    ROp& L = packed[open];
+                    if (cnt >= 2) {
+                        if (n_mats + 8 > max_mats) return false;
+                        const uint32_t mat = (uint32_t)n_mats;
+                        uint32_t present = 0, hmask = 0;
+                        uint16_t tm[4] = {0, 0, 0, 0};
+                        for (int b = 0; b < 4; ++b) {
+                            prog->mats[n_mats + 2 * b] = slots[b].c0;
+                            prog->mats[n_mats + 2 * b + 1] = slots[b].c1;
+                            if (!slots[b].used) continue;
+                            present |= 1u << b;
+                            if (slots[b].h) hmask |= 1u << b;
+                            tm[b] = slots[b].tm;
+                        }
+                        n_mats += 8;
+                        memset(&L, 0, sizeof(L));
+                        L.code = RC_LAYER;
+                        L.k = (uint8_t)(present | (hmask << 4));
+                        L.mat = mat;
+                        L.tmask = tm[0];
+                        L.rmask = tm[1];
+                        L.src[0] = (uint8_t)(tm[2] & 0xff); L.src[1] = (uint8_t)(tm[2] >> 8);
+                        L.src[2] = (uint8_t)(tm[3] & 0xff); L.b = (uint8_t)(tm[3] >> 8);
+                    }   // a layer with a single gate stays the plain op it was created from
+                    open = -1;
+                    return true;
+                };
+                for (const ROp& o : merged) {
+                    const int c = o.code;
+                    const bool is_h = c >= RC_H && c < RC_H + 4;
+                    const bool layerable = (is_h || (c >= RC_D1R && c < RC_D1R + 4)) && o.omask == 0;
+                    if (!layerable) {
+                        packed.push_back(o);
+                        if (open >= 0) touched |= reg_bits(o);
+                        continue;
+                    }
+                    const int bit = c & 3;
+                    if (open >= 0 && !slots[bit].used && !((touched >> bit) & 1u)) {
+                        // joins the open layer
+                    } else {
+                        if (!close_layer()) return false;
+                        open = (int)packed.size();
+                        packed.push_back(o);       // placeholder: rewritten by close_layer if the layer gets >= 2 gates
+                        touched = 0;
+                        for (int b = 0; b < 4; ++b) slots[b] = Slot{false, false, 0, make_double2(1.0, 0.0), make_double2(0.0, 1.0)};
+                    }
+                    slots[bit].used = true;
+                    slots[bit].h = is_h;
+                    slots[bit].tm = o.tmask;
+                    if (!is_h) {
+                        slots[bit].c0 = make_double2(prog->mats[o.mat + 0].x, prog->mats[o.mat + 1].x);   // p, q
+                        slots[bit].c1 = make_double2(prog->mats[o.mat + 2].x, prog->mats[o.mat + 3].x);   // r, s
+                    }
+                }
+                if (!close_layer()) return false;
+                merged.swap(packed);
+            }
             if (overflow || !acc_tabs.empty()) return false;
             if (rd.op_begin + merged.size() > max_ops) return false;
             n_ops = rd.op_begin;
