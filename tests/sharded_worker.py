@@ -64,16 +64,22 @@ def main():
         reg.close()
         return swaps
 
-    quick = world >= 8 or os.environ.get("QB_SHARDED_QUICK") == "1"      # bound the 8-GPU run (GPU-minutes are x8)
-    for n in ((3 * g + 1, 14) if quick else (3 * g + 1, 10, 14)):
+    quick = world >= 8 or os.environ.get("QB_SHARDED_QUICK") in ("1", "2")      # bound the 8-GPU run (GPU-minutes are x8)
+    minimal = os.environ.get("QB_SHARDED_QUICK") == "2"                          # two registers only
+    for n in (() if minimal else (3 * g + 1, 14) if quick else (3 * g + 1, 10, 14)):
         for fusion in ((1,) if quick else (0, 1)):
             s = check(f"layers n={n} fusion={fusion}", n, circuits.random_circuit(n, 6, seed=n), fusion,
                       measure=(n - 1, 0, n // 2))
             check(f"qft n={n} fusion={fusion}", n, circuits.qft_circuit(n), fusion)
             ops = [o for o in circuits.mixed_circuit(n, 80, seed=7 + n) if len(o[1]) <= n - g]
             check(f"mixed n={n} fusion={fusion}", n, ops, fusion, measure=(1, n - 1))
+    if minimal:
+        ops = [o for o in circuits.mixed_circuit(15, 80, seed=22) if len(o[1]) <= 15 - g]
+        check("mixed n=15 (minimal)", 15, ops, 1, measure=(1, 14))
     # a bigger one: 20 qubits, fused, 3 layers
-    check("layers n=20", 20, circuits.random_circuit(20, 3, seed=20), 1, measure=(19,))
+    swaps = check("layers n=20", 20, circuits.random_circuit(20, 3, seed=20), 1, measure=(19,))
+    if rank == 0:
+        print(f"exchanges in the n=20 run: {swaps}", flush=True)
 
     flag = torch.tensor([len(failures)], device="cuda")
     dist.all_reduce(flag)
