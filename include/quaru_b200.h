@@ -210,6 +210,12 @@ uint32_t qb_qasm_creg_size(const qb_qasm* prog, uint32_t i);
 uint64_t qb_qasm_num_ops(const qb_qasm* prog);
 const qb_qasm_op* qb_qasm_ops(const qb_qasm* prog);
 
+/* Serialises the register-blocked round programs the fused path would launch for `gates` on an n-qubit register
+ * (format: quaru_b200/csrc/qb_tile.cu rounds_debug).  tests/test_rounds_emulator.py replays them with a NumPy
+ * emulator of the kernel's semantics against the CPU oracle, so the host-side encoder is covered without a GPU.
+ * Returns the number of bytes written or a negative error. */
+int64_t qb_rounds_debug(uint32_t n, const qb_gate* gates, uint64_t count, void* out, uint64_t capacity);
+
 /* Dry run of the multi-GPU placement logic: the global<->local exchanges rank `rank` of `world` would
  * perform for this gate list, as a flat int32 list of records [gate index before which the exchange
  * happens, g', V[0..g') local bit positions, J[0..g') rank-bit indices], and the final logical->physical

@@ -88,6 +88,8 @@ SIGNATURES = {
     "qb_qasm_creg_size": (ctypes.c_uint32, [_reg, ctypes.c_uint32]),
     "qb_qasm_num_ops": (ctypes.c_uint64, [_reg]),
     "qb_qasm_ops": (ctypes.POINTER(QbQasmOp), [_reg]),
+    "qb_rounds_debug": (ctypes.c_int64, [ctypes.c_uint32, ctypes.POINTER(QbGate), ctypes.c_uint64, ctypes.c_void_p,
+                                         ctypes.c_uint64]),
     "qb_shard_plan_debug": (ctypes.c_int64, [ctypes.c_uint32, ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(QbGate),
                                              ctypes.c_uint64, _i32p, ctypes.c_uint64, _u32p]),
     "qb_plan_debug": (ctypes.c_int64, [ctypes.c_uint32, ctypes.POINTER(QbGate), ctypes.c_uint64, ctypes.c_uint32,

@@ -9,6 +9,7 @@
 
 #include "qb_common.h"
 #include "qb_shard.h"
+#include "qb_tile.h"
 
 namespace qb {
 const char* last_error_str();
@@ -155,6 +156,20 @@ int64_t qb_shard_plan_debug(uint32_t n, int32_t world, int32_t rank, const qb_ga
         gs.push_back(std::move(g));
     }
     return shard_plan_debug(n, world, rank, gs, events, capacity, final_phys_of);
+}
+
+int64_t qb_rounds_debug(uint32_t n, const qb_gate* gates, uint64_t count, void* out, uint64_t capacity) {
+    if ((count && !gates) || (capacity && !out)) return set_error(QB_ERR_INVALID_ARGUMENT, -1, "NULL argument");
+    std::vector<Gate> gs;
+    for (uint64_t i = 0; i < count; ++i) {
+        int rc = validate_targets(n, gates[i].targets, gates[i].k);
+        if (rc != QB_OK) return rc;
+        Gate g;
+        if (!classify_gate(gates[i].matrix, gates[i].targets, gates[i].k, &g)) continue;
+        g.tag = (int64_t)i;
+        gs.push_back(std::move(g));
+    }
+    return rounds_debug(n, gs, (unsigned char*)out, capacity);
 }
 
 const char* qb_version(void) { return "quaru_b200 0.1 (sm_100a)"; }

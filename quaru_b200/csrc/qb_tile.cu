@@ -375,4 +375,38 @@ int64_t plan_debug(uint32_t n, std::vector<Gate>& gates, uint32_t tile_bits, int
     return (int64_t)passes.size();
 }
 
+// Planner introspection (no GPU): every pass of the plan for an n-qubit register, serialised as
+//   u32 kind (0 = register-blocked round program follows, 1 = gates applied one by one / by the shared-memory kernel),
+//   u32 n_gates, i64 tags[n_gates], u8 tile_pos[12] (kind 0), then the round program (encode_rounds_debug).
+int64_t rounds_debug(uint32_t n, std::vector<Gate>& gates, unsigned char* out, uint64_t cap) {
+    std::vector<PlannedPass> passes;
+    plan_passes(gates, n, 12, (int)(sizeof(PassLarge::ops) / sizeof(TileOp)), (int)(sizeof(PassLarge::mats) / sizeof(c64)), &passes);
+    unsigned char* w = out;
+    auto room = [&](uint64_t bytes) { return (uint64_t)(w - out) + bytes <= cap; };
+    for (const PlannedPass& p : passes) {
+        const uint32_t ng = (uint32_t)p.gate_idx.size();
+        if (!room(8 + 8ull * ng + 12)) return set_error(QB_ERR_INVALID_ARGUMENT, -1, "buffer too small");
+        unsigned char* kind_at = w;
+        uint32_t kind = 1;
+        memcpy(w, &kind, 4); w += 4;
+        memcpy(w, &ng, 4); w += 4;
+        for (size_t gi : p.gate_idx) { const int64_t tag = gates[gi].tag; memcpy(w, &tag, 8); w += 8; }
+        if (p.unfused || n < 12) continue;
+        // same dispatch rule as run_fused: single diagonal / one-qubit gates go through the streaming kernels
+        if (p.gate_idx.size() == 1) {
+            const Gate& g = gates[p.gate_idx[0]];
+            if (g.kind == GK_DIAG || g.k == 1) continue;
+        }
+        unsigned char* tp_at = w;
+        for (uint32_t j = 0; j < 12; ++j) { const unsigned char b = j < p.tile_pos.size() ? (unsigned char)p.tile_pos[j] : 0; *w++ = b; }
+        const int64_t got = encode_rounds_debug(gates, p.gate_idx, p.tile_pos, p.lc, w, cap - (uint64_t)(w - out));
+        if (got < 0) return set_error(QB_ERR_INVALID_ARGUMENT, -1, "buffer too small");
+        if (got == 0) { w = tp_at; continue; }   // falls back to the shared-memory kernel: report as a plain gate list
+        kind = 0;
+        memcpy(kind_at, &kind, 4);
+        w += got;
+    }
+    return (int64_t)(w - out);
+}
+
 }  // namespace qb

@@ -845,6 +845,39 @@ static int launch_rpass(Reg* r, const Prog& prog) {
     return QB_OK;
 }
 
+// Planner introspection (no GPU): serialises the round program of one pass.  Layout (little endian):
+//   u32 lc, h, n_rounds, n_ops, n_mats; u8 hp[8]; RoundDesc[n_rounds]; ROp[n_ops]; c64[n_mats]
+// Returns the number of bytes written, 0 if the pass cannot go through the register-blocked kernel, -1 if `cap` is too small.
+int64_t encode_rounds_debug(const std::vector<Gate>& gates, const std::vector<size_t>& gate_idx, const std::vector<uint32_t>& tile_pos,
+                            uint32_t lc, unsigned char* out, uint64_t cap) {
+    if (tile_pos.size() != RT) return 0;
+    static thread_local RProgLarge prog;
+    memset(&prog, 0, sizeof(prog));
+    if (!encode_rounds(gates, gate_idx, tile_pos, lc, &prog)) return 0;
+    const uint32_t n_rounds = prog.n_rounds, n_ops = prog.rounds[n_rounds - 1].op_end;
+    uint32_t n_mats = 4;
+    for (uint32_t i = 0; i < n_ops; ++i) {   // the encoder does not keep the table count: recover an upper bound per op
+        const ROp& o = prog.ops[i];
+        uint32_t len = 4;
+        if (o.code == RC_D2) len = 16;
+        else if (o.code == RC_DG) len = 1u << o.k;
+        else if (o.code == RC_TAB || o.code == RC_TAB_ACC) len = 1u << o.k;
+        else if (o.code == RC_LAYER) len = 8;
+        n_mats = std::max(n_mats, o.mat + len);
+    }
+    n_mats = std::min<uint32_t>(n_mats, sizeof(prog.mats) / sizeof(c64));
+    const uint64_t need = 20 + 8 + (uint64_t)n_rounds * sizeof(RoundDesc) + (uint64_t)n_ops * sizeof(ROp) + (uint64_t)n_mats * sizeof(c64);
+    if (need > cap) return -1;
+    unsigned char* w = out;
+    const uint32_t hdr[5] = {prog.lc, prog.h, n_rounds, n_ops, n_mats};
+    memcpy(w, hdr, 20); w += 20;
+    memcpy(w, prog.hp, 8); w += 8;
+    memcpy(w, prog.rounds, n_rounds * sizeof(RoundDesc)); w += n_rounds * sizeof(RoundDesc);
+    memcpy(w, prog.ops, n_ops * sizeof(ROp)); w += n_ops * sizeof(ROp);
+    memcpy(w, prog.mats, n_mats * sizeof(c64)); w += n_mats * sizeof(c64);
+    return (int64_t)(w - out);
+}
+
 // returns QB_OK and *handled = true if the pass went through the register-blocked kernel
 int run_pass_v2(Reg* r, const std::vector<Gate>& gates, const std::vector<size_t>& gate_idx, const std::vector<uint32_t>& tile_pos,
                 uint32_t lc, bool* handled) {

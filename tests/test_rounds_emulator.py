@@ -1,0 +1,102 @@
+"""CPU coverage of the fused path's HOST logic: the pass programs produced by the planner + round encoder
+(qb_rounds_debug) are replayed with a NumPy emulator of the kernel's op semantics (tests/rounds_emulator.py)
+and must reproduce the CPU oracle.  Also checks structural invariants of the programs (register / thread bit
+partition, coalescing constraints of the HBM-facing rounds, host-computed swizzles) and that fusion happens."""
+import numpy as np
+import pytest
+
+from oracle import gates as og
+from oracle.oracle import OracleRegister
+from tests import circuits
+from tests import rounds_emulator as em
+from tests.util import assert_close, random_state
+
+
+def _replay(n, ops, seed):
+    s0 = random_state(n, seed)
+    ora = OracleRegister(s0.copy(), n)
+    for o in ops:
+        ora.apply(o)
+    passes = em.dump_programs(n, ops)
+    st = s0.copy()
+    seen = []
+    stats = {"prog": 0, "gates": 0, "rounds": 0, "ops": 0, "codes": set()}
+    for p in passes:
+        seen += p[1]
+        if p[0] == "gates":
+            stats["gates"] += 1
+            tmp = OracleRegister(st, n)
+            for tag in p[1]:
+                tmp.apply(ops[tag])
+            st = tmp.state
+        else:
+            stats["prog"] += 1
+            stats["rounds"] += len(p[3]["rounds"])
+            stats["ops"] += len(p[3]["ops"])
+            stats["codes"] |= {o["code"] for o in p[3]["ops"]}
+            st = em.emulate_program(st, n, p[2], p[3])
+    return st, ora.state, seen, stats
+
+
+@pytest.mark.parametrize("n,depth,seed", [(12, 8, 1), (13, 6, 2), (14, 6, 3), (15, 4, 4)])
+def test_random_layers_programs(n, depth, seed):
+    ops = circuits.random_circuit(n, depth, seed=seed)
+    got, want, seen, st = _replay(n, ops, 100 + seed)
+    assert sorted(seen) == list(range(len(ops))), "every gate must be scheduled exactly once"
+    assert_close(got, want, f"layers n={n}")
+    assert st["prog"] >= 1 and st["prog"] + st["gates"] < len(ops) / 4, "gates should be fused into few passes"
+    assert em.RC_LAYER in st["codes"] or em.RC_H in st["codes"]
+    assert st["ops"] < len(ops), "host-side merging (layers, phase tables) should shrink the op count"
+
+
+@pytest.mark.parametrize("n", [12, 14, 16])
+def test_qft_programs(n):
+    ops = circuits.qft_circuit(n)
+    got, want, seen, st = _replay(n, ops, 200 + n)
+    assert sorted(seen) == list(range(len(ops)))
+    assert_close(got, want, f"qft n={n}")
+    assert {em.RC_TAB_ACC, em.RC_PH_FLUSH} & {c - (c - em.RC_PH_FLUSH) % 4 if em.RC_PH_FLUSH <= c < em.RC_PH_FLUSH + 4 else c for c in st["codes"]}, \
+        "controlled-phase cascades should become accumulated chains"
+    assert st["ops"] < 0.8 * len(ops)
+
+
+@pytest.mark.parametrize("n,seed", [(12, 5), (13, 6), (14, 7), (15, 8)])
+def test_mixed_programs(n, seed):
+    ops = circuits.mixed_circuit(n, 120, seed)
+    got, want, seen, st = _replay(n, ops, 300 + seed)
+    identities = [i for i, (m, t) in enumerate(ops) if np.array_equal(np.asarray(m), np.eye(len(m)))]
+    assert sorted(seen + identities) == list(range(len(ops)))
+    assert_close(got, want, f"mixed n={n}")
+
+
+def test_controls_on_register_thread_and_outer_bits():
+    """A dense gate whose controls land on register bits, thread bits and bits outside the tile at once, plus
+    diagonals with mixed bit sources (n = 15: three outer bits)."""
+    n = 15
+    rng = np.random.default_rng(9)
+    ops = []
+    for _ in range(40):
+        qs = [int(x) for x in rng.permutation(n)]
+        nc = int(rng.integers(1, 5))
+        m = np.linalg.qr(rng.normal(size=(2, 2)) + 1j * rng.normal(size=(2, 2)))[0]
+        big = (m, [qs[0]])
+        for c in qs[1:1 + nc]:
+            big = og.to_controlled(big, c)
+        ops.append(big)
+        ops.append(og.hadamard(qs[5]))
+        ops.append(og.cnx(qs[6:8], qs[8]))
+        d = np.exp(1j * rng.uniform(0, 6.28, size=8))
+        ops.append((np.diag(d), qs[9:12]))
+        ops.append(og.cphase(float(rng.uniform(0, 6.28)), qs[12], qs[13]))
+    got, want, seen, st = _replay(n, ops, 17)
+    assert_close(got, want)
+    assert st["prog"] >= 1
+
+
+def test_program_dump_handles_small_registers_and_single_gates():
+    # fewer than 12 qubits: no register-blocked programs, everything is reported as plain gates
+    passes = em.dump_programs(8, circuits.random_circuit(8, 3, seed=1))
+    assert passes and all(p[0] == "gates" for p in passes)
+    # a lone one-qubit gate goes to the streaming kernel, not to a tile program
+    passes = em.dump_programs(13, [og.hadamard(3)])
+    assert [p[0] for p in passes] == ["gates"]
