@@ -546,6 +546,29 @@ static bool encode_rounds(const std::vector<Gate>& gates, const std::vector<size
                 if (!any_reg && op.rmask == 0) rd.has_tph = 1;
                 if (g.k == 1 && any_reg) { op.a = op.src[0]; op.code = (uint8_t)((op.rmask ? RC_DG1R_P : RC_DG1R) + op.a); }
                 if (g.k == 1 && !any_reg && op.rmask == 0) op.code = RC_DG1T;
+                // diag(d0, d1) on a register bit = d0 on the whole thread (thread-uniform: merges into the phase tables)
+                // times the relative phase d1/d0 on the 8 registers with the bit set (joins the phase chains of that
+                // bit): half the register traffic of multiplying all 16 registers.
+                if (op.code >= RC_DG1R && op.code < RC_DG1R + 4 && (mat[0].x != 0.0 || mat[0].y != 0.0) && n_ops + 2 <= max_ops &&
+                    n_mats + 2 <= max_mats) {
+                    const c64 d0 = mat[0], d1 = mat[1];
+                    const double den = d0.x * d0.x + d0.y * d0.y;
+                    const c64 rel = make_double2((d1.x * d0.x + d1.y * d0.y) / den, (d1.y * d0.x - d1.x * d0.y) / den);
+                    ROp u = op;               // thread-uniform part, same thread / outer controls
+                    u.code = RC_PH_T;
+                    u.a = 0; u.k = 0; u.src[0] = u.src[1] = u.src[2] = 0;
+                    u.mat = (uint32_t)n_mats;
+                    prog->mats[n_mats++] = d0;
+                    prog->ops[n_ops++] = u;
+                    rd.has_tph = 1;
+                    ROp r2 = u;               // relative phase on the registers with the bit set
+                    r2.rmask = (uint16_t)(1u << op.a);
+                    r2.code = (rel.x == -1.0 && rel.y == 0.0) ? RC_PH_NEG : RC_PH_R;
+                    r2.mat = (uint32_t)n_mats;
+                    prog->mats[n_mats++] = rel;
+                    prog->ops[n_ops++] = r2;
+                    continue;
+                }
             }
             memcpy(prog->mats + n_mats, mat.data(), mat.size() * sizeof(c64));
             n_mats += mat.size();
