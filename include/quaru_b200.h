@@ -48,6 +48,7 @@ typedef struct qb_reg qb_reg;
 #define QB_ERR_OOM 3
 #define QB_ERR_NO_DEVICE 4
 #define QB_ERR_UNSUPPORTED 5
+#define QB_ERR_IO 6                    /* state file missing / unreadable / corrupt; payload = errno or 0 */
 
 /* Message / payload (the usize carried by the OperationError variant) of the last failing call
  * on the calling thread. */
@@ -136,6 +137,17 @@ int qb_measure(qb_reg* reg, uint32_t target, double u, int32_t* outcome);
  * transferred (read: the rest of `out` is left untouched). */
 int qb_read_state(qb_reg* reg, uint64_t offset, uint64_t count, double* out);
 int qb_write_state(qb_reg* reg, uint64_t offset, uint64_t count, const double* in);
+
+/* Raw state files (checkpoint / restore).  The reference's `pub state` is a host array any driver can serialise
+ * (register.rs:23-37); for a device-resident state the engine streams it.  One file = one rank's shard: a 64-byte
+ * header ("QBSTATE1", version, n, n_local, world, rank, count, sum|a|^2, checksum) followed by 2^n_local interleaved
+ * little-endian (re, im) f64 pairs.  Sharded registers: every rank calls with ITS OWN path (collective, because the
+ * qubit placement is first restored to the identity).  qb_load_state needs a handle with the same n / world / rank
+ * and verifies the uploaded payload against the header's checksum (sum_j word_j*(2j+1) mod 2^64 over the raw 64-bit
+ * words, computed on the device); on QB_ERR_IO the
+ * register contents are unspecified and must be reset or reloaded. */
+int qb_save_state(qb_reg* reg, const char* path);
+int qb_load_state(qb_reg* reg, const char* path);
 
 /* sum |a_i|^2 ; max_i |a_i - b_i| (PartialEq uses < 1e-8, register.rs:411) ; sum |a_i-b_i|^2 */
 int qb_norm2(qb_reg* reg, double* out);

@@ -255,6 +255,8 @@ class Register {
         return out;
     }
     void set_state(const std::vector<c64>& s) { check(qb_write_state(h_, 0, s.size(), reinterpret_cast<const double*>(s.data()))); }
+    void save_state(const std::string& path) const { check(qb_save_state(h_, path.c_str())); }                     // raw shard file
+    void load_state(const std::string& path) { check(qb_load_state(h_, path.c_str())); }
     size_t size() const { return qb_num_qubits(h_); }                                                              // :404
     bool operator==(const Register& o) const {                                                                     // PartialEq (:409-413)
         if (size() != o.size()) return false;

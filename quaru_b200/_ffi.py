@@ -69,6 +69,8 @@ SIGNATURES = {
     "qb_measure": (ctypes.c_int, [_reg, ctypes.c_uint32, ctypes.c_double, _i32p]),
     "qb_read_state": (ctypes.c_int, [_reg, ctypes.c_uint64, ctypes.c_uint64, _dp]),
     "qb_write_state": (ctypes.c_int, [_reg, ctypes.c_uint64, ctypes.c_uint64, _dp]),
+    "qb_save_state": (ctypes.c_int, [_reg, ctypes.c_char_p]),
+    "qb_load_state": (ctypes.c_int, [_reg, ctypes.c_char_p]),
     "qb_norm2": (ctypes.c_int, [_reg, _dp]),
     "qb_max_abs_diff": (ctypes.c_int, [_reg, _reg, _dp]),
     "qb_l2_diff2": (ctypes.c_int, [_reg, _reg, _dp]),

@@ -342,6 +342,24 @@ int qb_write_state(qb_reg* reg, uint64_t offset, uint64_t count, const double* i
     return QB_OK;
 }
 
+int qb_save_state(qb_reg* reg, const char* path) {
+    CHECK_REG(reg);
+    Reg* r = REG(reg);
+    if (!path) return set_error(QB_ERR_INVALID_ARGUMENT, -1, "path is NULL");
+    QB_TRY(flush(r));
+    if (r->world > 1) QB_TRY(shard_canonicalize(r));
+    return state_save(r, path);
+}
+
+int qb_load_state(qb_reg* reg, const char* path) {
+    CHECK_REG(reg);
+    Reg* r = REG(reg);
+    if (!path) return set_error(QB_ERR_INVALID_ARGUMENT, -1, "path is NULL");
+    r->queue.clear();  // the loaded image replaces whatever the pending gates would have produced
+    for (uint32_t q = 0; q < r->n; ++q) r->phys_of[q] = q;  // files hold the identity placement
+    return state_load(r, path);
+}
+
 int qb_norm2(qb_reg* reg, double* out) {
     CHECK_REG(reg);
     Reg* r = REG(reg);

@@ -107,6 +107,10 @@ int k_scale_or_zero_all(Reg* r, bool keep, double total_prob);  // measured qubi
 int k_diff(Reg* a, Reg* b, double* max_abs, double* l2sq);
 int ensure_dmat(Reg* r, size_t bytes);
 
+// ---- raw state files (qb_stateio.cu); the caller has flushed the queue and restored the identity placement ------
+int state_save(Reg* r, const char* path);
+int state_load(Reg* r, const char* path);
+
 // ---- fused tile passes (qb_tile.cu) ----------------------------------------------------------------
 int drain_tile_events(Reg* r);  // fold finished profiling events into st_tile_ns
 int run_fused(Reg* r, std::vector<Gate>& gates);  // plan + launch; consumes `gates`

@@ -9,6 +9,7 @@ register.rs:317-318) or takes it explicitly through `u=`.
 There is no CPU path here: every method calls libquaru_b200.so.
 """
 import ctypes
+import os
 
 import numpy as np
 
@@ -237,6 +238,18 @@ class Register:
     def set_state(self, state, offset=0):
         s = np.ascontiguousarray(state, dtype=np.complex128).reshape(-1)
         _check(self._L.qb_write_state(self._h, offset, s.shape[0], _dp(s)))
+        return self
+
+    def save_state(self, path):
+        """Streams this rank's shard to a raw state file (header + interleaved f64 pairs, see include/quaru_b200.h);
+        the device-resident replacement for serialising the reference's `pub state` (register.rs:35)."""
+        _check(self._L.qb_save_state(self._h, os.fsencode(path)))
+        return self
+
+    def load_state(self, path):
+        """Restores a shard written by `save_state` into this register (same n / world / rank); pending gates are
+        dropped.  Raises EngineError (QB_ERR_IO) for a missing, truncated or corrupt file."""
+        _check(self._L.qb_load_state(self._h, os.fsencode(path)))
         return self
 
     def norm2(self):

@@ -43,6 +43,8 @@ extern "C" {
     pub fn qb_measure(reg: *mut qb_reg, target: u32, u: c_double, outcome: *mut i32) -> c_int;
     pub fn qb_read_state(reg: *mut qb_reg, offset: u64, count: u64, out: *mut c_double) -> c_int;
     pub fn qb_write_state(reg: *mut qb_reg, offset: u64, count: u64, input: *const c_double) -> c_int;
+    pub fn qb_save_state(reg: *mut qb_reg, path: *const c_char) -> c_int;
+    pub fn qb_load_state(reg: *mut qb_reg, path: *const c_char) -> c_int;
     pub fn qb_norm2(reg: *mut qb_reg, out: *mut c_double) -> c_int;
     pub fn qb_max_abs_diff(a: *mut qb_reg, b: *mut qb_reg, out: *mut c_double) -> c_int;
     pub fn qb_l2_diff2(a: *mut qb_reg, b: *mut qb_reg, out: *mut c_double) -> c_int;

@@ -56,6 +56,10 @@ fn check(rc: i32) -> Result<(), OperationError> {
     }
 }
 
+fn last_error_message() -> String {
+    unsafe { CStr::from_ptr(qb_last_error()) }.to_string_lossy().into_owned()
+}
+
 impl Register {
     /// register.rs:41
     pub fn new(input_bits: &[bool]) -> Self {
@@ -190,6 +194,24 @@ impl Register {
     pub fn set_state(&mut self, state: &Array2<c64>) {
         let s = state.as_standard_layout();
         check(unsafe { qb_write_state(self.handle, 0, s.len() as u64, s.as_ptr() as *const f64) }).expect("write_state");
+    }
+
+    /// Streams the device-resident state to a raw state file (one shard per file, see include/quaru_b200.h).
+    pub fn save_state(&self, path: &std::path::Path) -> Result<(), String> {
+        let p = std::ffi::CString::new(path.to_string_lossy().as_bytes()).map_err(|e| e.to_string())?;
+        match unsafe { qb_save_state(self.handle, p.as_ptr()) } {
+            0 => Ok(()),
+            _ => Err(last_error_message()),
+        }
+    }
+
+    /// Restores a file written by `save_state` into this register (same qubit count).
+    pub fn load_state(&mut self, path: &std::path::Path) -> Result<(), String> {
+        let p = std::ffi::CString::new(path.to_string_lossy().as_bytes()).map_err(|e| e.to_string())?;
+        match unsafe { qb_load_state(self.handle, p.as_ptr()) } {
+            0 => Ok(()),
+            _ => Err(last_error_message()),
+        }
     }
 
     /// register.rs:379

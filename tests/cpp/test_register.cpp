@@ -91,6 +91,19 @@ int main(int argc, char** argv) {
         REQUIRE(m.size() == 1 && m[0].second);
         REQUIRE(std::abs(t.state()[3] - c64(1, 0)) < 1e-12);
     }
+    {   // raw state files: save -> load is bit-exact, a missing file is an engine error
+        Register a(std::vector<bool>(9, false));
+        for (size_t i = 0; i < 9; ++i) a.apply(openqasm::u(0.3 + 0.1 * double(i), 0.7, 1.1, i));
+        const std::string path = std::string(argc > 2 ? argv[2] : "/tmp") + "/cpp_state.qbstate";
+        a.save_state(path);
+        Register b(std::vector<bool>(9, true));
+        b.load_state(path);
+        REQUIRE(a.state() == b.state());
+        std::remove(path.c_str());
+        bool threw = false;
+        try { b.load_state(path); } catch (const std::runtime_error&) { threw = true; }
+        REQUIRE(threw);
+    }
     std::printf("CPP_OK\n");
     return 0;
 }
