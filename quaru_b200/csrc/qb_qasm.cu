@@ -14,10 +14,12 @@
 // determined; here expressions are evaluated in f64 and rounded once to f32 when the U parameters are emitted.
 // Extension: `include "qelib1.inc";` is served from a built-in copy of the standard header's definitions.
 #include <ctype.h>
+#include <errno.h>
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <map>
 #include <memory>
 #include <string>
@@ -184,11 +186,35 @@ class Parser {
     void expect_sym(const char* s) { Tok t = next(); if (t.kind != T_SYM || t.text != s) fail(std::string("expected '") + s + "' but found '" + t.text + "'", t.line); }
     void expect_id(const char* s) { Tok t = next(); if (t.kind != T_ID || t.text != s) fail(std::string("expected '") + s + "'", t.line); }
     std::string ident() { Tok t = next(); if (t.kind != T_ID) fail("expected an identifier but found '" + t.text + "'", t.line); return t.text; }
-    uint32_t nninteger() { Tok t = next(); if (t.kind != T_INT) fail("expected a non-negative integer", t.line); return (uint32_t)strtoul(t.text.c_str(), nullptr, 10); }
+    uint32_t nninteger() {
+        Tok t = next();
+        if (t.kind != T_INT) fail("expected a non-negative integer", t.line);
+        errno = 0;
+        const unsigned long long v = strtoull(t.text.c_str(), nullptr, 10);
+        if (errno == ERANGE || v > 0xffffffffull) fail("integer '" + t.text + "' does not fit 32 bits", t.line);
+        return (uint32_t)v;
+    }
 
     // ---- expressions ---------------------------------------------------------------------------
-    ExprP expr(const std::vector<std::string>* params) { return additive(params); }
-    ExprP mk(Expr::Op op, ExprP a, ExprP b = nullptr) { auto e = std::make_shared<Expr>(); e->op = op; e->a = a; e->b = b; return e; }
+    // Recursion guards: the tree depth bounds the C++ stack of this parser, of eval() and of ~Expr (hostile or
+    // machine-generated input: 10^5 nested parentheses, unary-minus chains, 1+1+1+... sums).
+    static constexpr int kMaxExprNesting = 200;   // parentheses / function calls / unary chains
+    static constexpr int kMaxExprNodes = 4096;    // operator nodes of one expression (left-deep chains)
+    int expr_nesting_ = 0, expr_nodes_ = 0;
+    struct NestGuard {
+        Parser* p;
+        NestGuard(Parser* p_, int line) : p(p_) { if (++p->expr_nesting_ > kMaxExprNesting) { --p->expr_nesting_; p->fail("expression nested too deeply", line); } }
+        ~NestGuard() { --p->expr_nesting_; }
+    };
+    ExprP expr(const std::vector<std::string>* params) {
+        const bool outermost = expr_nesting_ == 0;
+        if (outermost) expr_nodes_ = 0;
+        return additive(params);
+    }
+    ExprP mk(Expr::Op op, ExprP a, ExprP b = nullptr) {
+        if (++expr_nodes_ > kMaxExprNodes) fail("expression too long", peek().line);
+        auto e = std::make_shared<Expr>(); e->op = op; e->a = a; e->b = b; return e;
+    }
     ExprP additive(const std::vector<std::string>* p) {
         ExprP l = multiplicative(p);
         while (is_sym("+") || is_sym("-")) { const bool add = next().text == "+"; l = mk(add ? Expr::ADD : Expr::SUB, l, multiplicative(p)); }
@@ -200,6 +226,7 @@ class Parser {
         return l;
     }
     ExprP unary(const std::vector<std::string>* p) {
+        NestGuard g(this, peek().line);
         if (is_sym("-")) { next(); return mk(Expr::NEG, unary(p)); }
         if (is_sym("+")) { next(); return unary(p); }
         return power(p);
@@ -310,12 +337,24 @@ class Parser {
         }
         def.qargs.push_back(ident());
         while (is_sym(",")) { next(); def.qargs.push_back(ident()); }
+        {   // formal names must be distinct (a repeated qubit argument would alias two operands of a CX in the body)
+            std::vector<std::string> names = def.params;
+            names.insert(names.end(), def.qargs.begin(), def.qargs.end());
+            std::sort(names.begin(), names.end());
+            const auto dup = std::adjacent_find(names.begin(), names.end());
+            if (dup != names.end()) fail("gate '" + name + "': formal name '" + *dup + "' is used twice", peek().line);
+        }
         if (opaque) { expect_sym(";"); gates_[name] = def; return; }
         expect_sym("{");
         while (!is_sym("}")) {
             const Tok& t = peek();
             if (t.kind == T_EOF) fail("unterminated gate body", t.line);
-            if (t.kind == T_ID && t.text == "barrier") { next(); while (!is_sym(";")) next(); next(); continue; }
+            if (t.kind == T_ID && t.text == "barrier") {
+                next();
+                while (!is_sym(";")) { if (peek().kind == T_EOF) fail("unterminated barrier", peek().line); next(); }
+                next();
+                continue;
+            }
             GateCall call;
             const int cl = t.line;
             call.name = ident();
@@ -370,7 +409,9 @@ class Parser {
         return a;
     }
 
+    static constexpr size_t kMaxOps = size_t(1) << 24;   // nested gate definitions can expand exponentially
     void emit(qb_qasm_op op, int cond_reg, uint32_t cond_val) {
+        if (prog_->ops.size() >= kMaxOps) fail("program expands to more than 2^24 basic operations", 0);
         op.cond_creg = cond_reg;
         op.cond_val = cond_val;
         prog_->ops.push_back(op);

@@ -115,6 +115,12 @@ def test_mixed_program_parses_and_runs():
     ("OPENQASM 2.0;\ninclude \"other.inc\";", "qelib1.inc"),
     ("OPENQASM 2.0;\nqreg q[1];\nU(0,0,zz) q[0];", "unknown identifier"),
     ("OPENQASM 2.0;\nqreg q[1];\nU(0,0,0) q[0] @", "unexpected character"),
+    ("OPENQASM 2.0;\nqreg q[99999999999999999999];", "does not fit 32 bits"),
+    ("OPENQASM 2.0;\nqreg q[1];\ncreg c[1];\nif (c == 99999999999) U(0,0,0) q[0];", "does not fit 32 bits"),
+    ("OPENQASM 2.0;\ngate g(a,a) x { U(a,0,0) x; }\nqreg q[1];", "used twice"),
+    ("OPENQASM 2.0;\ngate g x,x { CX x,x; }\nqreg q[1];", "used twice"),
+    ("OPENQASM 2.0;\nqreg q[1];\ngate g a { barrier a", "unterminated barrier"),
+    ("OPENQASM 2.0;\nqreg q[1];\ngate a x { a x; }", "not defined"),          # no recursion: a gate sees earlier gates only
 ])
 def test_parse_errors(src, fragment):
     oq = _oq()
@@ -129,3 +135,24 @@ def test_u_matches_the_reference_formula():
     from quaru_b200 import operation as op
     for th, ph, la in [(0.3, 1.1, -0.7), (math.pi / 2, 0.0, math.pi), (0.0, 0.0, 2.5)]:
         assert (op.u(th, ph, la, 1).matrix() == og.u(th, ph, la, 1)[0]).all()
+
+
+def test_hostile_programs_are_rejected_not_crashed_on():
+    """Recursion and expansion guards of the native parser: inputs that would otherwise overflow the C++ stack or
+    exhaust memory come back as parse errors."""
+    oq = _oq()
+    head = "OPENQASM 2.0;\nqreg q[1];\n"
+    for src, fragment in [
+        (head + "U(" + "(" * 100000 + "1" + ")" * 100000 + ",0,0) q[0];", "nested too deeply"),
+        (head + "U(" + "-" * 200000 + "1,0,0) q[0];", "nested too deeply"),
+        (head + "U(" + "+".join(["1"] * 100000) + ",0,0) q[0];", "too long"),
+        (head + "gate g0 a { U(0,0,0) a; U(0,0,0) a; }\n" +
+         "".join(f"gate g{i} a {{ g{i - 1} a; g{i - 1} a; }}\n" for i in range(1, 40)) + "g39 q[0];", "2^24"),
+    ]:
+        with pytest.raises(oq.OpenQASMParseError) as e:
+            oq.parse_openqasm_source(src)
+        assert fragment in str(e.value), str(e.value)
+    # generous limits: a 4000-term sum and 150 nested calls are fine
+    prog = oq.parse_openqasm_source(head + "U(" + "+".join(["1"] * 4000) + ",0,0) q[0];")
+    assert float(prog.get_basic_operations()[0].params[0]) == 4000.0
+    oq.parse_openqasm_source(head + "U(" + "sin(" * 150 + "1" + ")" * 150 + ",0,0) q[0];")
