@@ -18,6 +18,9 @@ int64_t last_error_payload();
 // register.rs:146-153 (get_duplicate :418-429 first, then the range check in `targets` order)
 static int validate_targets(uint32_t n, const uint32_t* targets, uint32_t k) {
     if (k > 0 && !targets) return set_error(QB_ERR_INVALID_ARGUMENT, -1, "targets is NULL");
+    // n <= 40, so any 41 targets already contain a duplicate or an out-of-range qubit: looking at no more than that
+    // keeps the sort below from sizing a buffer with a garbage arity
+    k = std::min(k, 41u);
     if (k >= 2) {
         std::vector<uint32_t> s(targets, targets + k);
         std::sort(s.begin(), s.end());
@@ -142,7 +145,7 @@ extern "C" {
 const char* qb_last_error(void) { return qb::last_error_str(); }
 int64_t qb_last_error_payload(void) { return qb::last_error_payload(); }
 int64_t qb_shard_plan_debug(uint32_t n, int32_t world, int32_t rank, const qb_gate* gates, uint64_t count, int32_t* events,
-                            uint64_t capacity, uint32_t* final_phys_of) {
+                            uint64_t capacity, uint32_t* final_phys_of) try {
     if ((count && !gates) || (capacity && !events)) return set_error(QB_ERR_INVALID_ARGUMENT, -1, "NULL argument");
     if (world < 1 || (world & (world - 1)) || rank < 0 || rank >= world)
         return set_error(QB_ERR_INVALID_ARGUMENT, world, "world must be a power of two and 0 <= rank < world");
@@ -156,9 +159,9 @@ int64_t qb_shard_plan_debug(uint32_t n, int32_t world, int32_t rank, const qb_ga
         gs.push_back(std::move(g));
     }
     return shard_plan_debug(n, world, rank, gs, events, capacity, final_phys_of);
-}
+} QB_CATCH_ALL
 
-int64_t qb_rounds_debug(uint32_t n, const qb_gate* gates, uint64_t count, void* out, uint64_t capacity) {
+int64_t qb_rounds_debug(uint32_t n, const qb_gate* gates, uint64_t count, void* out, uint64_t capacity) try {
     if ((count && !gates) || (capacity && !out)) return set_error(QB_ERR_INVALID_ARGUMENT, -1, "NULL argument");
     std::vector<Gate> gs;
     for (uint64_t i = 0; i < count; ++i) {
@@ -170,22 +173,22 @@ int64_t qb_rounds_debug(uint32_t n, const qb_gate* gates, uint64_t count, void* 
         gs.push_back(std::move(g));
     }
     return rounds_debug(n, gs, (unsigned char*)out, capacity);
-}
+} QB_CATCH_ALL
 
 const char* qb_version(void) { return "quaru_b200 0.1 (sm_100a)"; }
 
-int qb_create(uint32_t n, uint64_t basis_index, qb_reg** out) { return create_impl(n, basis_index, 0, 1, nullptr, -1, out); }
+int qb_create(uint32_t n, uint64_t basis_index, qb_reg** out) try { return create_impl(n, basis_index, 0, 1, nullptr, -1, out); } QB_CATCH_ALL
 
 int qb_create_sharded(uint32_t n, uint64_t basis_index, int32_t rank, int32_t world, const void* uid, int32_t device,
-                      qb_reg** out) {
+                      qb_reg** out) try {
     if (world > 1 && !uid) return set_error(QB_ERR_INVALID_ARGUMENT, -1, "nccl_unique_id is NULL");
     return create_impl(n, basis_index, rank, world, uid, device, out);
-}
+} QB_CATCH_ALL
 
-int qb_nccl_unique_id(void* out128) { return shard_unique_id(out128); }
+int qb_nccl_unique_id(void* out128) try { return shard_unique_id(out128); } QB_CATCH_ALL
 
 // Register::try_from_qubits (register.rs:81-102)
-int qb_create_product(const double* qubits, uint32_t n, qb_reg** out) {
+int qb_create_product(const double* qubits, uint32_t n, qb_reg** out) try {
     if (!out) return set_error(QB_ERR_INVALID_ARGUMENT, -1, "out is NULL");
     *out = nullptr;
     if (n > 0 && !qubits) return set_error(QB_ERR_INVALID_ARGUMENT, -1, "qubits is NULL");
@@ -202,9 +205,9 @@ int qb_create_product(const double* qubits, uint32_t n, qb_reg** out) {
     rc = k_init_product(REG(*out), qubits);
     if (rc != QB_OK) { free_reg(REG(*out)); *out = nullptr; }
     return rc;
-}
+} QB_CATCH_ALL
 
-int qb_clone(qb_reg* src_, qb_reg** out) {
+int qb_clone(qb_reg* src_, qb_reg** out) try {
     CHECK_REG(src_);
     if (!out) return set_error(QB_ERR_INVALID_ARGUMENT, -1, "out is NULL");
     Reg* src = REG(src_);
@@ -219,11 +222,11 @@ int qb_clone(qb_reg* src_, qb_reg** out) {
     if (e == cudaSuccess) e = cudaStreamSynchronize(src->stream);
     if (e != cudaSuccess) { free_reg(dst); *out = nullptr; return fail_cuda(e, "clone copy", __FILE__, __LINE__); }
     return QB_OK;
-}
+} QB_CATCH_ALL
 
 void qb_destroy(qb_reg* reg) { free_reg(REG(reg)); }
 
-int qb_reset(qb_reg* reg, uint64_t basis_index) {
+int qb_reset(qb_reg* reg, uint64_t basis_index) try {
     CHECK_REG(reg);
     Reg* r = REG(reg);
     if (basis_index >= (1ull << r->n)) return set_error(QB_ERR_INVALID_ARGUMENT, (int64_t)basis_index, "basis index out of range");
@@ -232,26 +235,28 @@ int qb_reset(qb_reg* reg, uint64_t basis_index) {
     for (uint32_t q = 0; q < r->n; ++q) r->phys_of[q] = q;
     const uint64_t owner = basis_index >> r->n_local;
     return k_init_basis(r, basis_index & ((1ull << r->n_local) - 1), owner == (uint64_t)r->rank);
-}
+} QB_CATCH_ALL
 
 uint32_t qb_num_qubits(const qb_reg* reg) { return reg ? reinterpret_cast<const qb::Reg*>(reg)->n : 0; }
 
 // Register::apply -> try_apply_fast (register.rs:134-191)
-int qb_apply(qb_reg* reg, const double* matrix, const uint32_t* targets, uint32_t k) {
+int qb_apply(qb_reg* reg, const double* matrix, const uint32_t* targets, uint32_t k) try {
     CHECK_REG(reg);
     Reg* r = REG(reg);
     if (!matrix) return set_error(QB_ERR_INVALID_ARGUMENT, -1, "matrix is NULL");
     QB_TRY(validate_targets(r->n, targets, k));
     return enqueue(r, matrix, targets, k);
-}
+} QB_CATCH_ALL
 
 int qb_apply_controlled(qb_reg* reg, const double* matrix, const uint32_t* targets, uint32_t k, const uint32_t* controls,
-                        uint32_t n_controls) {
+                        uint32_t n_controls) try {
     CHECK_REG(reg);
     Reg* r = REG(reg);
     if (!matrix) return set_error(QB_ERR_INVALID_ARGUMENT, -1, "matrix is NULL");
     if (n_controls && !controls) return set_error(QB_ERR_INVALID_ARGUMENT, -1, "controls is NULL");
-    std::vector<uint32_t> all(targets, targets + (targets ? k : 0));
+    if (k && !targets) return set_error(QB_ERR_INVALID_ARGUMENT, -1, "targets is NULL");
+    if (k > 40 || n_controls > 40) return set_error(QB_ERR_INVALID_TARGET, -1, "InvalidTarget: more targets or controls than qubits");
+    std::vector<uint32_t> all(targets, targets + k);
     all.insert(all.end(), controls, controls + n_controls);
     QB_TRY(validate_targets(r->n, all.data(), (uint32_t)all.size()));
     Gate g;
@@ -261,19 +266,19 @@ int qb_apply_controlled(qb_reg* reg, const double* matrix, const uint32_t* targe
     r->queue.push_back(std::move(g));
     if (!r->fusion || r->queue.size() >= r->max_queue) return flush(r);
     return QB_OK;
-}
+} QB_CATCH_ALL
 
 // Register::try_apply_all (register.rs:267-281) == the 2x2 gate on every qubit
-int qb_apply_all(qb_reg* reg, const double* m2x2) {
+int qb_apply_all(qb_reg* reg, const double* m2x2) try {
     CHECK_REG(reg);
     Reg* r = REG(reg);
     if (!m2x2) return set_error(QB_ERR_INVALID_ARGUMENT, -1, "matrix is NULL");
     for (uint32_t q = 0; q < r->n; ++q) QB_TRY(enqueue(r, m2x2, &q, 1));
     return QB_OK;
-}
+} QB_CATCH_ALL
 
 // gate loop of Register::apply_circuit (register.rs:346-350)
-int qb_apply_batch(qb_reg* reg, const qb_gate* gates, uint64_t count) {
+int qb_apply_batch(qb_reg* reg, const qb_gate* gates, uint64_t count) try {
     CHECK_REG(reg);
     Reg* r = REG(reg);
     if (count && !gates) return set_error(QB_ERR_INVALID_ARGUMENT, -1, "gates is NULL");
@@ -283,10 +288,10 @@ int qb_apply_batch(qb_reg* reg, const qb_gate* gates, uint64_t count) {
     }
     for (uint64_t i = 0; i < count; ++i) QB_TRY(enqueue(r, gates[i].matrix, gates[i].targets, gates[i].k));
     return QB_OK;
-}
+} QB_CATCH_ALL
 
 // first loop of try_measure (register.rs:303-315)
-int qb_probabilities(qb_reg* reg, uint32_t target, double* p0, double* p1) {
+int qb_probabilities(qb_reg* reg, uint32_t target, double* p0, double* p1) try {
     CHECK_REG(reg);
     Reg* r = REG(reg);
     if (!p0 || !p1) return set_error(QB_ERR_INVALID_ARGUMENT, -1, "output pointer is NULL");
@@ -294,10 +299,10 @@ int qb_probabilities(qb_reg* reg, uint32_t target, double* p0, double* p1) {
     QB_TRY(flush(r));
     if (r->world > 1) return shard_probabilities(r, target, p0, p1);
     return k_probabilities(r, (int)target, p0, p1);
-}
+} QB_CATCH_ALL
 
 // Register::try_measure (register.rs:297-342)
-int qb_measure(qb_reg* reg, uint32_t target, double u, int32_t* outcome) {
+int qb_measure(qb_reg* reg, uint32_t target, double u, int32_t* outcome) try {
     CHECK_REG(reg);
     Reg* r = REG(reg);
     if (!outcome) return set_error(QB_ERR_INVALID_ARGUMENT, -1, "outcome is NULL");
@@ -308,9 +313,9 @@ int qb_measure(qb_reg* reg, uint32_t target, double u, int32_t* outcome) {
     *outcome = res;
     if (r->world > 1) return shard_collapse(r, target, res, total);
     return k_collapse(r, target, res, total);
-}
+} QB_CATCH_ALL
 
-int qb_read_state(qb_reg* reg, uint64_t offset, uint64_t count, double* out) {
+int qb_read_state(qb_reg* reg, uint64_t offset, uint64_t count, double* out) try {
     CHECK_REG(reg);
     Reg* r = REG(reg);
     const uint64_t N = 1ull << r->n;
@@ -324,9 +329,9 @@ int qb_read_state(qb_reg* reg, uint64_t offset, uint64_t count, double* out) {
         QB_CUDA(cudaMemcpyAsync(out + 2 * (a - offset), r->state + (a - lo), (b - a) * sizeof(c64), cudaMemcpyDeviceToHost, r->stream));
     QB_CUDA(cudaStreamSynchronize(r->stream));
     return QB_OK;
-}
+} QB_CATCH_ALL
 
-int qb_write_state(qb_reg* reg, uint64_t offset, uint64_t count, const double* in) {
+int qb_write_state(qb_reg* reg, uint64_t offset, uint64_t count, const double* in) try {
     CHECK_REG(reg);
     Reg* r = REG(reg);
     const uint64_t N = 1ull << r->n;
@@ -340,27 +345,27 @@ int qb_write_state(qb_reg* reg, uint64_t offset, uint64_t count, const double* i
         QB_CUDA(cudaMemcpyAsync(r->state + (a - lo), in + 2 * (a - offset), (b - a) * sizeof(c64), cudaMemcpyHostToDevice, r->stream));
     QB_CUDA(cudaStreamSynchronize(r->stream));
     return QB_OK;
-}
+} QB_CATCH_ALL
 
-int qb_save_state(qb_reg* reg, const char* path) {
+int qb_save_state(qb_reg* reg, const char* path) try {
     CHECK_REG(reg);
     Reg* r = REG(reg);
     if (!path) return set_error(QB_ERR_INVALID_ARGUMENT, -1, "path is NULL");
     QB_TRY(flush(r));
     if (r->world > 1) QB_TRY(shard_canonicalize(r));
     return state_save(r, path);
-}
+} QB_CATCH_ALL
 
-int qb_load_state(qb_reg* reg, const char* path) {
+int qb_load_state(qb_reg* reg, const char* path) try {
     CHECK_REG(reg);
     Reg* r = REG(reg);
     if (!path) return set_error(QB_ERR_INVALID_ARGUMENT, -1, "path is NULL");
     r->queue.clear();  // the loaded image replaces whatever the pending gates would have produced
     for (uint32_t q = 0; q < r->n; ++q) r->phys_of[q] = q;  // files hold the identity placement
     return state_load(r, path);
-}
+} QB_CATCH_ALL
 
-int qb_norm2(qb_reg* reg, double* out) {
+int qb_norm2(qb_reg* reg, double* out) try {
     CHECK_REG(reg);
     Reg* r = REG(reg);
     if (!out) return set_error(QB_ERR_INVALID_ARGUMENT, -1, "out is NULL");
@@ -370,7 +375,7 @@ int qb_norm2(qb_reg* reg, double* out) {
     else QB_TRY(k_probabilities(r, -1, &p0, &p1));
     *out = p0;
     return QB_OK;
-}
+} QB_CATCH_ALL
 
 static int diff_impl(qb_reg* a_, qb_reg* b_, double* mx, double* l2) {
     CHECK_REG(a_);
@@ -389,40 +394,40 @@ static int diff_impl(qb_reg* a_, qb_reg* b_, double* mx, double* l2) {
     return QB_OK;
 }
 
-int qb_max_abs_diff(qb_reg* a, qb_reg* b, double* out) {
+int qb_max_abs_diff(qb_reg* a, qb_reg* b, double* out) try {
     if (!out) return set_error(QB_ERR_INVALID_ARGUMENT, -1, "out is NULL");
     double l2;
     return diff_impl(a, b, out, &l2);
-}
+} QB_CATCH_ALL
 
-int qb_l2_diff2(qb_reg* a, qb_reg* b, double* out) {
+int qb_l2_diff2(qb_reg* a, qb_reg* b, double* out) try {
     if (!out) return set_error(QB_ERR_INVALID_ARGUMENT, -1, "out is NULL");
     double mx;
     return diff_impl(a, b, &mx, out);
-}
+} QB_CATCH_ALL
 
-int qb_flush(qb_reg* reg) {
+int qb_flush(qb_reg* reg) try {
     CHECK_REG(reg);
     return flush(REG(reg));
-}
+} QB_CATCH_ALL
 
-int qb_sync(qb_reg* reg) {
+int qb_sync(qb_reg* reg) try {
     CHECK_REG(reg);
     Reg* r = REG(reg);
     QB_TRY(flush(r));
     QB_CUDA(cudaStreamSynchronize(r->stream));
     return QB_OK;
-}
+} QB_CATCH_ALL
 
-int qb_timer_start(qb_reg* reg) {
+int qb_timer_start(qb_reg* reg) try {
     CHECK_REG(reg);
     Reg* r = REG(reg);
     QB_TRY(flush(r));
     QB_CUDA(cudaEventRecord(r->ev0, r->stream));
     return QB_OK;
-}
+} QB_CATCH_ALL
 
-int qb_timer_stop(qb_reg* reg, float* ms) {
+int qb_timer_stop(qb_reg* reg, float* ms) try {
     CHECK_REG(reg);
     Reg* r = REG(reg);
     if (!ms) return set_error(QB_ERR_INVALID_ARGUMENT, -1, "ms is NULL");
@@ -431,9 +436,9 @@ int qb_timer_stop(qb_reg* reg, float* ms) {
     QB_CUDA(cudaEventSynchronize(r->ev1));
     QB_CUDA(cudaEventElapsedTime(ms, r->ev0, r->ev1));
     return QB_OK;
-}
+} QB_CATCH_ALL
 
-int qb_set_option(qb_reg* reg, int32_t option, int64_t value) {
+int qb_set_option(qb_reg* reg, int32_t option, int64_t value) try {
     CHECK_REG(reg);
     Reg* r = REG(reg);
     QB_TRY(flush(r));
@@ -454,9 +459,9 @@ int qb_set_option(qb_reg* reg, int32_t option, int64_t value) {
             return QB_OK;
     }
     return set_error(QB_ERR_INVALID_ARGUMENT, option, "unknown option %d", option);
-}
+} QB_CATCH_ALL
 
-int qb_get_stat(qb_reg* reg, int32_t stat, int64_t* value) {
+int qb_get_stat(qb_reg* reg, int32_t stat, int64_t* value) try {
     CHECK_REG(reg);
     Reg* r = REG(reg);
     if (!value) return set_error(QB_ERR_INVALID_ARGUMENT, -1, "value is NULL");
@@ -473,10 +478,10 @@ int qb_get_stat(qb_reg* reg, int32_t stat, int64_t* value) {
         case QB_STAT_TILE_NS: QB_TRY(drain_tile_events(r)); *value = r->st_tile_ns; return QB_OK;
     }
     return set_error(QB_ERR_INVALID_ARGUMENT, stat, "unknown stat %d", stat);
-}
+} QB_CATCH_ALL
 
 int64_t qb_plan_debug(uint32_t n, const qb_gate* gates, uint64_t count, uint32_t tile_bits, int32_t* pass_of_gate,
-                      int32_t* order_in_pass) {
+                      int32_t* order_in_pass) try {
     if (count && (!gates || !pass_of_gate || !order_in_pass)) return set_error(QB_ERR_INVALID_ARGUMENT, -1, "NULL argument");
     std::vector<Gate> gs;
     std::vector<int64_t> src;
@@ -491,6 +496,6 @@ int64_t qb_plan_debug(uint32_t n, const qb_gate* gates, uint64_t count, uint32_t
         gs.push_back(std::move(g));
     }
     return plan_debug(n, gs, tile_bits, pass_of_gate, order_in_pass);
-}
+} QB_CATCH_ALL
 
 }  // extern "C"

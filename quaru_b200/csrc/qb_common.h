@@ -27,6 +27,12 @@ int fail_cuda(cudaError_t e, const char* what, const char* file, int line);
         if (_e != cudaSuccess) return qb::fail_cuda(_e, #expr, __FILE__, __LINE__); \
     } while (0)
 
+// No C++ exception may cross the C ABI: every extern "C" entry point that can allocate is a function-try-block
+// ending in QB_CATCH_ALL (host allocation failure -> QB_ERR_OOM, anything else -> QB_ERR_UNSUPPORTED).
+int translate_exception() noexcept;
+#define QB_CATCH_ALL \
+    catch (...) { return qb::translate_exception(); }
+
 #define QB_TRY(expr)                  \
     do {                              \
         int _rc = (expr);             \

@@ -11,6 +11,9 @@
 #include <stdarg.h>
 #include <stdio.h>
 
+#include <exception>
+#include <new>
+
 #include "qb_common.h"
 
 namespace qb {
@@ -33,6 +36,18 @@ int fail_cuda(cudaError_t e, const char* what, const char* file, int line) {
                                                                               : QB_ERR_CUDA;
     return set_error(code, (int64_t)e, "CUDA error %d (%s) in %s at %s:%d", (int)e, cudaGetErrorString(e), what,
                      file, line);
+}
+
+int translate_exception() noexcept {
+    try {
+        throw;
+    } catch (const std::bad_alloc&) {
+        return set_error(QB_ERR_OOM, -1, "host allocation failed");
+    } catch (const std::exception& e) {
+        return set_error(QB_ERR_UNSUPPORTED, -1, "internal error: %s", e.what());
+    } catch (...) {
+        return set_error(QB_ERR_UNSUPPORTED, -1, "internal error (unknown exception)");
+    }
 }
 
 const char* last_error_str() { return g_err; }

@@ -546,7 +546,7 @@ using namespace qb;
 
 extern "C" {
 
-int qb_qasm_parse(const char* source, qb_qasm** out) {
+int qb_qasm_parse(const char* source, qb_qasm** out) try {
     if (!source || !out) return set_error(QB_ERR_INVALID_ARGUMENT, -1, "NULL argument");
     *out = nullptr;
     QasmProgram* p = nullptr;
@@ -554,7 +554,7 @@ int qb_qasm_parse(const char* source, qb_qasm** out) {
     if (rc != QB_OK) return rc;
     *out = reinterpret_cast<qb_qasm*>(p);
     return QB_OK;
-}
+} QB_CATCH_ALL
 
 void qb_qasm_free(qb_qasm* prog) { delete reinterpret_cast<QasmProgram*>(prog); }
 

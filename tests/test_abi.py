@@ -54,6 +54,29 @@ def test_null_and_range_arguments(engine):
     assert L.qb_last_error_payload() == 0
     assert L.qb_create_sharded(4, 0, 2, 2, None, -1, ctypes.byref(h)) == _ffi.QB_ERR_INVALID_ARGUMENT
     assert L.qb_create_sharded(4, 0, 0, 3, None, -1, ctypes.byref(h)) == _ffi.QB_ERR_INVALID_ARGUMENT
+    assert L.qb_save_state(None, b"/tmp/x") == _ffi.QB_ERR_INVALID_ARGUMENT
+    assert L.qb_load_state(None, b"/tmp/x") == _ffi.QB_ERR_INVALID_ARGUMENT
+
+
+def test_garbage_arity_is_an_invalid_target_not_a_crash(engine):
+    """An absurd arity must come back through the reference's validation (smallest duplicate, then first out of
+    range; register.rs:146-153) without sizing host buffers from it; no exception may cross the C ABI."""
+    from quaru_b200 import _ffi
+    L = _ffi.lib()
+    k = 100000
+    targets = (ctypes.c_uint32 * k)(*([7, 3] + [5] * (k - 2)))
+    m = (ctypes.c_double * 8)(1, 0, 0, 0, 0, 0, 1, 0)
+    gate = (_ffi.QbGate * 1)()
+    gate[0].matrix = ctypes.cast(m, ctypes.POINTER(ctypes.c_double))
+    gate[0].targets = targets
+    gate[0].k = k
+    pass_of, order = (ctypes.c_int32 * 1)(), (ctypes.c_int32 * 1)()
+    assert L.qb_plan_debug(12, gate, 1, 12, pass_of, order) == _ffi.QB_ERR_INVALID_TARGET
+    assert L.qb_last_error_payload() == 5                       # the duplicate
+    targets2 = (ctypes.c_uint32 * 64)(*range(64))
+    gate[0].targets, gate[0].k = targets2, 64
+    assert L.qb_plan_debug(12, gate, 1, 12, pass_of, order) == _ffi.QB_ERR_INVALID_TARGET
+    assert L.qb_last_error_payload() == 12                      # first target >= n
 
 
 def test_oracle_is_not_imported_by_the_product():
