@@ -231,8 +231,7 @@ int qb_reset(qb_reg* reg, uint64_t basis_index) try {
     Reg* r = REG(reg);
     if (basis_index >= (1ull << r->n)) return set_error(QB_ERR_INVALID_ARGUMENT, (int64_t)basis_index, "basis index out of range");
     r->queue.clear();
-    QB_CUDA(cudaSetDevice(r->device));
-    for (uint32_t q = 0; q < r->n; ++q) r->phys_of[q] = q;
+    shard_reset_placement(r);
     const uint64_t owner = basis_index >> r->n_local;
     return k_init_basis(r, basis_index & ((1ull << r->n_local) - 1), owner == (uint64_t)r->rank);
 } QB_CATCH_ALL
@@ -361,7 +360,7 @@ int qb_load_state(qb_reg* reg, const char* path) try {
     Reg* r = REG(reg);
     if (!path) return set_error(QB_ERR_INVALID_ARGUMENT, -1, "path is NULL");
     r->queue.clear();  // the loaded image replaces whatever the pending gates would have produced
-    for (uint32_t q = 0; q < r->n; ++q) r->phys_of[q] = q;  // files hold the identity placement
+    shard_reset_placement(r);  // files hold the identity placement
     return state_load(r, path);
 } QB_CATCH_ALL
 

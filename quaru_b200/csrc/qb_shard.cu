@@ -23,6 +23,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <mutex>
 
 #include "qb_shard.h"
 #include "qb_device.cuh"
@@ -44,7 +45,10 @@ struct NcclApi {
 
 static NcclApi g_nccl;
 
+static std::mutex g_nccl_mutex;
+
 static int load_nccl() {
+    std::lock_guard<std::mutex> lock(g_nccl_mutex);   // registers may be created from several host threads
     if (g_nccl.handle) return QB_OK;
     void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
     if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
@@ -124,15 +128,21 @@ int shard_init(Reg* r, const void* unique_id) {
     if (!(tr && !strcmp(tr, "nccl")) && r->world <= 8) {
         cudaIpcMemHandle_t mine, all[8];
         static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+        // Every rank takes part in both all-gathers whatever happened locally (a rank that skipped one would hang
+        // the others); a rank whose export failed publishes a zeroed handle, which no peer can open.
         char* dbuf = nullptr;
-        bool ok = cudaIpcGetMemHandle(&mine, r->state) == cudaSuccess && cudaMalloc((void**)&dbuf, 64 * (r->world + 1)) == cudaSuccess;
-        if (ok) {
-            ok = cudaMemcpyAsync(dbuf, &mine, 64, cudaMemcpyHostToDevice, r->stream) == cudaSuccess &&
-                 g_nccl.AllGather(dbuf, dbuf + 64, 64, ncclChar, s->comm, r->stream) == ncclSuccess &&
-                 cudaMemcpyAsync(all, dbuf + 64, 64 * r->world, cudaMemcpyDeviceToHost, r->stream) == cudaSuccess &&
-                 cudaStreamSynchronize(r->stream) == cudaSuccess;
+        bool ok = cudaIpcGetMemHandle(&mine, r->state) == cudaSuccess;
+        if (!ok) memset(&mine, 0, sizeof(mine));
+        cudaGetLastError();
+        QB_CUDA(cudaMalloc((void**)&dbuf, 64 * (r->world + 1)));
+        {
+            const bool moved = cudaMemcpyAsync(dbuf, &mine, 64, cudaMemcpyHostToDevice, r->stream) == cudaSuccess &&
+                               g_nccl.AllGather(dbuf, dbuf + 64, 64, ncclChar, s->comm, r->stream) == ncclSuccess &&
+                               cudaMemcpyAsync(all, dbuf + 64, 64 * r->world, cudaMemcpyDeviceToHost, r->stream) == cudaSuccess &&
+                               cudaStreamSynchronize(r->stream) == cudaSuccess;
+            cudaFree(dbuf);
+            if (!moved) return set_error(QB_ERR_NCCL, -1, "exchange of the shards' IPC handles failed");
         }
-        if (dbuf) cudaFree(dbuf);
         int opened = 0;
         if (ok) {
             for (int p = 0; p < r->world; ++p) {
@@ -154,17 +164,35 @@ int shard_init(Reg* r, const void* unique_id) {
         QB_CUDA(cudaStreamSynchronize(r->stream));
         s->p2p = true;
         for (int p = 0; p < r->world; ++p) s->p2p = s->p2p && flags[2 * p] == 1.0;
+        if (!s->p2p) {   // agreed fallback to NCCL send/recv: unmap whatever was mapped, then let nobody run ahead and
+                         // free a shard that a slower peer still has mapped
+            for (int p = 0; p < 8; ++p) {
+                if (s->peer[p] && p != r->rank) cudaIpcCloseMemHandle(s->peer[p]);
+                s->peer[p] = nullptr;
+            }
+            cudaGetLastError();
+            QB_NCCL(g_nccl.AllGather(s->d_gather, s->d_gather + 2, 2, ncclDouble, s->comm, r->stream));
+            QB_CUDA(cudaStreamSynchronize(r->stream));
+        }
     }
     return QB_OK;
+}
+
+// Back to the identity placement without moving data (the caller is about to overwrite the state).
+void shard_reset_placement(Reg* r) {
+    for (uint32_t q = 0; q < r->n; ++q) r->phys_of[q] = q;
+    if (r->shard)
+        for (uint32_t q = 0; q < r->n; ++q) r->shard->logical_at[q] = q;
 }
 
 void shard_destroy(Reg* r) {
     Shard* s = r->shard;
     if (!s) return;
-    bool mapped = false;
     for (int p = 0; p < 8; ++p)
-        if (s->peer[p] && p != r->rank) { cudaIpcCloseMemHandle(s->peer[p]); mapped = true; }
-    if (mapped && s->comm && g_nccl.AllGather) {   // nobody frees its shard before every peer has unmapped it
+        if (s->peer[p] && p != r->rank) cudaIpcCloseMemHandle(s->peer[p]);
+    // nobody frees its shard before every peer has unmapped it; keyed on the transport all ranks agreed on, so
+    // that every rank makes the same collective calls
+    if (s->p2p && s->comm && s->d_gather && g_nccl.AllGather) {
         g_nccl.AllGather(s->d_gather, s->d_gather + 2, 2, ncclDouble, s->comm, r->stream);
         cudaStreamSynchronize(r->stream);
     }

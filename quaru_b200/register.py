@@ -240,6 +240,12 @@ class Register:
         _check(self._L.qb_write_state(self._h, offset, s.shape[0], _dp(s)))
         return self
 
+    def reset(self, k=0):
+        """Back to the basis state |k> in place (what `*reg = Register::from_int(n, k)` does in the reference's
+        drivers, without reallocating 16 * 2^n bytes); pending gates are dropped."""
+        _check(self._L.qb_reset(self._h, int(k)))
+        return self
+
     def save_state(self, path):
         """Streams this rank's shard to a raw state file (header + interleaved f64 pairs, see include/quaru_b200.h);
         the device-resident replacement for serialising the reference's `pub state` (register.rs:35)."""

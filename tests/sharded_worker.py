@@ -81,6 +81,35 @@ def main():
     if rank == 0:
         print(f"exchanges in the n=20 run: {swaps}", flush=True)
 
+    if os.environ.get("QB_SHARDED_EXTRA") == "1":
+        # in-place reset and raw state files on a register whose placement has been permuted by exchanges
+        import tempfile
+        n = 3 * g + 4
+        ops = circuits.random_circuit(n, 4, seed=5)
+        reg = Register.sharded(n, 0, rank, world, new_uid(), device=local)
+        for m, t in ops:
+            reg.apply(Operation(m, t))
+        reg.flush()
+        nl, lo = n - g, rank << (n - g)
+        path = os.path.join(tempfile.gettempdir(), f"qb_shard_{os.getpid()}_{rank}.qbstate")
+        reg.save_state(path)
+        saved = reg.read(0, 1 << n)[lo:lo + (1 << nl)]
+        reg.reset(3)                                               # placement back to the identity, state |3>
+        ora = OracleRegister.from_int(n, 3)
+        for m, t in ops[:40]:
+            reg.apply(Operation(m, t))
+            ora.apply((m, t))
+        d = np.abs(reg.read(0, 1 << n)[lo:lo + (1 << nl)] - ora.state[lo:lo + (1 << nl)])
+        if d.max() > ABS_TOL:
+            failures.append(f"reset after exchanges: rank {rank} max|diff| {d.max():.3e}")
+        for m, t in ops[:25]:                                      # permute the placement again, then load over it
+            reg.apply(Operation(m, t))
+        reg.load_state(path)
+        if not np.array_equal(reg.read(0, 1 << n)[lo:lo + (1 << nl)], saved):
+            failures.append(f"save/load round trip differs on rank {rank}")
+        os.remove(path)
+        reg.close()
+
     flag = torch.tensor([len(failures)], device="cuda")
     dist.all_reduce(flag)
     for f in failures:
