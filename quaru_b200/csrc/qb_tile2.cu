@@ -506,10 +506,13 @@ static bool encode_rounds(const std::vector<Gate>& gates, const std::vector<size
             rd.sro[j] = (uint16_t)(l ^ (((l >> 3) ^ (l >> 6) ^ (l >> 9)) & 7u));
         }
         rd.op_begin = (uint16_t)n_ops;
+        // the round's ops before merging: unbounded here, the capacity of the program is checked on what is left after
+        // the three merging passes below (a round of 150 one-qubit phases shrinks to a handful of table ops)
+        std::vector<ROp> raw;
         for (size_t oi : members) {
             const LocalOp& lo = ops[oi];
             const Gate& g = *lo.g;
-            if (n_ops >= max_ops || n_mats + g.matrix.size() > max_mats) return false;
+            if (n_mats + g.matrix.size() > max_mats) return false;
             ROp op;
             memset(&op, 0, sizeof(op));
             op.mat = (uint32_t)n_mats;
@@ -549,8 +552,7 @@ static bool encode_rounds(const std::vector<Gate>& gates, const std::vector<size
                 // diag(d0, d1) on a register bit = d0 on the whole thread (thread-uniform: merges into the phase tables)
                 // times the relative phase d1/d0 on the 8 registers with the bit set (joins the phase chains of that
                 // bit): half the register traffic of multiplying all 16 registers.
-                if (op.code >= RC_DG1R && op.code < RC_DG1R + 4 && (mat[0].x != 0.0 || mat[0].y != 0.0) && n_ops + 2 <= max_ops &&
-                    n_mats + 2 <= max_mats) {
+                if (op.code >= RC_DG1R && op.code < RC_DG1R + 4 && (mat[0].x != 0.0 || mat[0].y != 0.0)) {
                     const c64 d0 = mat[0], d1 = mat[1];
                     const double den = d0.x * d0.x + d0.y * d0.y;
                     const c64 rel = make_double2((d1.x * d0.x + d1.y * d0.y) / den, (d1.y * d0.x - d1.x * d0.y) / den);
@@ -559,26 +561,27 @@ static bool encode_rounds(const std::vector<Gate>& gates, const std::vector<size
                     u.a = 0; u.k = 0; u.src[0] = u.src[1] = u.src[2] = 0;
                     u.mat = (uint32_t)n_mats;
                     prog->mats[n_mats++] = d0;
-                    prog->ops[n_ops++] = u;
+                    raw.push_back(u);
                     rd.has_tph = 1;
                     ROp r2 = u;               // relative phase on the registers with the bit set
                     r2.rmask = (uint16_t)(1u << op.a);
                     r2.code = (rel.x == -1.0 && rel.y == 0.0) ? RC_PH_NEG : RC_PH_R;
                     r2.mat = (uint32_t)n_mats;
                     prog->mats[n_mats++] = rel;
-                    prog->ops[n_ops++] = r2;
+                    raw.push_back(r2);
                     continue;
                 }
             }
             memcpy(prog->mats + n_mats, mat.data(), mat.size() * sizeof(c64));
             n_mats += mat.size();
-            prog->ops[n_ops++] = op;
+            raw.push_back(op);
         }
         // Chains of phases whose only register-bit control is the same single bit b (the controlled-phase cascade
         // of a QFT: CP(c_i, t) for many c_i) accumulate into one per-thread factor and touch the registers once.
         // Diagonal ops commute, so only an op that WRITES register bit b ends a chain.
         {
-            std::vector<ROp> in(prog->ops + rd.op_begin, prog->ops + n_ops), out;
+            std::vector<ROp>& in = raw;
+            std::vector<ROp> out;
             auto single_bit = [](const ROp& o) -> int {
                 if ((o.code != RC_PH_R && o.code != RC_PH_NEG) || __builtin_popcount(o.rmask) != 1) return -1;
                 return __builtin_ctz(o.rmask);
@@ -589,39 +592,55 @@ static bool encode_rounds(const std::vector<Gate>& gates, const std::vector<size
                 const bool d1 = c < RC_D2 || (c >= RC_H && c < RC_H + 4);
                 return d1 && (c & 3) == b && !(c >= RC_DG1R && c < RC_DG1R + 4) && !(c >= RC_DG1R_P && c < RC_DG1R_P + 4);
             };
-            // run length of the chain starting at i for bit b
-            auto chain_len = [&](size_t i, int b) {
-                size_t cnt = 0;
-                for (size_t j = i; j < in.size(); ++j) {
-                    if (single_bit(in[j]) == b) ++cnt;
-                    else if (writes_bit(in[j], b)) break;
+            // Diagonal ops commute with everything that does not write one of their bits, and nobody writes thread bits
+            // inside a round: a phase on register bit b may be deferred up to the next op that writes b.  So the phases
+            // of each bit are collected (however they interleave with other bits' phases and with dense gates elsewhere)
+            // and emitted as one group right before that writer, or at the end of the round.  The accumulator is the
+            // single per-thread `tph`, hence one group at a time: ACC ... ACC FLUSH.
+            // Groups of fewer than three phases do not pay for a flush: they stay where they are (deferring them would
+            // also separate dense gates that the layer packing below wants adjacent).
+            std::vector<int> group_of(in.size(), -1);
+            std::vector<size_t> group_size;
+            {
+                int open_group[4] = {-1, -1, -1, -1};
+                for (size_t i = 0; i < in.size(); ++i) {
+                    const int b = single_bit(in[i]);
+                    if (b >= 0) {
+                        if (open_group[b] < 0) { open_group[b] = (int)group_size.size(); group_size.push_back(0); }
+                        group_of[i] = open_group[b];
+                        group_size[open_group[b]]++;
+                        continue;
+                    }
+                    for (int wb = 0; wb < 4; ++wb)
+                        if (writes_bit(in[i], wb)) open_group[wb] = -1;
                 }
-                return cnt;
-            };
-            int cb = -1;
-            auto flush = [&]() {
-                if (cb < 0) return;
-                ROp f;
-                memset(&f, 0, sizeof(f));
-                f.code = (uint8_t)(RC_PH_FLUSH + cb);
-                out.push_back(f);
-                cb = -1;
-            };
-            for (size_t i = 0; i < in.size(); ++i) {
-                const int b = single_bit(in[i]);
-                if (b >= 0 && (cb == b || chain_len(i, b) >= 3)) {
-                    if (cb != b) flush();
-                    cb = b;
-                    ROp a = in[i];
+            }
+            std::vector<ROp> pending[4];
+            auto emit_group = [&](int b) {
+                std::vector<ROp>& grp = pending[b];
+                if (grp.empty()) return;
+                for (ROp a : grp) {
                     a.code = RC_PH_ACC;   // the -1 of RC_PH_NEG is already the coefficient at `mat`
                     a.rmask = 0;
                     out.push_back(a);
+                }
+                ROp f;
+                memset(&f, 0, sizeof(f));
+                f.code = (uint8_t)(RC_PH_FLUSH + b);
+                out.push_back(f);
+                grp.clear();
+            };
+            for (size_t i = 0; i < in.size(); ++i) {
+                const int b = single_bit(in[i]);
+                if (b >= 0) {
+                    if (group_size[group_of[i]] >= 3) pending[b].push_back(in[i]); else out.push_back(in[i]);
                     continue;
                 }
-                if (cb >= 0 && writes_bit(in[i], cb)) flush();
+                for (int wb = 0; wb < 4; ++wb)
+                    if (writes_bit(in[i], wb)) emit_group(wb);
                 out.push_back(in[i]);
             }
-            flush();
+            for (int b = 0; b < 4; ++b) emit_group(b);
             // Second pass: every thread-uniform phase (RC_PH_T, RC_DG1T, RC_PH_ACC) is a function of a few thread / outer
             // bits.  They all commute, so they are multiplied together on the host into tables over <= 4 selector bits:
             // one table op replaces several ops (each op costs ~25 instructions of decode for 4 FP64 instructions of work).

@@ -100,3 +100,30 @@ def test_program_dump_handles_small_registers_and_single_gates():
     # a lone one-qubit gate goes to the streaming kernel, not to a tile program
     passes = em.dump_programs(13, [og.hadamard(3)])
     assert [p[0] for p in passes] == ["gates"]
+
+
+def test_interleaved_phases_on_register_bits_become_per_bit_chains():
+    """156 RZ gates alternating over four qubits that are register bits of the same round: diagonal ops commute, so the
+    encoder regroups them per bit (one accumulated chain + flush each) instead of overflowing the program and falling
+    back to the shared-memory kernel."""
+    n = 14
+    rng = np.random.default_rng(0)
+    ops = [og.hadamard(q) for q in (8, 9, 10, 11)]
+    ops += [og.rz(float(rng.uniform(0, 6)), 8 + i % 4) for i in range(156)]
+    passes = em.dump_programs(n, ops)
+    assert [p[0] for p in passes] == ["prog"] and len(passes[0][1]) == 160
+    assert len(passes[0][3]["ops"]) <= 16
+    got, want, seen, st = _replay(n, ops, 5)
+    assert_close(got, want)
+
+
+def test_short_phase_groups_stay_in_place_for_layer_packing():
+    """RZ then H on each of four register bits: the lone phases must not be deferred in between the Hadamards, which the
+    layer packing wants adjacent (one RC_LAYER instead of four ops)."""
+    n = 13
+    ops = [og.rz(0.3 + q, q) for q in (8, 9, 10, 11)] + [og.hadamard(q) for q in (8, 9, 10, 11)]
+    passes = em.dump_programs(n, ops)
+    codes = [o["code"] for p in passes if p[0] == "prog" for o in p[3]["ops"]]
+    assert codes.count(em.RC_LAYER) == 1 and not any(em.RC_H <= c < em.RC_H + 4 for c in codes)
+    got, want, seen, st = _replay(n, ops, 6)
+    assert_close(got, want)
