@@ -49,6 +49,7 @@ def dump_programs(n, ops):
             passes.append(("gates", tags))
             continue
         tile_pos = list(raw[off:off + 12]); off += 12
+        prog_begin = off
         lc, h, n_rounds, n_ops, n_mats = struct.unpack_from("<5I", raw, off); off += 20
         hp = list(raw[off:off + 8]); off += 8
         rounds = []
@@ -61,7 +62,10 @@ def dump_programs(n, ops):
             rops.append({"code": f[0], "a": f[1], "b": f[2], "flags": f[3], "rmask": f[4], "tmask": f[5], "mat": f[6],
                          "src": list(f[7]), "k": f[8], "omask": f[9]})
         mats = np.frombuffer(raw, dtype=np.complex128, count=n_mats, offset=off).copy(); off += 16 * n_mats
-        passes.append(("prog", tags, tile_pos, {"lc": lc, "h": h, "hp": hp, "rounds": rounds, "ops": rops, "mats": mats}))
+        gro_first = list(struct.unpack_from("<16Q", raw, off)); off += 128
+        gro_last = list(struct.unpack_from("<16Q", raw, off)); off += 128
+        passes.append(("prog", tags, tile_pos, {"lc": lc, "h": h, "hp": hp, "rounds": rounds, "ops": rops, "mats": mats,
+                                                "gro_first": gro_first, "gro_last": gro_last, "bytes": raw[prog_begin:off]}))
     return passes
 
 
@@ -86,6 +90,10 @@ def emulate_program(state, n, tile_pos, prog):
     mats = prog["mats"]
     assert mats[0] == 1 and mats[1] == 0 and mats[2] == 0 and mats[3] == 1, "mats[0..3] must hold the identity"
     n_rounds = len(prog["rounds"])
+    for which, rd in (("gro_first", prog["rounds"][0]), ("gro_last", prog["rounds"][-1])):   # host-computed HBM offsets
+        for j in range(16):
+            want = sum(((j >> i) & 1) << tile_pos[rd["R"][i]] for i in range(4))
+            assert prog[which][j] == want, f"{which}[{j}]"
     for ri, rd in enumerate(prog["rounds"]):
         R = rd["R"]
         assert sorted(set(R)) == R and len(R) == 4
