@@ -467,6 +467,7 @@ static bool encode_rounds(const std::vector<Gate>& gates, const std::vector<size
         if (!emit_round(0xf00, {})) return false;
     }
     prog->n_rounds = (uint32_t)n_rounds;
+    prog->n_mats = (uint32_t)n_mats;
     auto goff_host = [&](uint32_t x) {
         uint64_t o = x & ((1u << lc) - 1u);
         for (uint32_t i = 0; i < prog->h; ++i) o |= (uint64_t)((x >> (lc + i)) & 1u) << prog->hp[i];
@@ -493,6 +494,35 @@ static int launch_rpass(Reg* r, const Prog& prog) {
     if (tiles > 0x7fffffffull) return set_error(QB_ERR_UNSUPPORTED, (int64_t)tiles, "too many tiles for one grid");
     if (r->profile) QB_TRY(tile_profile_begin(r));
     k2r_tile_pass<Prog><<<(unsigned)tiles, RTHREADS, sizeof(c64) << RT, r->stream>>>(r->state, prog);
+    QB_CUDA(cudaGetLastError());
+    if (r->profile) QB_TRY(tile_profile_end(r));
+    r->st_launches++;
+    r->st_passes++;
+    r->st_rounds += prog.n_rounds;
+    r->st_bytes += (int64_t)(32ull << r->n_local);
+    return QB_OK;
+}
+
+// Experimental (QB_OPT_FORCE_PATH = 5): persistent CTAs with the coefficient tables staged in shared memory.
+template <class Prog>
+static int launch_rpass_persist(Reg* r, const Prog& prog) {
+    const size_t smem = (sizeof(c64) << RT) + (size_t)prog.n_mats * sizeof(c64);
+    static std::atomic<uint64_t> attr_devs{0};
+    if (!((attr_devs.load() >> (r->device & 63)) & 1)) {
+        QB_CUDA(cudaFuncSetAttribute(k2r_tile_pass_persist<Prog>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)((sizeof(c64) << RT) + sizeof(prog.mats))));
+        attr_devs.fetch_or(1ull << (r->device & 63));
+    }
+    const uint64_t tiles = 1ull << (r->n_local - RT);
+    if (tiles > 0x7fffffffull) return set_error(QB_ERR_UNSUPPORTED, (int64_t)tiles, "too many tiles for one grid");
+    int sms = 148;
+    QB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, r->device));
+    int per_sm = 0;
+    QB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2r_tile_pass_persist<Prog>, RTHREADS, smem));
+    if (per_sm < 1) return set_error(QB_ERR_UNSUPPORTED, -1, "persistent tile kernel does not fit an SM");
+    const unsigned grid = (unsigned)std::min<uint64_t>(tiles, (uint64_t)sms * (uint64_t)per_sm);
+    if (r->profile) QB_TRY(tile_profile_begin(r));
+    k2r_tile_pass_persist<Prog><<<grid, RTHREADS, smem, r->stream>>>(r->state, prog, (uint32_t)tiles, prog.n_mats);
     QB_CUDA(cudaGetLastError());
     if (r->profile) QB_TRY(tile_profile_end(r));
     r->st_launches++;
@@ -549,13 +579,13 @@ int run_pass_v2(Reg* r, const std::vector<Gate>& gates, const std::vector<size_t
         RProgSmall small;
         if (encode_rounds(gates, gate_idx, tile_pos, lc, &small)) {
             *handled = true;
-            return launch_rpass(r, small);
+            return r->force_path == 5 ? launch_rpass_persist(r, small) : launch_rpass(r, small);
         }
     }
     static thread_local RProgLarge large;
     if (!encode_rounds(gates, gate_idx, tile_pos, lc, &large)) return QB_OK;
     *handled = true;
-    return launch_rpass(r, large);
+    return r->force_path == 5 ? launch_rpass_persist(r, large) : launch_rpass(r, large);
 }
 
 }  // namespace qb

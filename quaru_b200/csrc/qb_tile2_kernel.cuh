@@ -45,7 +45,7 @@ struct RoundDesc {
 
 template <int NOPS, int NMAT, int NROUNDS>
 struct RProgram {
-    uint32_t lc, h, n_rounds, pad;
+    uint32_t lc, h, n_rounds, n_mats;   // n_mats: coefficients in use (what the persistent kernel stages in shared memory)
     uint8_t hp[8];
     uint64_t gro_first[16], gro_last[16];  // offset from the tile base of register j in the first / last round
     RoundDesc rounds[NROUNDS];
@@ -271,167 +271,44 @@ __device__ __forceinline__ void r_d2_dispatch(c64 (&v)[16], const c64* M, uint32
     }
 }
 
+#ifdef QB_HOST_EMU
+#define QB_DYNAMIC_SMEM(name) unsigned char* name = qb_emu_shared()
+#else
+#define QB_DYNAMIC_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#endif
+
+// One CTA per tile; coefficients are read from the kernel-parameter (constant) bank.  Every measurement so far was taken
+// with this kernel.
 template <class Prog>
 __global__ void __launch_bounds__(RTHREADS, 2) k2r_tile_pass(c64* __restrict__ st, const __grid_constant__ Prog prog) {
-#ifdef QB_HOST_EMU
-    unsigned char* smem_raw = qb_emu_shared();
-#else
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-#endif
+    QB_DYNAMIC_SMEM(smem_raw);
     c64* tile = reinterpret_cast<c64*>(smem_raw);
-    const uint32_t tid = threadIdx.x;
-    const uint32_t lc = prog.lc, h = prog.h;
+#define QB_TILE_IX blockIdx.x
+#define QB_MATS prog.mats
+#include "qb_tile2_body.inc"
+#undef QB_TILE_IX
+#undef QB_MATS
+}
 
-    uint64_t base = (uint64_t)blockIdx.x << lc;
-    for (uint32_t j = 0; j < h; ++j) base = insert_zero_bit(base, prog.hp[j]);
-
-    // tile-local index -> offset from `base` (bit-linear: low lc bits direct, bit lc+i -> global bit hp[i])
-    auto goff = [&](uint32_t x) -> uint64_t {
-        uint64_t o = x & ((1u << lc) - 1u);
-        for (uint32_t i = 0; i < h; ++i) o |= (uint64_t)((x >> (lc + i)) & 1u) << prog.hp[i];
-        return o;
-    };
-
-    c64 v[16];
-    uint32_t tl = 0;          // this thread's tile-local index bits (register bits are 0)
-    auto set_mapping = [&](const RoundDesc& rd) {
-        tl = 0;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) tl |= ((tid >> i) & 1u) << rd.tb[i];
-    };
-
-    // ---- round 0: HBM -> registers ------------------------------------------------------------------
-    set_mapping(prog.rounds[0]);
-    {
-        const uint64_t gt = base + goff(tl);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = ld128(st + (gt + prog.gro_first[j]));
-    }
-
-    for (uint32_t r = 0; r < prog.n_rounds; ++r) {
-        const RoundDesc& rd = prog.rounds[r];
-        if (r > 0) {  // transpose through shared memory into the new register bits
-            const uint32_t s_t = swz(tl);
-            const RoundDesc& prev = prog.rounds[r - 1];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) tile[s_t ^ prev.sro[j]] = v[j];
-            __syncthreads();
-            set_mapping(rd);
-            const uint32_t s_n = swz(tl);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = tile[s_n ^ rd.sro[j]];
-            __syncthreads();
-        }
-        c64 tph = make_double2(1.0, 0.0);
-        // `tph` doubles as the accumulator of a phase chain on one register bit: the host orders the ops of a round so that
-        // every other writer of tph (merged tables, Hadamard scalars, wide phases) comes after the last RC_PH_FLUSH
-        for (uint32_t oi = rd.op_begin; oi < rd.op_end; ++oi) {
-            const ROp& op = prog.ops[oi];
-            if (((uint64_t)blockIdx.x & op.omask) != op.omask) continue;   // uniform per CTA; blockIdx needs no live register
-            const bool act = (tl & op.tmask) == op.tmask;       // per thread; never branched on
-            const uint32_t rmask = op.rmask;
-            // mats[0..3] holds the 2x2 identity (mats[0] = mats[3] = 1): an inactive thread reads its coefficients
-            // from there (per-thread constant-bank index) instead of selecting them register by register
-            const c64* M = prog.mats + (act ? op.mat : 0u);
-            const c64* M1 = prog.mats + (act ? op.mat : 3u);   // for two-entry diagonals: (1, 1)
-            const c64 one = make_double2(1.0, 0.0);
-            // one flat switch: nested switches would double the register traffic at the joins
-            switch (op.code) {
-#define QB_CASE4(BASE, STMT0, STMT1, STMT2, STMT3) \
-    case BASE + 0: STMT0; break;                  \
-    case BASE + 1: STMT1; break;                  \
-    case BASE + 2: STMT2; break;                  \
-    case BASE + 3: STMT3; break;
-                QB_CASE4(RC_D1C, (r_d1<0, false, false>(v, M, 0, act)), (r_d1<1, false, false>(v, M, 0, act)),
-                         (r_d1<2, false, false>(v, M, 0, act)), (r_d1<3, false, false>(v, M, 0, act)))
-                QB_CASE4(RC_D1R, (r_d1<0, true, false>(v, M, 0, act)), (r_d1<1, true, false>(v, M, 0, act)),
-                         (r_d1<2, true, false>(v, M, 0, act)), (r_d1<3, true, false>(v, M, 0, act)))
-                QB_CASE4(RC_DG1R, (r_dg1<0, false>(v, M[0], M1[act ? 1 : 0], 0, act)), (r_dg1<1, false>(v, M[0], M1[act ? 1 : 0], 0, act)),
-                         (r_dg1<2, false>(v, M[0], M1[act ? 1 : 0], 0, act)), (r_dg1<3, false>(v, M[0], M1[act ? 1 : 0], 0, act)))
-                QB_CASE4(RC_D1C_P, (r_d1<0, false, true>(v, M, rmask, act)), (r_d1<1, false, true>(v, M, rmask, act)),
-                         (r_d1<2, false, true>(v, M, rmask, act)), (r_d1<3, false, true>(v, M, rmask, act)))
-                QB_CASE4(RC_D1R_P, (r_d1<0, true, true>(v, M, rmask, act)), (r_d1<1, true, true>(v, M, rmask, act)),
-                         (r_d1<2, true, true>(v, M, rmask, act)), (r_d1<3, true, true>(v, M, rmask, act)))
-                QB_CASE4(RC_DG1R_P, (r_dg1<0, true>(v, M[0], M1[act ? 1 : 0], rmask, act)), (r_dg1<1, true>(v, M[0], M1[act ? 1 : 0], rmask, act)),
-                         (r_dg1<2, true>(v, M[0], M1[act ? 1 : 0], rmask, act)), (r_dg1<3, true>(v, M[0], M1[act ? 1 : 0], rmask, act)))
-#undef QB_CASE4
-                case RC_D2:
-                    if (act) r_d2_dispatch(v, prog.mats + op.mat, op.a, op.b, rmask);   // rare: controlled 2-qubit dense gates only
-                    break;
-                case RC_PH_T: ip_cmul(tph, M[0]); break;
-                case RC_PH_NEG: r_ph_dispatch<true>(v, rmask, one, act ? -1.0 : 1.0); break;
-                case RC_PH_R: r_ph_dispatch<false>(v, rmask, M[0], 1.0); break;
-                case RC_PH_ACC: ip_cmul(tph, M[0]); break;        // M is the identity slot for inactive threads
-                case RC_TAB:
-                case RC_TAB_ACC: {   // host-merged phases: index a table with up to 4 thread / outer bits
-                    const uint32_t sel[4] = {op.src[0], op.src[1], op.src[2], op.b};
-                    uint32_t idx = 0;
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        if (i >= op.k) break;
-                        const uint32_t sc = sel[i];
-                        idx |= (((sc & 0x80) ? (blockIdx.x >> (sc & 0x3f)) : (tl >> (sc & 0x3f))) & 1u) << i;
-                    }
-                    const c64 f = prog.mats[op.mat + idx];
-                    ip_cmul(tph, f);   // RC_TAB_ACC: the chain's flush follows; RC_TAB: applied at the end of the round
-                } break;
-                case RC_LAYER: {   // several dense one-qubit gates decoded once (masks are packed into otherwise unused fields)
-                    const uint32_t present = op.k & 15u, hmask = op.k >> 4;
-                    const c64* C = prog.mats + op.mat;
-                    r_layer_slot<0>(v, present, hmask, C, op.tmask, tl);
-                    r_layer_slot<1>(v, present, hmask, C, op.rmask, tl);
-                    r_layer_slot<2>(v, present, hmask, C, (uint32_t)op.src[0] | ((uint32_t)op.src[1] << 8), tl);
-                    r_layer_slot<3>(v, present, hmask, C, (uint32_t)op.src[2] | ((uint32_t)op.b << 8), tl);
-                } break;
-                case RC_PH_FLUSH + 0: r_ph<1, false>(v, tph, 1.0); tph = one; break;
-                case RC_PH_FLUSH + 1: r_ph<2, false>(v, tph, 1.0); tph = one; break;
-                case RC_PH_FLUSH + 2: r_ph<4, false>(v, tph, 1.0); tph = one; break;
-                case RC_PH_FLUSH + 3: r_ph<8, false>(v, tph, 1.0); tph = one; break;
-                case RC_H + 0: r_h<0>(v); break;   // uncontrolled; the scalar is folded into a table by the host
-                case RC_H + 1: r_h<1>(v); break;
-                case RC_H + 2: r_h<2>(v); break;
-                case RC_H + 3: r_h<3>(v); break;
-                case RC_DG1T: {  // one-qubit diagonal (RZ...) on a thread bit or an outer bit: one multiply per thread
-                    const uint32_t s0 = op.src[0];
-                    const uint32_t bit = (s0 & 0x80) ? ((blockIdx.x >> (s0 & 0x3f)) & 1u) : ((tl >> (s0 & 0x3f)) & 1u);
-                    ip_cmul(tph, act ? prog.mats[op.mat + bit] : one);
-                } break;
-                default: {  // RC_DG: k <= 3 index bits from register / thread / outer bits
-                    uint32_t fixed = 0, r0 = 0, r1 = 0, r2 = 0;   // r_i: mask over the register index j that feeds index bit i
-#pragma unroll
-                    for (int i = 0; i < 3; ++i) {
-                        if (i >= op.k) break;
-                        const uint32_t s = op.src[i];
-                        if (s & 0x80) fixed |= ((blockIdx.x >> (s & 0x3f)) & 1u) << i;
-                        else if (s & 0x40) fixed |= ((tl >> (s & 0x3f)) & 1u) << i;
-                        else if (i == 0) r0 = 1u << (s & 3u);
-                        else if (i == 1) r1 = 1u << (s & 3u);
-                        else r2 = 1u << (s & 3u);
-                    }
-                    if ((r0 | r1 | r2) == 0 && rmask == 0) {
-                        ip_cmul(tph, act ? prog.mats[op.mat + fixed] : one);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            if ((j & rmask) != rmask) continue;
-                            const uint32_t x = fixed | ((j & r0) ? 1u : 0u) | ((j & r1) ? 2u : 0u) | ((j & r2) ? 4u : 0u);
-                            ip_cmul(v[j], act ? prog.mats[op.mat + x] : one);   // per-thread indexed constant load
-                        }
-                    }
-                } break;
-            }
-        }
-        if (rd.has_tph) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) ip_cmul(v[j], tph);
-        }
-    }
-
-    // ---- last round: registers -> HBM -----------------------------------------------------------------
-    {
-        const uint64_t gt = base + goff(tl);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) st128(st + (gt + prog.gro_last[j]), v[j]);
+// Experimental persistent variant (QB_OPT_FORCE_PATH = 5, not yet measured): grid = resident CTAs; each CTA stages the
+// coefficient tables of the pass in shared memory once (behind the 64 KB transpose buffer), where per-thread-indexed reads
+// are not serialised like divergent constant-bank reads, and then walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...
+// Within a tile the transpose buffer is last read before a __syncthreads() (second barrier of a transpose), so the next
+// tile's first transpose store needs no extra barrier.
+template <class Prog>
+__global__ void __launch_bounds__(RTHREADS, 2) k2r_tile_pass_persist(c64* __restrict__ st, const __grid_constant__ Prog prog, uint32_t n_tiles,
+                                                                     uint32_t n_mats) {
+    QB_DYNAMIC_SMEM(smem_raw);
+    c64* tile = reinterpret_cast<c64*>(smem_raw);
+    c64* s_mats = tile + (1u << RT);
+    for (uint32_t i = threadIdx.x; i < n_mats; i += RTHREADS) s_mats[i] = prog.mats[i];
+    __syncthreads();
+    for (uint32_t tile_ix = blockIdx.x; tile_ix < n_tiles; tile_ix += gridDim.x) {
+#define QB_TILE_IX tile_ix
+#define QB_MATS s_mats
+#include "qb_tile2_body.inc"
+#undef QB_TILE_IX
+#undef QB_MATS
     }
 }
 

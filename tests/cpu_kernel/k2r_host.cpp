@@ -33,6 +33,7 @@ static bool deserialise(const unsigned char* bytes, uint64_t len, Prog* prog) {
     prog->lc = hdr[0];
     prog->h = hdr[1];
     prog->n_rounds = n_rounds;
+    prog->n_mats = n_mats;
     const unsigned char* r = bytes + 20;
     memcpy(prog->hp, r, 8); r += 8;
     memcpy(prog->rounds, r, n_rounds * sizeof(RoundDesc)); r += n_rounds * sizeof(RoundDesc);
@@ -60,6 +61,41 @@ static void run_grid(double* state, uint32_t n_tiles, const Prog& prog) {
         });
     for (std::thread& th : threads) th.join();
     pthread_barrier_destroy(&qb_emu_barrier);
+}
+
+template <class Prog>
+static void run_grid_persist(double* state, uint32_t n_tiles, uint32_t grid, const Prog& prog) {
+    blockDim = {RTHREADS, 1, 1};
+    gridDim = {grid, 1, 1};
+    pthread_barrier_init(&qb_emu_barrier, nullptr, RTHREADS);
+    std::vector<std::thread> threads;
+    for (unsigned t = 0; t < RTHREADS; ++t)
+        threads.emplace_back([=, &prog]() {
+            for (unsigned b = 0; b < grid; ++b) {   // the resident CTAs, one after the other
+                threadIdx = {t, 0, 0};
+                blockIdx = {b, 0, 0};
+                k2r_tile_pass_persist<Prog>(reinterpret_cast<c64*>(state), prog, n_tiles, prog.n_mats);
+                pthread_barrier_wait(&qb_emu_barrier);
+            }
+        });
+    for (std::thread& th : threads) th.join();
+    pthread_barrier_destroy(&qb_emu_barrier);
+}
+
+// the experimental persistent kernel with `grid` CTAs walking the tiles
+extern "C" int k2r_host_run_persist(double* state, uint32_t n, const unsigned char* program, uint64_t len, int use_small, uint32_t grid) {
+    if (n < RT || grid < 1) return -1;
+    const uint32_t n_tiles = 1u << (n - RT);
+    if (use_small) {
+        static RProgSmall small;
+        if (!deserialise(program, len, &small)) return -2;
+        run_grid_persist(state, n_tiles, grid, small);
+    } else {
+        static RProgLarge large;
+        if (!deserialise(program, len, &large)) return -2;
+        run_grid_persist(state, n_tiles, grid, large);
+    }
+    return 0;
 }
 
 extern "C" int k2r_host_run(double* state, uint32_t n, const unsigned char* program, uint64_t len, int use_small) {

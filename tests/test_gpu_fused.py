@@ -1,5 +1,7 @@
 """GPU parity of the FUSED path (gate queue -> planner -> tile-pass kernel) against the oracle, on the
 synthetic circuits of the BASELINE configs and on adversarial gate mixes, for several tile sizes."""
+import os
+
 import numpy as np
 import pytest
 
@@ -134,3 +136,15 @@ def test_register_blocked_qft_and_diagonals(engine, n):
             ops.append(((np.sqrt(0.5) * np.array([[1, 1], [1, -1]])).astype(complex), [qs[2]]))
     reg, ora = _run(engine, n, ops, 3400 + n, tile_bits=12, batch=True)
     assert_close(reg.state, ora.state, f"v2 qft+diag n={n}")
+
+
+@pytest.mark.skipif(os.environ.get("QB_TEST_EXPERIMENTAL") != "1", reason="experimental kernel variants: set QB_TEST_EXPERIMENTAL=1")
+@pytest.mark.parametrize("n,kind", [(12, "layers"), (14, "mixed"), (16, "qft"), (18, "layers"), (20, "mixed")])
+def test_persistent_tile_kernel(engine, n, kind):
+    """QB_OPT_FORCE_PATH = 5: persistent CTAs, coefficient tables staged in shared memory.  Its logic is covered on CPU by
+    tests/test_cpu_kernel.py; this is the hardware check, opt-in until the variant has been measured."""
+    ops = {"layers": circuits.random_circuit(n, 5, seed=n), "qft": circuits.qft_circuit(n), "mixed": circuits.mixed_circuit(n, 120, n)}[kind]
+    reg, ora = _run(engine, n, ops, 3000 + n, force=5)
+    assert_close(reg.state, ora.state, f"persistent kernel n={n} {kind}")
+    ref, _ = _run(engine, n, ops, 3000 + n)
+    assert reg.max_abs_diff(ref) == 0.0, "same arithmetic as the default kernel: bit-identical"

@@ -1,4 +1,6 @@
-"""Fused vs unfused timing of the C3-style random layered circuit.  Usage: bench_fused.py [n] [depth] [tile_bits]"""
+"""Fused vs unfused timing of the C3-style random layered circuit.
+Usage: bench_fused.py [n] [depth] [tile_bits] [fused|both] [layers|qft] [force_path]
+force_path 5 selects the experimental persistent tile kernel (QB_OPT_FORCE_PATH)."""
 import os
 import sys
 import time
@@ -16,6 +18,8 @@ ops = [Operation(m, t) for m, t in raw]
 depth = 1 if kind == 'qft' else depth
 reg = Register.new([False] * n)
 reg.set_option(2, tb)
+if len(sys.argv) > 6:
+    reg.set_option(4, int(sys.argv[6]))
 B = 32.0 * (1 << n)
 modes = (1,) if (len(sys.argv) > 4 and sys.argv[4] == 'fused') else (1, 0)
 for fusion in modes:
