@@ -16,11 +16,13 @@ struct __align__(32) c64x2 {
 // Streaming accesses: every amplitude is read once and written once per pass and the state is far
 // larger than L2, so loads do not allocate in L1 and stores are plain write-back.
 #ifdef QB_HOST_EMU
+__device__ __forceinline__ void prefetch_l2(const void*) {}
 __device__ __forceinline__ c64x2 ld256(const double2* p) { c64x2 v; v.a = p[0]; v.b = p[1]; return v; }
 __device__ __forceinline__ void st256(double2* p, const c64x2& v) { p[0] = v.a; p[1] = v.b; }
 __device__ __forceinline__ double2 ld128(const double2* p) { return *p; }
 __device__ __forceinline__ void st128(double2* p, const double2& v) { *p = v; }
 #else
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ c64x2 ld256(const double2* p) {
     c64x2 v;
     asm volatile("ld.global.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"

@@ -503,14 +503,16 @@ static int launch_rpass(Reg* r, const Prog& prog) {
     return QB_OK;
 }
 
-// Experimental (QB_OPT_FORCE_PATH = 5): persistent CTAs with the coefficient tables staged in shared memory.
-template <class Prog>
+// Experimental (QB_OPT_FORCE_PATH = 5..8): persistent CTAs with the coefficient tables staged in shared memory;
+// 6 and 8 also stage the op records, 7 and 8 prefetch the next tile into L2.
+template <class Prog, bool STAGE_OPS, bool PREFETCH>
 static int launch_rpass_persist(Reg* r, const Prog& prog) {
-    const size_t smem = (sizeof(c64) << RT) + (size_t)prog.n_mats * sizeof(c64);
+    const uint32_t n_ops = prog.rounds[prog.n_rounds - 1].op_end;
+    const size_t smem = (sizeof(c64) << RT) + (size_t)prog.n_mats * sizeof(c64) + (STAGE_OPS ? (size_t)n_ops * sizeof(ROp) : 0);
     static std::atomic<uint64_t> attr_devs{0};
     if (!((attr_devs.load() >> (r->device & 63)) & 1)) {
-        QB_CUDA(cudaFuncSetAttribute(k2r_tile_pass_persist<Prog>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)((sizeof(c64) << RT) + sizeof(prog.mats))));
+        QB_CUDA(cudaFuncSetAttribute(k2r_tile_pass_persist<Prog, STAGE_OPS, PREFETCH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)((sizeof(c64) << RT) + sizeof(prog.mats) + sizeof(prog.ops))));
         attr_devs.fetch_or(1ull << (r->device & 63));
     }
     const uint64_t tiles = 1ull << (r->n_local - RT);
@@ -518,11 +520,11 @@ static int launch_rpass_persist(Reg* r, const Prog& prog) {
     int sms = 148;
     QB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, r->device));
     int per_sm = 0;
-    QB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2r_tile_pass_persist<Prog>, RTHREADS, smem));
+    QB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2r_tile_pass_persist<Prog, STAGE_OPS, PREFETCH>, RTHREADS, smem));
     if (per_sm < 1) return set_error(QB_ERR_UNSUPPORTED, -1, "persistent tile kernel does not fit an SM");
     const unsigned grid = (unsigned)std::min<uint64_t>(tiles, (uint64_t)sms * (uint64_t)per_sm);
     if (r->profile) QB_TRY(tile_profile_begin(r));
-    k2r_tile_pass_persist<Prog><<<grid, RTHREADS, smem, r->stream>>>(r->state, prog, (uint32_t)tiles, prog.n_mats);
+    k2r_tile_pass_persist<Prog, STAGE_OPS, PREFETCH><<<grid, RTHREADS, smem, r->stream>>>(r->state, prog, (uint32_t)tiles, prog.n_mats, n_ops);
     QB_CUDA(cudaGetLastError());
     if (r->profile) QB_TRY(tile_profile_end(r));
     r->st_launches++;
@@ -568,6 +570,17 @@ int64_t encode_rounds_debug(const std::vector<Gate>& gates, const std::vector<si
     return (int64_t)(w - out);
 }
 
+template <class Prog>
+static int launch_variant(Reg* r, const Prog& prog) {
+    switch (r->force_path) {
+        case 5: return launch_rpass_persist<Prog, false, false>(r, prog);
+        case 6: return launch_rpass_persist<Prog, true, false>(r, prog);
+        case 7: return launch_rpass_persist<Prog, false, true>(r, prog);
+        case 8: return launch_rpass_persist<Prog, true, true>(r, prog);
+        default: return launch_rpass(r, prog);
+    }
+}
+
 // returns QB_OK and *handled = true if the pass went through the register-blocked kernel
 int run_pass_v2(Reg* r, const std::vector<Gate>& gates, const std::vector<size_t>& gate_idx, const std::vector<uint32_t>& tile_pos,
                 uint32_t lc, bool* handled) {
@@ -579,13 +592,13 @@ int run_pass_v2(Reg* r, const std::vector<Gate>& gates, const std::vector<size_t
         RProgSmall small;
         if (encode_rounds(gates, gate_idx, tile_pos, lc, &small)) {
             *handled = true;
-            return r->force_path == 5 ? launch_rpass_persist(r, small) : launch_rpass(r, small);
+            return launch_variant(r, small);
         }
     }
     static thread_local RProgLarge large;
     if (!encode_rounds(gates, gate_idx, tile_pos, lc, &large)) return QB_OK;
     *handled = true;
-    return r->force_path == 5 ? launch_rpass_persist(r, large) : launch_rpass(r, large);
+    return launch_variant(r, large);
 }
 
 }  // namespace qb

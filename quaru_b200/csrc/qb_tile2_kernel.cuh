@@ -285,30 +285,55 @@ __global__ void __launch_bounds__(RTHREADS, 2) k2r_tile_pass(c64* __restrict__ s
     c64* tile = reinterpret_cast<c64*>(smem_raw);
 #define QB_TILE_IX blockIdx.x
 #define QB_MATS prog.mats
+#define QB_OPS prog.ops
+#define QB_AFTER_FIRST_LOADS
 #include "qb_tile2_body.inc"
 #undef QB_TILE_IX
 #undef QB_MATS
+#undef QB_OPS
+#undef QB_AFTER_FIRST_LOADS
 }
 
-// Experimental persistent variant (QB_OPT_FORCE_PATH = 5, not yet measured): grid = resident CTAs; each CTA stages the
-// coefficient tables of the pass in shared memory once (behind the 64 KB transpose buffer), where per-thread-indexed reads
-// are not serialised like divergent constant-bank reads, and then walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...
+// Experimental persistent variants (QB_OPT_FORCE_PATH = 5..8, not yet measured on hardware): grid = resident CTAs; each CTA
+// stages the coefficient tables of the pass in shared memory once (behind the 64 KB transpose buffer), where
+// per-thread-indexed reads are not serialised like divergent constant-bank reads, and then walks tiles blockIdx.x,
+// blockIdx.x + gridDim.x, ...   STAGE_OPS also stages the op records; PREFETCH asks L2 for the next tile's lines as soon as
+// the current tile's loads have been issued, so that the next round-0 loads find them there.
 // Within a tile the transpose buffer is last read before a __syncthreads() (second barrier of a transpose), so the next
 // tile's first transpose store needs no extra barrier.
-template <class Prog>
+template <class Prog, bool STAGE_OPS, bool PREFETCH>
 __global__ void __launch_bounds__(RTHREADS, 2) k2r_tile_pass_persist(c64* __restrict__ st, const __grid_constant__ Prog prog, uint32_t n_tiles,
-                                                                     uint32_t n_mats) {
+                                                                     uint32_t n_mats, uint32_t n_ops) {
     QB_DYNAMIC_SMEM(smem_raw);
     c64* tile = reinterpret_cast<c64*>(smem_raw);
     c64* s_mats = tile + (1u << RT);
+    ROp* s_ops = reinterpret_cast<ROp*>(s_mats + n_mats);   // 16-byte aligned; an ROp is three 8-byte words
     for (uint32_t i = threadIdx.x; i < n_mats; i += RTHREADS) s_mats[i] = prog.mats[i];
+    if (STAGE_OPS) {
+        const uint64_t* src = reinterpret_cast<const uint64_t*>(prog.ops);
+        uint64_t* dst = reinterpret_cast<uint64_t*>(s_ops);
+        for (uint32_t i = threadIdx.x; i < 3u * n_ops; i += RTHREADS) dst[i] = src[i];
+    }
     __syncthreads();
     for (uint32_t tile_ix = blockIdx.x; tile_ix < n_tiles; tile_ix += gridDim.x) {
 #define QB_TILE_IX tile_ix
 #define QB_MATS s_mats
+#define QB_OPS (STAGE_OPS ? s_ops : prog.ops)
+#define QB_AFTER_FIRST_LOADS                                                                         \
+    if (PREFETCH) {                                                                                  \
+        const uint32_t next_ix = tile_ix + gridDim.x;                                                \
+        if (next_ix < n_tiles && (tid & 7u) == 0u) { /* lanes are tile bits 0..4: one thread per 128-byte line */ \
+            uint64_t nb = (uint64_t)next_ix << lc;                                                   \
+            for (uint32_t j = 0; j < h; ++j) nb = insert_zero_bit(nb, prog.hp[j]);                   \
+            const uint64_t ngt = nb + goff(tl);                                                      \
+            _Pragma("unroll") for (int j = 0; j < 16; ++j) prefetch_l2(st + (ngt + prog.gro_first[j])); \
+        }                                                                                            \
+    }
 #include "qb_tile2_body.inc"
 #undef QB_TILE_IX
 #undef QB_MATS
+#undef QB_OPS
+#undef QB_AFTER_FIRST_LOADS
     }
 }
 

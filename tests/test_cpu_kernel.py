@@ -34,11 +34,11 @@ def host_kernel():
     lib.k2r_host_run.restype = ctypes.c_int
     lib.k2r_host_run.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_char_p, ctypes.c_uint64, ctypes.c_int]
     lib.k2r_host_run_persist.restype = ctypes.c_int
-    lib.k2r_host_run_persist.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_char_p, ctypes.c_uint64, ctypes.c_int, ctypes.c_uint32]
+    lib.k2r_host_run_persist.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_char_p, ctypes.c_uint64, ctypes.c_int, ctypes.c_uint32, ctypes.c_int]
     return lib
 
 
-def _run(lib, n, ops, seed, small=False, persist_grid=0):
+def _run(lib, n, ops, seed, small=False, persist_grid=0, variant=5):
     s0 = random_state(n, seed)
     ora = OracleRegister(s0.copy(), n)
     for o in ops:
@@ -56,7 +56,7 @@ def _run(lib, n, ops, seed, small=False, persist_grid=0):
         n_prog += 1
         assert p[2][:p[3]["lc"]] == list(range(p[3]["lc"]))
         if persist_grid:
-            rc = lib.k2r_host_run_persist(dev.ctypes.data, n, p[3]["bytes"], len(p[3]["bytes"]), int(small), persist_grid)
+            rc = lib.k2r_host_run_persist(dev.ctypes.data, n, p[3]["bytes"], len(p[3]["bytes"]), int(small), persist_grid, variant)
         else:
             rc = lib.k2r_host_run(dev.ctypes.data, n, p[3]["bytes"], len(p[3]["bytes"]), int(small))
         assert rc == 0, rc
@@ -97,14 +97,18 @@ def test_small_program_instantiation(host_kernel):
     assert_close(dev, want)
 
 
-@pytest.mark.parametrize("n,grid,kind", [(14, 3, "layers"), (14, 1, "mixed"), (15, 5, "qft"), (13, 2, "mixed"), (12, 1, "layers")])
-def test_persistent_variant_on_the_host_compiled_kernel(host_kernel, n, grid, kind):
-    """The experimental persistent kernel (QB_OPT_FORCE_PATH = 5): `grid` CTAs walk 2^(n-12) tiles with the coefficient
-    tables staged in shared memory; grids that do not divide the tile count and a single CTA doing everything included."""
+@pytest.mark.parametrize("n,grid,kind,variant", [(14, 3, "layers", 5), (14, 1, "mixed", 6), (15, 5, "qft", 7), (13, 2, "mixed", 8),
+                                                 (12, 1, "layers", 6), (14, 3, "qft", 8)])
+def test_persistent_variants_on_the_host_compiled_kernel(host_kernel, n, grid, kind, variant):
+    """The experimental persistent kernels (QB_OPT_FORCE_PATH = 5..8): `grid` CTAs walk 2^(n-12) tiles with the coefficient
+    tables (and, for 6 / 8, the op records) staged in shared memory; grids that do not divide the tile count and a single
+    CTA doing everything included."""
     ops = {"layers": circuits.random_circuit(n, 4, seed=n), "qft": circuits.qft_circuit(n), "mixed": circuits.mixed_circuit(n, 100, n)}[kind]
-    dev, emu, want, n_prog = _run(host_kernel, n, ops, 80 + n, persist_grid=grid)
+    dev, emu, want, n_prog = _run(host_kernel, n, ops, 80 + n, persist_grid=grid, variant=variant)
     assert n_prog >= 1
-    assert_close(dev, want, f"persistent kernel vs oracle, {kind} n={n} grid={grid}")
-    dev_s, _, _, _ = _run(host_kernel, 13, [og.hadamard(3), og.cnot(3, 9), og.rz(0.7, 9), og.hadamard(12)], 3, small=True, persist_grid=2)
-    ref_s, _, want_s, _ = _run(host_kernel, 13, [og.hadamard(3), og.cnot(3, 9), og.rz(0.7, 9), og.hadamard(12)], 3, small=True)
-    assert np.array_equal(dev_s, ref_s), "same arithmetic in both kernels: bit-identical results"
+    assert_close(dev, want, f"persistent kernel {variant} vs oracle, {kind} n={n} grid={grid}")
+    ref, _, _, _ = _run(host_kernel, n, ops, 80 + n)
+    assert np.array_equal(dev, ref), "same arithmetic as the default kernel: bit-identical results"
+    short = [og.hadamard(3), og.cnot(3, 9), og.rz(0.7, 9), og.hadamard(12)]
+    dev_s, _, want_s, _ = _run(host_kernel, 13, short, 3, small=True, persist_grid=2, variant=variant)
+    assert_close(dev_s, want_s)
