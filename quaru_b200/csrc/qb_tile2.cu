@@ -503,15 +503,15 @@ static int launch_rpass(Reg* r, const Prog& prog) {
     return QB_OK;
 }
 
-// Experimental (QB_OPT_FORCE_PATH = 5..8): persistent CTAs with the coefficient tables staged in shared memory;
-// 6 and 8 also stage the op records, 7 and 8 prefetch the next tile into L2.
-template <class Prog, bool STAGE_OPS, bool PREFETCH>
+// Experimental (QB_OPT_FORCE_PATH = 5..10): persistent CTAs with the coefficient tables staged in shared memory;
+// 6, 8, 10 also stage the op records, 7 and 8 prefetch the next tile into L2, 9 and 10 fetch op records one op ahead.
+template <class Prog, bool STAGE_OPS, bool PREFETCH, bool AHEAD>
 static int launch_rpass_persist(Reg* r, const Prog& prog) {
     const uint32_t n_ops = prog.rounds[prog.n_rounds - 1].op_end;
     const size_t smem = (sizeof(c64) << RT) + (size_t)prog.n_mats * sizeof(c64) + (STAGE_OPS ? (size_t)n_ops * sizeof(ROp) : 0);
     static std::atomic<uint64_t> attr_devs{0};
     if (!((attr_devs.load() >> (r->device & 63)) & 1)) {
-        QB_CUDA(cudaFuncSetAttribute(k2r_tile_pass_persist<Prog, STAGE_OPS, PREFETCH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        QB_CUDA(cudaFuncSetAttribute(k2r_tile_pass_persist<Prog, STAGE_OPS, PREFETCH, AHEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)((sizeof(c64) << RT) + sizeof(prog.mats) + sizeof(prog.ops))));
         attr_devs.fetch_or(1ull << (r->device & 63));
     }
@@ -520,11 +520,11 @@ static int launch_rpass_persist(Reg* r, const Prog& prog) {
     int sms = 148;
     QB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, r->device));
     int per_sm = 0;
-    QB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2r_tile_pass_persist<Prog, STAGE_OPS, PREFETCH>, RTHREADS, smem));
+    QB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2r_tile_pass_persist<Prog, STAGE_OPS, PREFETCH, AHEAD>, RTHREADS, smem));
     if (per_sm < 1) return set_error(QB_ERR_UNSUPPORTED, -1, "persistent tile kernel does not fit an SM");
     const unsigned grid = (unsigned)std::min<uint64_t>(tiles, (uint64_t)sms * (uint64_t)per_sm);
     if (r->profile) QB_TRY(tile_profile_begin(r));
-    k2r_tile_pass_persist<Prog, STAGE_OPS, PREFETCH><<<grid, RTHREADS, smem, r->stream>>>(r->state, prog, (uint32_t)tiles, prog.n_mats, n_ops);
+    k2r_tile_pass_persist<Prog, STAGE_OPS, PREFETCH, AHEAD><<<grid, RTHREADS, smem, r->stream>>>(r->state, prog, (uint32_t)tiles, prog.n_mats, n_ops);
     QB_CUDA(cudaGetLastError());
     if (r->profile) QB_TRY(tile_profile_end(r));
     r->st_launches++;
@@ -573,10 +573,12 @@ int64_t encode_rounds_debug(const std::vector<Gate>& gates, const std::vector<si
 template <class Prog>
 static int launch_variant(Reg* r, const Prog& prog) {
     switch (r->force_path) {
-        case 5: return launch_rpass_persist<Prog, false, false>(r, prog);
-        case 6: return launch_rpass_persist<Prog, true, false>(r, prog);
-        case 7: return launch_rpass_persist<Prog, false, true>(r, prog);
-        case 8: return launch_rpass_persist<Prog, true, true>(r, prog);
+        case 5: return launch_rpass_persist<Prog, false, false, false>(r, prog);
+        case 6: return launch_rpass_persist<Prog, true, false, false>(r, prog);
+        case 7: return launch_rpass_persist<Prog, false, true, false>(r, prog);
+        case 8: return launch_rpass_persist<Prog, true, true, false>(r, prog);
+        case 9: return launch_rpass_persist<Prog, false, false, true>(r, prog);
+        case 10: return launch_rpass_persist<Prog, true, false, true>(r, prog);
         default: return launch_rpass(r, prog);
     }
 }

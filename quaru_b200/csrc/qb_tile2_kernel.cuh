@@ -285,12 +285,14 @@ __global__ void __launch_bounds__(RTHREADS, 2) k2r_tile_pass(c64* __restrict__ s
     c64* tile = reinterpret_cast<c64*>(smem_raw);
 #define QB_TILE_IX blockIdx.x
 #define QB_MATS prog.mats
-#define QB_OPS prog.ops
+#define QB_BEFORE_OPS
+#define QB_FETCH_OP const ROp& op = prog.ops[oi];
 #define QB_AFTER_FIRST_LOADS
 #include "qb_tile2_body.inc"
 #undef QB_TILE_IX
 #undef QB_MATS
-#undef QB_OPS
+#undef QB_BEFORE_OPS
+#undef QB_FETCH_OP
 #undef QB_AFTER_FIRST_LOADS
 }
 
@@ -298,10 +300,11 @@ __global__ void __launch_bounds__(RTHREADS, 2) k2r_tile_pass(c64* __restrict__ s
 // stages the coefficient tables of the pass in shared memory once (behind the 64 KB transpose buffer), where
 // per-thread-indexed reads are not serialised like divergent constant-bank reads, and then walks tiles blockIdx.x,
 // blockIdx.x + gridDim.x, ...   STAGE_OPS also stages the op records; PREFETCH asks L2 for the next tile's lines as soon as
-// the current tile's loads have been issued, so that the next round-0 loads find them there.
+// the current tile's loads have been issued, so that the next round-0 loads find them there; AHEAD fetches each op record
+// one op before its use.
 // Within a tile the transpose buffer is last read before a __syncthreads() (second barrier of a transpose), so the next
 // tile's first transpose store needs no extra barrier.
-template <class Prog, bool STAGE_OPS, bool PREFETCH>
+template <class Prog, bool STAGE_OPS, bool PREFETCH, bool AHEAD>
 __global__ void __launch_bounds__(RTHREADS, 2) k2r_tile_pass_persist(c64* __restrict__ st, const __grid_constant__ Prog prog, uint32_t n_tiles,
                                                                      uint32_t n_mats, uint32_t n_ops) {
     QB_DYNAMIC_SMEM(smem_raw);
@@ -319,6 +322,13 @@ __global__ void __launch_bounds__(RTHREADS, 2) k2r_tile_pass_persist(c64* __rest
 #define QB_TILE_IX tile_ix
 #define QB_MATS s_mats
 #define QB_OPS (STAGE_OPS ? s_ops : prog.ops)
+    /* AHEAD: the record of op oi+1 is requested before op oi is executed, so the decode chain of the next op (record ->   \
+       compare / branch -> coefficients) starts from registers instead of from a load */                                    \
+#define QB_BEFORE_OPS ROp op_next; if (AHEAD && rd.op_begin < rd.op_end) op_next = QB_OPS[rd.op_begin];
+#define QB_FETCH_OP                                                        \
+    ROp op_cur;                                                            \
+    if (AHEAD) { op_cur = op_next; if (oi + 1 < rd.op_end) op_next = QB_OPS[oi + 1]; } \
+    const ROp& op = AHEAD ? op_cur : QB_OPS[oi];
 #define QB_AFTER_FIRST_LOADS                                                                         \
     if (PREFETCH) {                                                                                  \
         const uint32_t next_ix = tile_ix + gridDim.x;                                                \
@@ -333,6 +343,8 @@ __global__ void __launch_bounds__(RTHREADS, 2) k2r_tile_pass_persist(c64* __rest
 #undef QB_TILE_IX
 #undef QB_MATS
 #undef QB_OPS
+#undef QB_BEFORE_OPS
+#undef QB_FETCH_OP
 #undef QB_AFTER_FIRST_LOADS
     }
 }

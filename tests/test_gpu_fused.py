@@ -139,11 +139,11 @@ def test_register_blocked_qft_and_diagonals(engine, n):
 
 
 @pytest.mark.skipif(os.environ.get("QB_TEST_EXPERIMENTAL") != "1", reason="experimental kernel variants: set QB_TEST_EXPERIMENTAL=1")
-@pytest.mark.parametrize("variant", [5, 6, 7, 8])
+@pytest.mark.parametrize("variant", [5, 6, 7, 8, 9, 10])
 @pytest.mark.parametrize("n,kind", [(12, "layers"), (14, "mixed"), (16, "qft"), (18, "layers"), (20, "mixed")])
 def test_persistent_tile_kernels(engine, n, kind, variant):
-    """QB_OPT_FORCE_PATH = 5..8: persistent CTAs, coefficient tables (6, 8: op records too) staged in shared memory, 7 / 8 with
-    an L2 prefetch of the next tile.  Their logic is covered on CPU by tests/test_cpu_kernel.py; this is the hardware check,
+    """QB_OPT_FORCE_PATH = 5..10: persistent CTAs, coefficient tables (6, 8: op records too) staged in shared memory, 7 / 8 with
+    an L2 prefetch of the next tile, 9 / 10 with op records fetched one op ahead.  Their logic is covered on CPU by tests/test_cpu_kernel.py; this is the hardware check,
     opt-in until the variants have been measured."""
     ops = {"layers": circuits.random_circuit(n, 5, seed=n), "qft": circuits.qft_circuit(n), "mixed": circuits.mixed_circuit(n, 120, n)}[kind]
     reg, ora = _run(engine, n, ops, 3000 + n, force=variant)
