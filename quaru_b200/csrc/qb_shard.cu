@@ -90,7 +90,15 @@ struct Shard {
     bool dry = false;                  // planner introspection: record exchanges, move no data
     std::vector<int32_t> events;       // dry run: [gate index, g', V..., J...] per exchange
     int64_t cur_gate = -1;
+    int64_t dry_passes = 0;            // dry run: state sweeps the local planner would need for the epochs so far
 };
+
+// dry run only: how many sweeps the fused local path would need for this batch of mapped gates
+static int64_t count_passes(Reg* r, std::vector<Gate>& batch) {
+    std::vector<int32_t> pass_of(batch.size()), order(batch.size());
+    for (size_t i = 0; i < batch.size(); ++i) batch[i].tag = (int64_t)i;
+    return plan_debug(r->n_local, batch, 12, pass_of.data(), order.data());
+}
 
 int shard_unique_id(void* out128) {
     if (!out128) return set_error(QB_ERR_INVALID_ARGUMENT, -1, "out128 is NULL");
@@ -436,14 +444,14 @@ static MapResult map_gate(const Reg* r, const Gate& g, Gate* out) {
 }
 
 // Chooses and performs the exchange needed before gates[i] (a dense gate with a global target).
-static int swap_for(Reg* r, const std::vector<Gate>& gates, size_t i) {
+static int swap_for(Reg* r, const std::vector<Gate>& gates, size_t i, const std::vector<char>* done = nullptr) {
     Shard* s = r->shard;
     const uint32_t nl = r->n_local, n = r->n;
     const size_t INF = (size_t)-1;
-    // next use as a DENSE target, per logical qubit, from gate i on
+    // next use as a DENSE target, per logical qubit, from gate i on (gates already executed out of order do not count)
     std::vector<size_t> next_use(n, INF);
     for (size_t j = gates.size(); j-- > i;)
-        if (gates[j].kind == GK_DENSE)
+        if (gates[j].kind == GK_DENSE && !(done && (*done)[j]))
             for (uint32_t t : gates[j].targets) next_use[t] = j;
     // candidates to evict: the top local positions (contiguous runs stay long), widened if needed
     const uint32_t window = std::min<uint32_t>(nl, 10);
@@ -485,13 +493,64 @@ static int swap_for(Reg* r, const std::vector<Gate>& gates, size_t i) {
     return exchange(r, V, J);
 }
 
+// Experimental scheduler (QB_SHARD_REORDER=1, off by default until it has run on hardware): instead of cutting the gate
+// list at the first gate that needs an exchange, that gate is DEFERRED and the scan goes on; later gates that are local and
+// commute with everything deferred (same read / write rule as the pass planner, on logical qubits) still join the current
+// epoch.  Epochs get longer, so the local planner fuses more gates per sweep and fewer exchanges are needed.  Every decision
+// depends only on the placement and on the gates' qubit masks, never on this rank's bits, so all ranks stay in step.
+static int shard_run_reordered(Reg* r, std::vector<Gate>& gates) {
+    Shard* s = r->shard;
+    std::vector<char> done(gates.size(), 0);
+    size_t remaining = gates.size(), first_open = 0;
+    while (remaining) {
+        std::vector<Gate> batch;
+        uint64_t blocked_w = 0, blocked_r = 0;
+        size_t first_deferred = (size_t)-1;
+        while (first_open < gates.size() && done[first_open]) ++first_open;
+        for (size_t i = first_open; i < gates.size(); ++i) {
+            if (done[i]) continue;
+            const Gate& g = gates[i];
+            const uint64_t wm = g.kind == GK_DENSE ? g.target_mask() : 0;
+            const uint64_t rm = g.ctrl_mask | (g.kind == GK_DIAG ? g.target_mask() : 0);
+            bool defer = (wm & (blocked_w | blocked_r)) || (rm & blocked_w);
+            Gate m;
+            MapResult res = MAP_SKIP;
+            if (!defer) {
+                res = map_gate(r, g, &m);
+                if (res == MAP_NEEDS_SWAP) {
+                    defer = true;
+                    if (first_deferred == (size_t)-1) first_deferred = i;
+                }
+            }
+            if (defer) { blocked_w |= wm; blocked_r |= rm; continue; }
+            if (s->dry) s->events.push_back(-1 - (int32_t)(g.tag >= 0 ? g.tag : (int64_t)i));   // run record
+            if (res == MAP_LOCAL) batch.push_back(std::move(m));
+            done[i] = 1;
+            --remaining;
+        }
+        if (!batch.empty() && !s->dry) QB_TRY(run_local(r, batch));
+        if (!batch.empty() && s->dry) s->dry_passes += count_passes(r, batch);
+        if (!remaining) break;
+        if (first_deferred == (size_t)-1) return set_error(QB_ERR_UNSUPPORTED, -1, "internal: scheduler made no progress");
+        s->cur_gate = gates[first_deferred].tag >= 0 ? gates[first_deferred].tag : (int64_t)first_deferred;
+        QB_TRY(swap_for(r, gates, first_deferred, &done));
+        Gate probe;
+        if (map_gate(r, gates[first_deferred], &probe) == MAP_NEEDS_SWAP)
+            return set_error(QB_ERR_UNSUPPORTED, (int64_t)first_deferred, "internal: gate still global after exchange");
+    }
+    return QB_OK;
+}
+
 int shard_run(Reg* r, std::vector<Gate>& gates) {
+    const char* reorder = getenv("QB_SHARD_REORDER");
+    if (reorder && !strcmp(reorder, "1")) return shard_run_reordered(r, gates);
     std::vector<Gate> batch;
     for (size_t i = 0; i < gates.size(); ++i) {
         Gate m;
         MapResult res = map_gate(r, gates[i], &m);
         if (res == MAP_NEEDS_SWAP) {
             if (!batch.empty() && !r->shard->dry) QB_TRY(run_local(r, batch));
+            if (!batch.empty() && r->shard->dry) r->shard->dry_passes += count_passes(r, batch);
             batch.clear();
             r->shard->cur_gate = gates[i].tag >= 0 ? gates[i].tag : (int64_t)i;
             QB_TRY(swap_for(r, gates, i));
@@ -501,6 +560,7 @@ int shard_run(Reg* r, std::vector<Gate>& gates) {
         if (res == MAP_LOCAL) batch.push_back(std::move(m));
     }
     if (!batch.empty() && !r->shard->dry) QB_TRY(run_local(r, batch));
+    if (!batch.empty() && r->shard->dry) r->shard->dry_passes += count_passes(r, batch);
     return QB_OK;
 }
 
@@ -524,6 +584,11 @@ int64_t shard_plan_debug(uint32_t n, int world, int rank, std::vector<Gate>& gat
     r.shard = nullptr;
     if (rc != QB_OK) return rc;
     if (s.events.size() > capacity) return set_error(QB_ERR_INVALID_ARGUMENT, (int64_t)s.events.size(), "event buffer too small");
+    if (getenv("QB_SHARD_PLAN_STATS")) {   // introspection: trailing record [INT32_MIN, sweeps of the local planner]
+        s.events.push_back(INT32_MIN);
+        s.events.push_back((int32_t)s.dry_passes);
+        if (s.events.size() > capacity) return set_error(QB_ERR_INVALID_ARGUMENT, (int64_t)s.events.size(), "event buffer too small");
+    }
     for (size_t i = 0; i < s.events.size(); ++i) events[i] = s.events[i];
     if (final_phys_of)
         for (uint32_t q = 0; q < n; ++q) final_phys_of[q] = r.phys_of[q];

@@ -168,3 +168,91 @@ def test_ranks_agree_over_gloo(world):
         p.join(timeout=60)
     assert all(ok for _, ok, _ in res), res
     assert len({cnt for _, _, cnt in res}) == 1
+
+
+# ---- experimental commutation-aware scheduler (QB_SHARD_REORDER=1) ---------------------------------------------------
+def _plan_events_reordered(n, world, rank, ops):
+    """Event stream with run records: a negative entry -1 - i means "gate i runs now"; exchange records as before."""
+    from quaru_b200 import _ffi
+    L = _ffi.lib()
+    arr = (_ffi.QbGate * max(len(ops), 1))()
+    keep = []
+    for i, (m, t) in enumerate(ops):
+        mm = np.ascontiguousarray(m, dtype=np.complex128)
+        tt = (ctypes.c_uint32 * max(len(t), 1))(*t)
+        keep += [mm, tt]
+        arr[i].matrix = mm.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+        arr[i].targets = tt
+        arr[i].k = len(t)
+    cap = 64 * (len(ops) + 1)
+    ev = (ctypes.c_int32 * cap)()
+    phys = (ctypes.c_uint32 * n)()
+    os.environ["QB_SHARD_REORDER"] = "1"
+    try:
+        cnt = L.qb_shard_plan_debug(n, world, rank, arr, len(ops), ev, cap, phys)
+    finally:
+        del os.environ["QB_SHARD_REORDER"]
+    assert cnt >= 0, _ffi.last_error()
+    flat, out, i = list(ev)[:cnt], [], 0
+    while i < len(flat):
+        if flat[i] < 0:
+            out.append(("run", -1 - flat[i]))
+            i += 1
+        else:
+            gp = flat[i + 1]
+            out.append(("swap", flat[i + 2:i + 2 + gp], flat[i + 2 + gp:i + 2 + 2 * gp]))
+            i += 2 + 2 * gp
+    return out, list(phys)
+
+
+def _replay_reordered(n, world, ops, events, seed):
+    g = int(np.log2(world))
+    nl = n - g
+    s0 = random_state(n, seed)
+    ora = OracleRegister(s0.copy(), n)
+    for o in ops:
+        ora.apply(o)
+    phys, st, ran = list(range(n)), s0.copy(), []
+    for e in events:
+        if e[0] == "swap":
+            for v, j in zip(e[1], e[2]):
+                assert 0 <= v < nl and 0 <= j < g
+                a = st.reshape((2,) * n)
+                st = np.ascontiguousarray(np.swapaxes(a, n - 1 - v, n - 1 - (nl + j))).reshape(-1)
+                ql, qg = phys.index(v), phys.index(nl + j)
+                phys[ql], phys[qg] = nl + j, v
+            continue
+        m, t = ops[e[1]]
+        for q in _dense_targets(m, t):
+            assert phys[q] < nl, f"gate {e[1]}: dense target {q} is on a rank bit when the gate runs"
+        st = oracle_np.apply_np(st, n, m, [phys[q] for q in t])
+        ran.append(e[1])
+    identities = [i for i, (m, t) in enumerate(ops) if np.array_equal(np.asarray(m), np.eye(len(m)))]
+    assert sorted(ran + identities) == list(range(len(ops))), "every gate runs exactly once"
+    a = st.reshape((2,) * n)
+    a = np.transpose(a, [n - 1 - phys[n - 1 - ax] for ax in range(n)])
+    return np.ascontiguousarray(a).reshape(-1), ora.state, phys
+
+
+@pytest.mark.parametrize("n,world,kind", [(8, 2, "layers"), (10, 4, "layers"), (12, 8, "layers"), (9, 4, "qft"), (10, 4, "mixed"),
+                                          (12, 8, "mixed"), (14, 4, "bench")])
+def test_reordering_scheduler_replay_matches_oracle(n, world, kind):
+    g = int(np.log2(world))
+    if kind == "layers":
+        ops = circuits.random_circuit(n, 8, seed=n + world)
+    elif kind == "qft":
+        ops = circuits.qft_circuit(n)
+    elif kind == "bench":
+        ops = circuits.qft_circuit(n) + circuits.random_circuit(n, 10, seed=1)
+    else:
+        ops = [o for o in circuits.mixed_circuit(n, 100, seed=n) if len(o[1]) <= n - g]
+    per_rank = [_plan_events_reordered(n, world, r, ops) for r in range(world)]
+    for ev, ph in per_rank[1:]:
+        assert ev == per_rank[0][0] and ph == per_rank[0][1], "ranks disagree on the schedule"
+    events, final_phys = per_rank[0]
+    got, want, phys = _replay_reordered(n, world, ops, events, seed=n * 17 + world)
+    assert phys == final_phys
+    assert_close(got, want, f"reordered replay n={n} P={world} {kind}")
+    swaps = sum(1 for e in events if e[0] == "swap")
+    base = len(_plan_events(n, world, 0, ops)[0])
+    assert swaps <= base, f"deferring must not need more exchanges ({swaps} vs {base})"

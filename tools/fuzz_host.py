@@ -2,6 +2,7 @@
 
     python tools/fuzz_host.py rounds  SECONDS [SEED0]   pass planner + round encoder, replayed by tests/rounds_emulator.py
     python tools/fuzz_host.py shard   SECONDS [SEED0]   exchange schedule of the sharded path (qb_shard_plan_debug), all ranks
+    python tools/fuzz_host.py shard-reorder SECONDS [SEED0]   the same for the experimental scheduler (QB_SHARD_REORDER=1)
     python tools/fuzz_host.py qasm    COUNT   [SEED0]   mutated OpenQASM programs: the parser must return, never crash
 
 Round 1: 2700 `rounds`, 26000 `shard` and 160000 `qasm` cases without a finding after the fixes they prompted
@@ -93,8 +94,8 @@ def fuzz_rounds(budget, seed0):
     print("rounds: cases", it, "worst error", worst)
 
 
-def fuzz_shard(budget, seed0):
-    from tests.test_dist_cpu import _plan_events, _replay
+def fuzz_shard(budget, seed0, reorder=False):
+    from tests.test_dist_cpu import _plan_events, _plan_events_reordered, _replay, _replay_reordered
     t0, it, worst = time.time(), 0, 0.0
     while time.time() - t0 < budget:
         seed = seed0 + it
@@ -109,17 +110,17 @@ def fuzz_shard(budget, seed0):
             if len(t) <= n - g:
                 ops.append((m, t))
         try:
-            per_rank = [_plan_events(n, world, r, ops) for r in range(world)]
+            per_rank = [(_plan_events_reordered if reorder else _plan_events)(n, world, r, ops) for r in range(world)]
             for ev, ph in per_rank[1:]:
                 assert ev == per_rank[0][0] and ph == per_rank[0][1], "ranks disagree on the schedule"
-            got, want, phys = _replay(n, world, ops, per_rank[0][0], seed)
+            got, want, phys = (_replay_reordered if reorder else _replay)(n, world, ops, per_rank[0][0], seed)
             assert phys == per_rank[0][1], "final placement differs from the replay"
             err = float(np.max(np.abs(got - want)))
             worst = max(worst, err)
             assert err <= 1e-11, f"amplitude error {err}"
         except AssertionError as e:
             print("FAIL seed", seed, "n", n, "world", world, "gates", len(ops), str(e)[:200])
-    print("shard: cases", it, "worst error", worst)
+    print("shard-reorder:" if reorder else "shard:", "cases", it, "worst error", worst)
 
 
 def fuzz_qasm(count, seed0):
@@ -161,4 +162,5 @@ def fuzz_qasm(count, seed0):
 if __name__ == "__main__":
     mode, amount = sys.argv[1], float(sys.argv[2])
     seed0 = int(sys.argv[3]) if len(sys.argv) > 3 else 0
-    {"rounds": fuzz_rounds, "shard": fuzz_shard, "qasm": lambda a, s: fuzz_qasm(int(a), s)}[mode](amount, seed0)
+    {"rounds": fuzz_rounds, "shard": fuzz_shard, "shard-reorder": lambda a, s: fuzz_shard(a, s, True),
+     "qasm": lambda a, s: fuzz_qasm(int(a), s)}[mode](amount, seed0)
