@@ -51,9 +51,10 @@ static bool is_x(const Gate& g) {
            g.matrix[1].x == 1.0 && g.matrix[1].y == 0.0 && g.matrix[2].x == 1.0 && g.matrix[2].y == 0.0;
 }
 
+// `low_first`: one of the two round-selection strategies tried by encode_rounds (see the round loop).
 template <class Prog>
-static bool encode_rounds(const std::vector<Gate>& gates, const std::vector<size_t>& gate_idx, const std::vector<uint32_t>& tile_pos,
-                          uint32_t lc, Prog* prog) {
+static bool encode_rounds_with(const std::vector<Gate>& gates, const std::vector<size_t>& gate_idx, const std::vector<uint32_t>& tile_pos,
+                               uint32_t lc, Prog* prog, bool low_first) {
     const uint32_t T = (uint32_t)tile_pos.size();
     if (T != RT) return false;
     int8_t local_of[64];
@@ -443,6 +444,22 @@ static bool encode_rounds(const std::vector<Gate>& gates, const std::vector<size
     while (remaining) {
         uint32_t R = 0, blocked_w = 0, blocked_r = 0;
         const uint32_t allowed = first ? io_allowed : 0xfffu;
+        // Strategy `low_first`: middle rounds reserve their register bits for the LOW tile bits (0..4) that are ready.
+        // Those can never be register bits of the HBM-facing first and last rounds, so serving them early tends to leave
+        // the high bits for a last round that can store straight to HBM (otherwise an empty extra round -- one more
+        // transpose -- has to be appended).  Dependencies decide which strategy needs fewer rounds; both are tried.
+        if (!first && low_first) {
+            uint32_t bw = 0, br = 0;
+            for (size_t i = 0; i < ops.size(); ++i) {
+                if (done[i]) continue;
+                const LocalOp& lo = ops[i];
+                bool ok = !(lo.dense & (bw | br)) && !(lo.reads & bw);
+                if (ok && (lo.dense & io_allowed)) ok = false;
+                if (ok && __builtin_popcount(R | lo.dense) > 4) ok = false;
+                if (!ok) { bw |= lo.dense; br |= lo.reads; continue; }
+                R |= lo.dense;   // reserved; the op itself is picked up by the scan below
+            }
+        }
         std::vector<size_t> members;
         for (size_t i = 0; i < ops.size(); ++i) {
             if (done[i]) continue;
@@ -480,6 +497,19 @@ static bool encode_rounds(const std::vector<Gate>& gates, const std::vector<size
         prog->gro_first[j] = goff_host(lf);
         prog->gro_last[j] = goff_host(ll);
     }
+    return true;
+}
+
+// Encodes the pass with both round-selection strategies and keeps the program with fewer rounds (then fewer ops).
+template <class Prog>
+static bool encode_rounds(const std::vector<Gate>& gates, const std::vector<size_t>& gate_idx, const std::vector<uint32_t>& tile_pos,
+                          uint32_t lc, Prog* prog) {
+    static thread_local Prog other;
+    const bool ok_a = encode_rounds_with(gates, gate_idx, tile_pos, lc, prog, false);
+    const bool ok_b = encode_rounds_with(gates, gate_idx, tile_pos, lc, &other, true);
+    if (!ok_b) return ok_a;
+    auto n_ops = [](const Prog& p) { return p.rounds[p.n_rounds - 1].op_end; };
+    if (!ok_a || other.n_rounds < prog->n_rounds || (other.n_rounds == prog->n_rounds && n_ops(other) < n_ops(*prog))) *prog = other;
     return true;
 }
 
