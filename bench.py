@@ -182,18 +182,25 @@ def run_reference(args):
         return
     n = args.qubits or (33 + int(np.log2(args.gpus)))
     threads = os.cpu_count() or 1
-    vals = []
+    vals, step_ms = [], []
     cb = None
     for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
         cb = cpu_baseline(n, threads, budget_s=6.0)
         if i >= args.warmup:
             vals.append(cb["value"])
+            step_ms.append((time.perf_counter() - t0) * 1e3)
     v = float(np.mean(vals)) if vals else cb["value"]
     cb["value"] = v
+    g = int(np.log2(args.gpus))
+    # same workload description as our arm; a step here is the bounded CPU sample of it described in cpu_baseline.sample
+    # (ms_per_step is the wall time of that sample, not of the 33-qubit circuit, which would take days on the host)
     line = {"impl": "reference", "metric": "gates/s", "value": v, "unit": "gates/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"QFT + {N_LAYERS} random H/RZ/CNOT/CZ layers, {n} qubits (CPU sample scaled, see cpu_baseline.sample)"},
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(step_ms)) if step_ms else None,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"QFT({n}) + {N_LAYERS} random H/RZ/CNOT/CZ layers, {n} qubits, Complex<f64> state "
+                                   f"{16 * (1 << n) / 1e9:.1f} GB ({16 * (1 << (n - g)) / 1e9:.1f} GB per GPU)",
+                       "qubits": n, "step": "bounded CPU sample of the workload, scaled (see cpu_baseline.sample)"},
             "cpu_baseline": cb,
             "e2e": {"value": v, "unit": "gates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
