@@ -11,6 +11,7 @@
 //   * diagonal gates never constrain the tile either: their non-tile bits select a sub-table.
 // The pass program travels in kernel-parameter (constant-bank) space, so there is no device
 // allocation or copy per pass.
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -176,17 +177,19 @@ static void plan_passes(const std::vector<Gate>& gates, uint32_t n_local, uint32
     const uint32_t h_max = std::min<uint32_t>(T - lc_min, 7);
     std::vector<char> done(gates.size(), 0);
     size_t first = 0, remaining = gates.size();
-    while (remaining) {
-        while (done[first]) ++first;
-        PlannedPass pass;
-        uint64_t high = 0;  // chosen high tile bits (positions >= lc_min)
-        uint32_t nh = 0;
-        // A gate WRITES its dense target bits and READS its control / diagonal bits.  Two gates commute unless
-        // one writes a bit the other touches (diagonal gates and controls commute among themselves).
-        uint64_t blocked_w = 0, blocked_r = 0;
+    // One pass = one scan of the remaining gates in program order.  A gate WRITES its dense target bits and READS its
+    // control / diagonal bits; two gates commute unless one writes a bit the other touches (diagonal gates and controls
+    // commute among themselves).  `preset` = high tile bits fixed in advance; the scan adds further high bits while slots
+    // are free.  With `picked` the scan commits (marks the gates done), otherwise it only counts.
+    struct PassScan { uint64_t high; uint32_t nh; int count; };
+    auto scan_pass = [&](size_t from, uint64_t preset, size_t window, std::vector<size_t>* picked) -> PassScan {
+        uint64_t high = preset, blocked_w = 0, blocked_r = 0;
+        uint32_t nh = (uint32_t)__builtin_popcountll(preset);
         int n_ops = 0, n_mats = 0;
-        for (size_t i = first; i < gates.size(); ++i) {
+        size_t seen = 0;
+        for (size_t i = from; i < gates.size() && seen < window; ++i) {
             if (done[i]) continue;
+            ++seen;
             const Gate& g = gates[i];
             const uint64_t wm = g.kind == GK_DENSE ? g.target_mask() : 0;
             const uint64_t rm = g.ctrl_mask | (g.kind == GK_DIAG ? g.target_mask() : 0);
@@ -205,10 +208,63 @@ static void plan_passes(const std::vector<Gate>& gates, uint32_t n_local, uint32
             nh += (uint32_t)__builtin_popcountll(need);
             n_ops++;
             n_mats += mats;
-            pass.gate_idx.push_back(i);
-            done[i] = 1;
-            --remaining;
+            if (picked) { picked->push_back(i); done[i] = 1; --remaining; }
         }
+        return PassScan{high, nh, n_ops};
+    };
+    // Look-ahead over the choice of high tile bits (big registers only: a sweep must cost more than planning it).  The
+    // plain scan takes high bits first come, first served; alternatives -- the most frequent dense targets of the next
+    // gates, and the greedy set with one bit exchanged -- are scored by the number of gates the pass would take.
+    const char* la_env = getenv("QB_PLAN_LOOKAHEAD");   // "0": never, "1": always (tests), unset: registers of >= 28 local qubits
+    const bool lookahead = h_max > 0 && (la_env ? la_env[0] == '1' : n_local >= 28);
+    const size_t kWindow = 1024;
+    while (remaining) {
+        while (done[first]) ++first;
+        PlannedPass pass;
+        uint64_t preset = 0;
+        if (lookahead) {
+            const PassScan g0 = scan_pass(first, 0, kWindow, nullptr);
+            int best = g0.count;
+            if (g0.count > 0) {
+                // dense-target frequency among the upcoming gates
+                uint32_t freq[64] = {0};
+                std::vector<uint64_t> cands;
+                size_t seen = 0;
+                const size_t marks[4] = {48, 96, 192, 384};
+                auto top_bits = [&](uint32_t k) {
+                    uint64_t m = 0;
+                    for (uint32_t c = 0; c < k; ++c) {
+                        int arg = -1;
+                        for (int bpos = (int)lc_min; bpos < 64; ++bpos)
+                            if (!((m >> bpos) & 1) && freq[bpos] && (arg < 0 || freq[bpos] > freq[arg])) arg = bpos;
+                        if (arg < 0) break;
+                        m |= 1ull << arg;
+                    }
+                    return m;
+                };
+                size_t mi = 0;
+                for (size_t i = first; i < gates.size() && mi < 4; ++i) {
+                    if (done[i]) continue;
+                    if (gates[i].kind == GK_DENSE)
+                        for (uint32_t t : gates[i].targets)
+                            if (t >= lc_min) freq[t]++;
+                    if (++seen == marks[mi]) { cands.push_back(top_bits(h_max)); ++mi; }
+                }
+                if (mi == 0) cands.push_back(top_bits(h_max));
+                const uint64_t pool = top_bits(12) & ~g0.high;   // exchange candidates
+                for (uint64_t out_b = g0.high; out_b; out_b &= out_b - 1)
+                    for (uint64_t in_b = pool; in_b; in_b &= in_b - 1)
+                        cands.push_back((g0.high & ~(out_b & -out_b)) | (in_b & -in_b));
+                for (uint64_t c : cands) {
+                    if (c == 0 || (uint32_t)__builtin_popcountll(c) > h_max) continue;
+                    const PassScan r = scan_pass(first, c, kWindow, nullptr);
+                    if (r.count > best) { best = r.count; preset = c; }
+                }
+            }
+        }
+        const PassScan fin = scan_pass(first, preset, (size_t)-1, &pass.gate_idx);
+        const uint64_t high = fin.high;
+        const uint32_t nh = fin.nh;
         if (pass.gate_idx.empty()) {  // the first remaining gate cannot go through the tile kernel
             pass.unfused = true;
             pass.gate_idx.push_back(first);
