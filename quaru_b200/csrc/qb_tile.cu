@@ -251,14 +251,20 @@ static void plan_passes(const std::vector<Gate>& gates, uint32_t n_local, uint32
                     if (++seen == marks[mi]) { cands.push_back(top_bits(h_max)); ++mi; }
                 }
                 if (mi == 0) cands.push_back(top_bits(h_max));
-                const uint64_t pool = top_bits(12) & ~g0.high;   // exchange candidates
-                for (uint64_t out_b = g0.high; out_b; out_b &= out_b - 1)
-                    for (uint64_t in_b = pool; in_b; in_b &= in_b - 1)
-                        cands.push_back((g0.high & ~(out_b & -out_b)) | (in_b & -in_b));
-                for (uint64_t c : cands) {
-                    if (c == 0 || (uint32_t)__builtin_popcountll(c) > h_max) continue;
-                    const PassScan r = scan_pass(first, c, kWindow, nullptr);
-                    if (r.count > best) { best = r.count; preset = c; }
+                uint64_t centre = g0.high;
+                for (int climb = 0; climb < 3; ++climb) {   // hill climbing over one-bit exchanges of the best set so far
+                    const uint64_t pool = top_bits(12) & ~centre;
+                    for (uint64_t out_b = centre; out_b; out_b &= out_b - 1)
+                        for (uint64_t in_b = pool; in_b; in_b &= in_b - 1)
+                            cands.push_back((centre & ~(out_b & -out_b)) | (in_b & -in_b));
+                    const int before = best;
+                    for (uint64_t c : cands) {
+                        if (c == 0 || (uint32_t)__builtin_popcountll(c) > h_max) continue;
+                        const PassScan r = scan_pass(first, c, kWindow, nullptr);
+                        if (r.count > best) { best = r.count; preset = c; centre = r.high; }
+                    }
+                    cands.clear();
+                    if (best == before) break;
                 }
             }
         }
