@@ -176,7 +176,7 @@ static void plan_passes(const std::vector<Gate>& gates, uint32_t n_local, uint32
     const uint32_t lc_min = std::min(MIN_LC, T);
     const uint32_t h_max = std::min<uint32_t>(T - lc_min, 7);
     std::vector<char> done(gates.size(), 0);
-    size_t first = 0, remaining = gates.size();
+    size_t remaining = gates.size();
     // One pass = one scan of the remaining gates in program order.  A gate WRITES its dense target bits and READS its
     // control / diagonal bits; two gates commute unless one writes a bit the other touches (diagonal gates and controls
     // commute among themselves).  `preset` = high tile bits fixed in advance; the scan adds further high bits while slots
@@ -218,12 +218,28 @@ static void plan_passes(const std::vector<Gate>& gates, uint32_t n_local, uint32
     const char* la_env = getenv("QB_PLAN_LOOKAHEAD");   // "0": never, "1": always (tests), unset: registers of >= 28 local qubits
     const bool lookahead = h_max > 0 && (la_env ? la_env[0] == '1' : n_local >= 28);
     const size_t kWindow = 1024;
+    // score of a candidate set of high bits: the gates its pass would take, plus -- for registers of >= 30 local qubits,
+    // where a sweep costs far more than planning -- the gates of the plain pass that would follow (two-step look-ahead:
+    // commit tentatively, scan again, roll back)
+    const bool two_step = n_local >= 30 || (la_env && la_env[0] == '1');
+    size_t first = 0;
+    auto score = [&](uint64_t preset) -> PassScan {
+        if (!two_step) return scan_pass(first, preset, kWindow, nullptr);
+        std::vector<size_t> tentative;
+        PassScan r = scan_pass(first, preset, kWindow, &tentative);
+        size_t next = first;
+        while (next < gates.size() && done[next]) ++next;
+        if (next < gates.size()) r.count += scan_pass(next, 0, kWindow, nullptr).count;
+        for (size_t ix : tentative) done[ix] = 0;
+        remaining += tentative.size();
+        return r;
+    };
     while (remaining) {
         while (done[first]) ++first;
         PlannedPass pass;
         uint64_t preset = 0;
         if (lookahead) {
-            const PassScan g0 = scan_pass(first, 0, kWindow, nullptr);
+            const PassScan g0 = score(0);
             int best = g0.count;
             if (g0.count > 0) {
                 // dense-target frequency among the upcoming gates
@@ -260,7 +276,7 @@ static void plan_passes(const std::vector<Gate>& gates, uint32_t n_local, uint32
                     const int before = best;
                     for (uint64_t c : cands) {
                         if (c == 0 || (uint32_t)__builtin_popcountll(c) > h_max) continue;
-                        const PassScan r = scan_pass(first, c, kWindow, nullptr);
+                        const PassScan r = score(c);
                         if (r.count > best) { best = r.count; preset = c; centre = r.high; }
                     }
                     cands.clear();
