@@ -477,7 +477,7 @@ int64_t rounds_debug(uint32_t n, std::vector<Gate>& gates, unsigned char* out, u
         }
         unsigned char* tp_at = w;
         for (uint32_t j = 0; j < 12; ++j) { const unsigned char b = j < p.tile_pos.size() ? (unsigned char)p.tile_pos[j] : 0; *w++ = b; }
-        const int64_t got = encode_rounds_debug(gates, p.gate_idx, p.tile_pos, p.lc, w, cap - (uint64_t)(w - out));
+        const int64_t got = encode_rounds_debug(n, gates, p.gate_idx, p.tile_pos, p.lc, w, cap - (uint64_t)(w - out));
         if (got < 0) return set_error(QB_ERR_INVALID_ARGUMENT, -1, "buffer too small");
         if (got == 0) { w = tp_at; continue; }   // falls back to the shared-memory kernel: report as a plain gate list
         kind = 0;

@@ -15,6 +15,7 @@
 //     bits outside the tile; diagonal gates whose bits are all thread/outer bits cost ONE complex multiply per
 //     thread: they accumulate into a per-thread phase that is applied once at the end of the round.
 // Special cases with fewer FP64 instructions: real matrices (H), X (register swap), phase -1 (sign flip).
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -51,10 +52,11 @@ static bool is_x(const Gate& g) {
            g.matrix[1].x == 1.0 && g.matrix[1].y == 0.0 && g.matrix[2].x == 1.0 && g.matrix[2].y == 0.0;
 }
 
-// `low_first`: one of the two round-selection strategies tried by encode_rounds (see the round loop).
+// `mode`: the round-selection strategy (0 plain scan, 1 low tile bits first in middle rounds, 2 roll-out search); encode_rounds
+// tries all three and keeps the shortest program.
 template <class Prog>
 static bool encode_rounds_with(const std::vector<Gate>& gates, const std::vector<size_t>& gate_idx, const std::vector<uint32_t>& tile_pos,
-                               uint32_t lc, Prog* prog, bool low_first) {
+                               uint32_t lc, Prog* prog, int mode) {
     const uint32_t T = (uint32_t)tile_pos.size();
     if (T != RT) return false;
     int8_t local_of[64];
@@ -439,43 +441,104 @@ static bool encode_rounds_with(const std::vector<Gate>& gates, const std::vector
         return true;
     };
 
-    bool first = true;
-    uint32_t last_R = 0;
-    while (remaining) {
-        uint32_t R = 0, blocked_w = 0, blocked_r = 0;
-        const uint32_t allowed = first ? io_allowed : 0xfffu;
-        // Strategy `low_first`: middle rounds reserve their register bits for the LOW tile bits (0..4) that are ready.
-        // Those can never be register bits of the HBM-facing first and last rounds, so serving them early tends to leave
-        // the high bits for a last round that can store straight to HBM (otherwise an empty extra round -- one more
-        // transpose -- has to be appended).  Dependencies decide which strategy needs fewer rounds; both are tried.
-        if (!first && low_first) {
-            uint32_t bw = 0, br = 0;
-            for (size_t i = 0; i < ops.size(); ++i) {
-                if (done[i]) continue;
-                const LocalOp& lo = ops[i];
-                bool ok = !(lo.dense & (bw | br)) && !(lo.reads & bw);
-                if (ok && (lo.dense & io_allowed)) ok = false;
-                if (ok && __builtin_popcount(R | lo.dense) > 4) ok = false;
-                if (!ok) { bw |= lo.dense; br |= lo.reads; continue; }
-                R |= lo.dense;   // reserved; the op itself is picked up by the scan below
-            }
-        }
-        std::vector<size_t> members;
+    // ---- choosing the rounds -------------------------------------------------------------------------------------
+    // One round = one scan of the remaining ops in program order with the same read / write commutation rule as the pass
+    // planner; `preset` reserves register bits in advance.  Returns the register bits used (before filling up to four).
+    auto pick_round = [&](std::vector<char>& dn, uint32_t preset, bool first_round, std::vector<size_t>* members) -> uint32_t {
+        uint32_t R = preset, blocked_w = 0, blocked_r = 0;
+        const uint32_t allowed = first_round ? io_allowed : 0xfffu;
         for (size_t i = 0; i < ops.size(); ++i) {
-            if (done[i]) continue;
+            if (dn[i]) continue;
             const LocalOp& lo = ops[i];
             bool ok = !(lo.dense & (blocked_w | blocked_r)) && !(lo.reads & blocked_w);
             if (ok && (lo.dense & ~allowed)) ok = false;
             if (ok && __builtin_popcount(R | lo.dense) > 4) ok = false;
             if (!ok) { blocked_w |= lo.dense; blocked_r |= lo.reads; continue; }
             R |= lo.dense;
-            members.push_back(i);
-            done[i] = 1;
-            --remaining;
+            dn[i] = 1;
+            if (members) members->push_back(i);
         }
-        // fill R up to 4 bits with free bits, highest first (keeps HBM-facing rounds within bits 5..11)
+        return R;
+    };
+    // fill R up to 4 bits with free bits, highest first (keeps HBM-facing rounds within bits 5..11)
+    auto fill_R = [&](uint32_t R, bool first_round) {
+        const uint32_t allowed = first_round ? io_allowed : 0xfffu;
         for (int b = RT - 1; b >= 0 && __builtin_popcount(R) < 4; --b)
             if (!((R >> b) & 1) && ((allowed >> b) & 1)) R |= 1u << b;
+        return R;
+    };
+    // low tile bits (0..4) that are ready: they can never be register bits of the HBM-facing first and last rounds, so
+    // serving them early tends to leave the high bits for a last round that can store straight to HBM
+    auto low_seed = [&](const std::vector<char>& dn) {
+        uint32_t R = 0, bw = 0, br = 0;
+        for (size_t i = 0; i < ops.size(); ++i) {
+            if (dn[i]) continue;
+            const LocalOp& lo = ops[i];
+            bool ok = !(lo.dense & (bw | br)) && !(lo.reads & bw);
+            if (ok && (lo.dense & io_allowed)) ok = false;
+            if (ok && __builtin_popcount(R | lo.dense) > 4) ok = false;
+            if (!ok) { bw |= lo.dense; br |= lo.reads; continue; }
+            R |= lo.dense;
+        }
+        return R;
+    };
+    // rounds the plain scan would still need from this state on, including the empty round that has to be appended when
+    // the last computing round holds low bits
+    auto rollout = [&](std::vector<char> dn, size_t rem, bool first_round, uint32_t last) {
+        int rounds = 0;
+        while (rem) {
+            std::vector<size_t> m;
+            const uint32_t R = pick_round(dn, 0, first_round, &m);
+            rem -= m.size();
+            last = fill_R(R, first_round);
+            first_round = false;
+            ++rounds;
+        }
+        if (last == 0 || (last & ~io_allowed)) ++rounds;
+        return rounds;
+    };
+
+    bool first = true;
+    uint32_t last_R = 0;
+    while (remaining) {
+        uint32_t preset = 0;
+        if (mode == 1 && !first) preset = low_seed(done);
+        if (mode == 2) {
+            // roll-out policy: every candidate choice of register bits is completed with the plain scan; the choice with
+            // the fewest rounds overall wins (ties: the one that takes more ops now)
+            const uint32_t allowed = first ? io_allowed : 0xfffu;
+            uint32_t pending = 0;
+            for (size_t i = 0; i < ops.size(); ++i)
+                if (!done[i]) pending |= ops[i].dense;
+            std::vector<uint32_t> cands{0u};
+            if (!first) cands.push_back(low_seed(done));
+            {
+                std::vector<char> dn = done;
+                const uint32_t g0 = pick_round(dn, 0, first, nullptr);
+                for (uint32_t out_b = g0; out_b; out_b &= out_b - 1)
+                    for (uint32_t in_b = pending & allowed & ~g0; in_b; in_b &= in_b - 1)
+                        cands.push_back((g0 & ~(out_b & -out_b)) | (in_b & -in_b));
+            }
+            int best_rounds = 1 << 30;
+            size_t best_members = 0;
+            for (uint32_t c : cands) {
+                if (__builtin_popcount(c) > 4 || (c & ~allowed)) continue;
+                std::vector<char> dn = done;
+                std::vector<size_t> m;
+                const uint32_t R = fill_R(pick_round(dn, c, first, &m), first);
+                if (m.empty()) continue;
+                const int total = 1 + rollout(dn, remaining - m.size(), false, R);
+                if (total < best_rounds || (total == best_rounds && m.size() > best_members)) {
+                    best_rounds = total;
+                    best_members = m.size();
+                    preset = c;
+                }
+            }
+        }
+        std::vector<size_t> members;
+        uint32_t R = pick_round(done, preset, first, &members);
+        remaining -= members.size();
+        R = fill_R(R, first);
         if (!emit_round(R, members)) return false;
         last_R = R;
         first = false;
@@ -500,17 +563,27 @@ static bool encode_rounds_with(const std::vector<Gate>& gates, const std::vector
     return true;
 }
 
-// Encodes the pass with both round-selection strategies and keeps the program with fewer rounds (then fewer ops).
+// Encodes the pass with every round-selection strategy and keeps the program with the fewest rounds (then the fewest ops).
+// Only for big registers (`thorough`): below ~2^26 amplitudes a sweep is cheaper than the extra encoding time.
+static bool thorough_encoding(uint32_t n_local) {
+    const char* env = getenv("QB_PLAN_LOOKAHEAD");   // same switch as the pass planner's look-ahead: "0" never, "1" always (tests)
+    return env ? env[0] == '1' : n_local >= 26;
+}
+
 template <class Prog>
 static bool encode_rounds(const std::vector<Gate>& gates, const std::vector<size_t>& gate_idx, const std::vector<uint32_t>& tile_pos,
-                          uint32_t lc, Prog* prog) {
+                          uint32_t lc, Prog* prog, bool thorough) {
     static thread_local Prog other;
-    const bool ok_a = encode_rounds_with(gates, gate_idx, tile_pos, lc, prog, false);
-    const bool ok_b = encode_rounds_with(gates, gate_idx, tile_pos, lc, &other, true);
-    if (!ok_b) return ok_a;
     auto n_ops = [](const Prog& p) { return p.rounds[p.n_rounds - 1].op_end; };
-    if (!ok_a || other.n_rounds < prog->n_rounds || (other.n_rounds == prog->n_rounds && n_ops(other) < n_ops(*prog))) *prog = other;
-    return true;
+    bool have = encode_rounds_with(gates, gate_idx, tile_pos, lc, prog, 0);
+    for (int mode = 1; thorough && mode <= 2; ++mode) {
+        if (!encode_rounds_with(gates, gate_idx, tile_pos, lc, &other, mode)) continue;
+        if (!have || other.n_rounds < prog->n_rounds || (other.n_rounds == prog->n_rounds && n_ops(other) < n_ops(*prog))) {
+            *prog = other;
+            have = true;
+        }
+    }
+    return have;
 }
 
 template <class Prog>
@@ -567,12 +640,12 @@ static int launch_rpass_persist(Reg* r, const Prog& prog) {
 // Planner introspection (no GPU): serialises the round program of one pass.  Layout (little endian):
 //   u32 lc, h, n_rounds, n_ops, n_mats; u8 hp[8]; RoundDesc[n_rounds]; ROp[n_ops]; c64[n_mats]; u64 gro_first[16], gro_last[16]
 // Returns the number of bytes written, 0 if the pass cannot go through the register-blocked kernel, -1 if `cap` is too small.
-int64_t encode_rounds_debug(const std::vector<Gate>& gates, const std::vector<size_t>& gate_idx, const std::vector<uint32_t>& tile_pos,
-                            uint32_t lc, unsigned char* out, uint64_t cap) {
+int64_t encode_rounds_debug(uint32_t n_local, const std::vector<Gate>& gates, const std::vector<size_t>& gate_idx,
+                            const std::vector<uint32_t>& tile_pos, uint32_t lc, unsigned char* out, uint64_t cap) {
     if (tile_pos.size() != RT) return 0;
     static thread_local RProgLarge prog;
     memset(&prog, 0, sizeof(prog));
-    if (!encode_rounds(gates, gate_idx, tile_pos, lc, &prog)) return 0;
+    if (!encode_rounds(gates, gate_idx, tile_pos, lc, &prog, thorough_encoding(n_local))) return 0;
     const uint32_t n_rounds = prog.n_rounds, n_ops = prog.rounds[n_rounds - 1].op_end;
     uint32_t n_mats = 4;
     for (uint32_t i = 0; i < n_ops; ++i) {   // the encoder does not keep the table count: recover an upper bound per op
@@ -622,13 +695,13 @@ int run_pass_v2(Reg* r, const std::vector<Gate>& gates, const std::vector<size_t
     for (size_t gi : gate_idx) mats += gates[gi].matrix.size();
     if (gate_idx.size() <= 20 && mats <= 150) {
         RProgSmall small;
-        if (encode_rounds(gates, gate_idx, tile_pos, lc, &small)) {
+        if (encode_rounds(gates, gate_idx, tile_pos, lc, &small, thorough_encoding(r->n_local))) {
             *handled = true;
             return launch_variant(r, small);
         }
     }
     static thread_local RProgLarge large;
-    if (!encode_rounds(gates, gate_idx, tile_pos, lc, &large)) return QB_OK;
+    if (!encode_rounds(gates, gate_idx, tile_pos, lc, &large, thorough_encoding(r->n_local))) return QB_OK;
     *handled = true;
     return launch_variant(r, large);
 }

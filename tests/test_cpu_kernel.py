@@ -112,3 +112,15 @@ def test_persistent_variants_on_the_host_compiled_kernel(host_kernel, n, grid, k
     short = [og.hadamard(3), og.cnot(3, 9), og.rz(0.7, 9), og.hadamard(12)]
     dev_s, _, want_s, _ = _run(host_kernel, 13, short, 3, small=True, persist_grid=2, variant=variant)
     assert_close(dev_s, want_s)
+
+
+@pytest.mark.parametrize("kind,n", [("layers", 14), ("mixed", 13), ("qft", 14)])
+def test_programs_of_the_thorough_encoder_on_the_host_compiled_kernel(host_kernel, kind, n, monkeypatch):
+    """The round programs big registers get (look-ahead planner, roll-out round selection; forced on here with
+    QB_PLAN_LOOKAHEAD=1) through the kernel's own source."""
+    monkeypatch.setenv("QB_PLAN_LOOKAHEAD", "1")
+    ops = {"layers": circuits.random_circuit(n, 6, seed=3 * n), "qft": circuits.qft_circuit(n), "mixed": circuits.mixed_circuit(n, 120, 2 * n)}[kind]
+    dev, emu, want, n_prog = _run(host_kernel, n, ops, 90 + n)
+    assert n_prog >= 1
+    assert_close(dev, want, f"thorough encoder, kernel vs oracle, {kind} n={n}")
+    assert_close(dev, emu, "kernel vs program emulator")

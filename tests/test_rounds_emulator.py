@@ -127,3 +127,22 @@ def test_short_phase_groups_stay_in_place_for_layer_packing():
     assert codes.count(em.RC_LAYER) == 1 and not any(em.RC_H <= c < em.RC_H + 4 for c in codes)
     got, want, seen, st = _replay(n, ops, 6)
     assert_close(got, want)
+
+
+@pytest.mark.parametrize("kind,n,seed", [("layers", 14, 11), ("mixed", 15, 12), ("qft", 16, 13), ("mixed", 13, 14), ("layers", 16, 15)])
+def test_thorough_planning_and_encoding_forced_on_small_registers(kind, n, seed, monkeypatch):
+    """Big registers (>= 26 / 28 local qubits) plan passes with a look-ahead over the tile bits and choose rounds by trying
+    three strategies (plain scan, low bits first, roll-out search).  QB_PLAN_LOOKAHEAD=1 forces all of that on at sizes
+    the emulator can replay; the programs must still reproduce the oracle and never need more rounds than the plain scan."""
+    ops = {"layers": circuits.random_circuit(n, 8, seed=seed), "qft": circuits.qft_circuit(n),
+           "mixed": circuits.mixed_circuit(n, 150, seed)}[kind]
+    monkeypatch.setenv("QB_PLAN_LOOKAHEAD", "0")
+    _, _, _, plain = _replay(n, ops, 400 + seed)
+    monkeypatch.setenv("QB_PLAN_LOOKAHEAD", "1")
+    got, want, seen, st = _replay(n, ops, 400 + seed)
+    identities = [i for i, (m, t) in enumerate(ops) if np.array_equal(np.asarray(m), np.eye(len(m)))]
+    assert sorted(seen + identities) == list(range(len(ops)))
+    assert_close(got, want, f"thorough {kind} n={n}")
+    assert st["prog"] + st["gates"] <= plain["prog"] + plain["gates"] + 1
+    if st["prog"] + st["gates"] == plain["prog"] + plain["gates"]:
+        assert st["rounds"] <= plain["rounds"], (st["rounds"], plain["rounds"])
