@@ -96,6 +96,12 @@ static bool encode_rounds_with(const std::vector<Gate>& gates, const std::vector
     prog->mats[0] = prog->mats[3] = make_double2(1.0, 0.0);
     prog->mats[1] = prog->mats[2] = make_double2(0.0, 0.0);
     const uint32_t io_allowed = 0xfe0;  // tile bits 5..11: register bits of the HBM-facing rounds
+    // Unconditional constant factors (the deferred 1/sqrt(2) of every Hadamard, the common factor d0 of a one-qubit diagonal
+    // diag(d0, d1) on a register bit, global phases) commute with everything: they are multiplied together on the host
+    // over the whole pass and applied once, in its last round, instead of costing a table op and 16 complex multiplies
+    // in every round.
+    c64 pass_scalar = make_double2(1.0, 0.0);
+    auto scale_pass = [&](c64 f) { pass_scalar = make_double2(pass_scalar.x * f.x - pass_scalar.y * f.y, pass_scalar.x * f.y + pass_scalar.y * f.x); };
     auto emit_round = [&](uint32_t R, const std::vector<size_t>& members) -> bool {
         if (n_rounds >= max_rounds) return false;
         RoundDesc& rd = prog->rounds[n_rounds];
@@ -338,13 +344,13 @@ static bool encode_rounds_with(const std::vector<Gate>& gates, const std::vector
                     (writes_tph ? tail : merged).push_back(o);
                     continue;
                 }
+                if (o.code != RC_PH_ACC && f.sel.empty()) { scale_pass(f.tab[0]); continue; }   // a constant: deferred to the end of the pass
                 merge_into(o.code == RC_PH_ACC ? &acc_tabs : &tph_tabs, f);
             }
-            if (any_h) {   // the deferred 1/sqrt(2) factors of the round's Hadamards: one constant
-                PhaseFn c;
-                c.tab.assign(1, make_double2(h_scalar, 0.0));
-                merge_into(&tph_tabs, c);
-            }
+            if (any_h) scale_pass(make_double2(h_scalar, 0.0));   // the deferred 1/sqrt(2) factors of the round's Hadamards
+            // the per-thread phase is applied at the end of the round only if something is left in it then: chains flush
+            // and reset it, and every other writer has been moved behind the last flush (`tail`, the merged tables)
+            rd.has_tph = (!tph_tabs.empty() || !tail.empty()) ? 1 : 0;
             for (const ROp& o : tail) merged.push_back(o);
             emit_tabs(&tph_tabs, RC_TAB, &merged);
             // Third pass: bundle real one-qubit gates (H, X, real rotations; no register-bit or outer control) on DISTINCT
@@ -545,6 +551,18 @@ static bool encode_rounds_with(const std::vector<Gate>& gates, const std::vector
     }
     if (n_rounds == 0 || (last_R & ~io_allowed)) {  // the storing round must have its register bits within 5..11
         if (!emit_round(0xf00, {})) return false;
+    }
+    if (pass_scalar.x != 1.0 || pass_scalar.y != 0.0) {   // the pass's constant factor: one table op without selectors, last round
+        if (n_ops >= max_ops || n_mats + 1 > max_mats) return false;
+        RoundDesc& last = prog->rounds[n_rounds - 1];
+        ROp o;
+        memset(&o, 0, sizeof(o));
+        o.code = RC_TAB;
+        o.mat = (uint32_t)n_mats;
+        prog->mats[n_mats++] = pass_scalar;
+        prog->ops[n_ops++] = o;
+        last.op_end = (uint16_t)n_ops;
+        last.has_tph = 1;
     }
     prog->n_rounds = (uint32_t)n_rounds;
     prog->n_mats = (uint32_t)n_mats;
