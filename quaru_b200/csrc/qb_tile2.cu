@@ -223,16 +223,32 @@ static bool encode_rounds_with(const std::vector<Gate>& gates, const std::vector
             // single per-thread `tph`, hence one group at a time: ACC ... ACC FLUSH.
             // Groups of fewer than three phases do not pay for a flush: they stay where they are (deferring them would
             // also separate dense gates that the layer packing below wants adjacent).
+            // The UNCONDITIONAL phases of a group (no thread / outer control: the relative phase of an RZ, a Z) are first
+            // multiplied together on the host into the group's first such op; the others are dropped.
             std::vector<int> group_of(in.size(), -1);
             std::vector<size_t> group_size;
+            std::vector<int> group_rep;   // per group: index of the op that carries the product of the unconditional phases
             {
                 int open_group[4] = {-1, -1, -1, -1};
                 for (size_t i = 0; i < in.size(); ++i) {
                     const int b = single_bit(in[i]);
                     if (b >= 0) {
-                        if (open_group[b] < 0) { open_group[b] = (int)group_size.size(); group_size.push_back(0); }
-                        group_of[i] = open_group[b];
-                        group_size[open_group[b]]++;
+                        if (open_group[b] < 0) { open_group[b] = (int)group_size.size(); group_size.push_back(0); group_rep.push_back(-1); }
+                        const int gid = open_group[b];
+                        if (in[i].tmask == 0 && in[i].omask == 0) {
+                            if (group_rep[gid] < 0) {
+                                group_rep[gid] = (int)i;
+                            } else {   // fold into the representative and drop
+                                c64& acc = prog->mats[in[group_rep[gid]].mat];
+                                const c64 f = prog->mats[in[i].mat];
+                                acc = make_double2(acc.x * f.x - acc.y * f.y, acc.x * f.y + acc.y * f.x);
+                                in[group_rep[gid]].code = RC_PH_R;   // the product is a general phase (maybe -1 again: fixed below)
+                                group_of[i] = -2;                    // dropped
+                                continue;
+                            }
+                        }
+                        group_of[i] = gid;
+                        group_size[gid]++;
                         continue;
                     }
                     for (int wb = 0; wb < 4; ++wb)
@@ -257,6 +273,12 @@ static bool encode_rounds_with(const std::vector<Gate>& gates, const std::vector
             for (size_t i = 0; i < in.size(); ++i) {
                 const int b = single_bit(in[i]);
                 if (b >= 0) {
+                    if (group_of[i] == -2) continue;   // folded into its group's representative
+                    if (in[i].tmask == 0 && in[i].omask == 0) {   // a representative: normalise the product
+                        const c64 f = prog->mats[in[i].mat];
+                        if (f.x == 1.0 && f.y == 0.0 && group_size[group_of[i]] < 3) continue;   // the phases cancelled
+                        if (f.y == 0.0 && f.x == -1.0) in[i].code = RC_PH_NEG;
+                    }
                     if (group_size[group_of[i]] >= 3) pending[b].push_back(in[i]); else out.push_back(in[i]);
                     continue;
                 }

@@ -146,3 +146,23 @@ def test_thorough_planning_and_encoding_forced_on_small_registers(kind, n, seed,
     assert st["prog"] + st["gates"] <= plain["prog"] + plain["gates"] + 1
     if st["prog"] + st["gates"] == plain["prog"] + plain["gates"]:
         assert st["rounds"] <= plain["rounds"], (st["rounds"], plain["rounds"])
+
+
+def test_unconditional_phases_on_one_bit_are_multiplied_on_the_host():
+    """Five RZ / Z / S gates on the same qubit between two Hadamards commute and have no controls: the encoder multiplies
+    them into one relative phase (one op), instead of an accumulated chain; Z Z cancels completely."""
+    n = 13
+    q = 9
+    ops = [og.hadamard(q), og.rz(0.3, q), og.pauli_z(q), og.rz(-1.1, q), og.phase(q), og.pauli_z(q), og.hadamard(q)]
+    passes = em.dump_programs(n, ops)
+    codes = [o["code"] for p in passes if p[0] == "prog" for o in p[3]["ops"]]
+    assert codes.count(em.RC_PH_R) + codes.count(em.RC_PH_NEG) == 1
+    assert not any(em.RC_PH_FLUSH <= c < em.RC_PH_FLUSH + 4 for c in codes)
+    got, want, seen, st = _replay(n, ops, 31)
+    assert_close(got, want)
+    ops = [og.hadamard(q), og.pauli_z(q), og.pauli_z(q), og.hadamard(q), og.hadamard(3)]
+    passes = em.dump_programs(n, ops)
+    codes = [o["code"] for p in passes if p[0] == "prog" for o in p[3]["ops"]]
+    assert em.RC_PH_R not in codes and em.RC_PH_NEG not in codes
+    got, want, seen, st = _replay(n, ops, 32)
+    assert_close(got, want)
