@@ -56,7 +56,7 @@ static bool is_x(const Gate& g) {
 // tries all three and keeps the shortest program.
 template <class Prog>
 static bool encode_rounds_with(const std::vector<Gate>& gates, const std::vector<size_t>& gate_idx, const std::vector<uint32_t>& tile_pos,
-                               uint32_t lc, Prog* prog, int mode) {
+                               uint32_t lc, Prog* prog, int mode, bool allow_rtab) {
     const uint32_t T = (uint32_t)tile_pos.size();
     if (T != RT) return false;
     int8_t local_of[64];
@@ -287,6 +287,65 @@ static bool encode_rounds_with(const std::vector<Gate>& gates, const std::vector
                 out.push_back(in[i]);
             }
             for (int b = 0; b < 4; ++b) emit_group(b);
+            // Experimental (kernels with RC_RTAB only): the unconditional phases on register bits that are left (relative
+            // phases of RZ gates, CZ between register bits, the same under one outer control) are merged into register-indexed
+            // tables.  A later phase may join an earlier one if nothing in between writes one of its bits; merging pays when
+            // the ops saved outweigh the 16 complex multiplies of the table (~40 FP64 instructions of overhead per op).
+            if (allow_rtab) {
+                struct Group { uint64_t omask; uint32_t written; std::vector<size_t> members; };
+                std::vector<Group> groups;
+                auto dense_writes = [](const ROp& o) -> uint32_t {
+                    const int c = o.code;
+                    if (c == RC_D2) return (1u << o.a) | (1u << o.b);
+                    if (c >= RC_H && c < RC_H + 4) return 1u << (c - RC_H);
+                    const bool diag1 = (c >= RC_DG1R && c < RC_DG1R + 4) || (c >= RC_DG1R_P && c < RC_DG1R_P + 4);
+                    if (c < RC_D2 && !diag1) return 1u << (c & 3);
+                    return 0;
+                };
+                for (size_t i = 0; i < out.size(); ++i) {
+                    const ROp& o = out[i];
+                    if ((o.code == RC_PH_R || o.code == RC_PH_NEG) && o.tmask == 0 && o.rmask != 0) {
+                        bool placed = false;
+                        for (Group& g : groups)
+                            if (g.omask == o.omask && !(g.written & o.rmask)) { g.members.push_back(i); placed = true; break; }
+                        if (!placed) groups.push_back(Group{o.omask, 0u, {i}});
+                        continue;
+                    }
+                    const uint32_t w = dense_writes(o);
+                    for (Group& g : groups) g.written |= w;
+                }
+                std::vector<char> drop(out.size(), 0);
+                for (const Group& g : groups) {
+                    if (g.members.size() < 2 || n_mats + 16 > max_mats) continue;
+                    int fp = 0;
+                    for (size_t i : g.members) {
+                        const int regs = 16 >> __builtin_popcount(out[i].rmask);
+                        fp += (out[i].code == RC_PH_R ? 4 : 2) * regs;
+                    }
+                    if ((int)(g.members.size() - 1) * 40 <= 64 - fp) continue;
+                    c64 T[16];
+                    for (int j = 0; j < 16; ++j) T[j] = make_double2(1.0, 0.0);
+                    for (size_t i : g.members) {
+                        const c64 f = prog->mats[out[i].mat];
+                        for (uint32_t j = 0; j < 16; ++j)
+                            if ((j & out[i].rmask) == out[i].rmask) T[j] = make_double2(T[j].x * f.x - T[j].y * f.y, T[j].x * f.y + T[j].y * f.x);
+                    }
+                    ROp t;
+                    memset(&t, 0, sizeof(t));
+                    t.code = RC_RTAB;
+                    t.omask = g.omask;
+                    for (size_t i : g.members) t.a |= (uint8_t)out[i].rmask;   // register bits the table depends on (host bookkeeping only)
+                    t.mat = (uint32_t)n_mats;
+                    memcpy(prog->mats + n_mats, T, sizeof(T));
+                    n_mats += 16;
+                    out[g.members[0]] = t;
+                    for (size_t m = 1; m < g.members.size(); ++m) drop[g.members[m]] = 1;
+                }
+                std::vector<ROp> kept;
+                for (size_t i = 0; i < out.size(); ++i)
+                    if (!drop[i]) kept.push_back(out[i]);
+                out.swap(kept);
+            }
             // Second pass: every thread-uniform phase (RC_PH_T, RC_DG1T, RC_PH_ACC) is a function of a few thread / outer
             // bits.  They all commute, so they are multiplied together on the host into tables over <= 4 selector bits:
             // one table op replaces several ops (each op costs ~25 instructions of decode for 4 FP64 instructions of work).
@@ -384,6 +443,7 @@ static bool encode_rounds_with(const std::vector<Gate>& gates, const std::vector
                     if (c < RC_D2) return (1u << (c & 3)) | o.rmask;                  // D1C / D1R / DG1R and predicated forms
                     if (c == RC_D2) return (1u << o.a) | (1u << o.b) | o.rmask;
                     if (c == RC_PH_NEG || c == RC_PH_R) return o.rmask;
+                    if (c == RC_RTAB) return o.a;
                     if (c >= RC_PH_FLUSH && c < RC_PH_FLUSH + 4) return 1u << (c - RC_PH_FLUSH);
                     if (c >= RC_H && c < RC_H + 4) return 1u << (c - RC_H);
                     if (c == RC_DG) {
@@ -612,12 +672,12 @@ static bool thorough_encoding(uint32_t n_local) {
 
 template <class Prog>
 static bool encode_rounds(const std::vector<Gate>& gates, const std::vector<size_t>& gate_idx, const std::vector<uint32_t>& tile_pos,
-                          uint32_t lc, Prog* prog, bool thorough) {
+                          uint32_t lc, Prog* prog, bool thorough, bool allow_rtab) {
     static thread_local Prog other;
     auto n_ops = [](const Prog& p) { return p.rounds[p.n_rounds - 1].op_end; };
-    bool have = encode_rounds_with(gates, gate_idx, tile_pos, lc, prog, 0);
+    bool have = encode_rounds_with(gates, gate_idx, tile_pos, lc, prog, 0, allow_rtab);
     for (int mode = 1; thorough && mode <= 2; ++mode) {
-        if (!encode_rounds_with(gates, gate_idx, tile_pos, lc, &other, mode)) continue;
+        if (!encode_rounds_with(gates, gate_idx, tile_pos, lc, &other, mode, allow_rtab)) continue;
         if (!have || other.n_rounds < prog->n_rounds || (other.n_rounds == prog->n_rounds && n_ops(other) < n_ops(*prog))) {
             *prog = other;
             have = true;
@@ -685,7 +745,7 @@ int64_t encode_rounds_debug(uint32_t n_local, const std::vector<Gate>& gates, co
     if (tile_pos.size() != RT) return 0;
     static thread_local RProgLarge prog;
     memset(&prog, 0, sizeof(prog));
-    if (!encode_rounds(gates, gate_idx, tile_pos, lc, &prog, thorough_encoding(n_local))) return 0;
+    if (!encode_rounds(gates, gate_idx, tile_pos, lc, &prog, thorough_encoding(n_local), getenv("QB_TILE_RTAB") != nullptr)) return 0;
     const uint32_t n_rounds = prog.n_rounds, n_ops = prog.rounds[n_rounds - 1].op_end;
     uint32_t n_mats = 4;
     for (uint32_t i = 0; i < n_ops; ++i) {   // the encoder does not keep the table count: recover an upper bound per op
@@ -695,6 +755,7 @@ int64_t encode_rounds_debug(uint32_t n_local, const std::vector<Gate>& gates, co
         else if (o.code == RC_DG) len = 1u << o.k;
         else if (o.code == RC_TAB || o.code == RC_TAB_ACC) len = 1u << o.k;
         else if (o.code == RC_LAYER) len = 8;
+        else if (o.code == RC_RTAB) len = 16;
         n_mats = std::max(n_mats, o.mat + len);
     }
     n_mats = std::min<uint32_t>(n_mats, sizeof(prog.mats) / sizeof(c64));
@@ -735,13 +796,15 @@ int run_pass_v2(Reg* r, const std::vector<Gate>& gates, const std::vector<size_t
     for (size_t gi : gate_idx) mats += gates[gi].matrix.size();
     if (gate_idx.size() <= 20 && mats <= 150) {
         RProgSmall small;
-        if (encode_rounds(gates, gate_idx, tile_pos, lc, &small, thorough_encoding(r->n_local))) {
+        const bool rtab = r->force_path >= 5 && getenv("QB_TILE_RTAB") != nullptr;   // only the persistent kernels implement RC_RTAB
+        if (encode_rounds(gates, gate_idx, tile_pos, lc, &small, thorough_encoding(r->n_local), rtab)) {
             *handled = true;
             return launch_variant(r, small);
         }
     }
     static thread_local RProgLarge large;
-    if (!encode_rounds(gates, gate_idx, tile_pos, lc, &large, thorough_encoding(r->n_local))) return QB_OK;
+    if (!encode_rounds(gates, gate_idx, tile_pos, lc, &large, thorough_encoding(r->n_local), r->force_path >= 5 && getenv("QB_TILE_RTAB") != nullptr))
+        return QB_OK;
     *handled = true;
     return launch_variant(r, large);
 }

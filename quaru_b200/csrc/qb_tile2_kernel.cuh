@@ -18,7 +18,9 @@ enum RCode : uint8_t {
     RC_PH_ACC = 44,                                // phase whose only register-bit control is one bit: accumulate per thread ...
     RC_PH_FLUSH = 48,                              // + register bit: ... and apply the product to the 8 registers with that bit set
     RC_TAB = 52, RC_TAB_ACC = 53,                  // merged thread-uniform phases: table over <= 4 thread / outer bits -> tph
-    RC_LAYER = 54                                  // up to four real 2x2 gates, one per register bit, decoded once
+    RC_LAYER = 54,                                 // up to four real 2x2 gates, one per register bit, decoded once
+    RC_RTAB = 55                                   // experimental (persistent kernels only): unconditional diagonal over the register
+                                                   // bits, register j is multiplied by the j-th of 16 coefficients
 };
 
 struct ROp {
@@ -288,12 +290,14 @@ __global__ void __launch_bounds__(RTHREADS, 2) k2r_tile_pass(c64* __restrict__ s
 #define QB_BEFORE_OPS
 #define QB_FETCH_OP const ROp& op = prog.ops[oi];
 #define QB_AFTER_FIRST_LOADS
+#define QB_EXTRA_CASES
 #include "qb_tile2_body.inc"
 #undef QB_TILE_IX
 #undef QB_MATS
 #undef QB_BEFORE_OPS
 #undef QB_FETCH_OP
 #undef QB_AFTER_FIRST_LOADS
+#undef QB_EXTRA_CASES
 }
 
 // Experimental persistent variants (QB_OPT_FORCE_PATH = 5..8, not yet measured on hardware): grid = resident CTAs; each CTA
@@ -339,6 +343,11 @@ __global__ void __launch_bounds__(RTHREADS, 2) k2r_tile_pass_persist(c64* __rest
             _Pragma("unroll") for (int j = 0; j < 16; ++j) prefetch_l2(st + (ngt + prog.gro_first[j])); \
         }                                                                                            \
     }
+#define QB_EXTRA_CASES                                                                    \
+    case RC_RTAB: {                                                                       \
+        const c64* T = QB_MATS + op.mat;                                                  \
+        _Pragma("unroll") for (int j = 0; j < 16; ++j) ip_cmul(v[j], T[j]);               \
+    } break;
 #include "qb_tile2_body.inc"
 #undef QB_TILE_IX
 #undef QB_MATS
@@ -346,6 +355,7 @@ __global__ void __launch_bounds__(RTHREADS, 2) k2r_tile_pass_persist(c64* __rest
 #undef QB_BEFORE_OPS
 #undef QB_FETCH_OP
 #undef QB_AFTER_FIRST_LOADS
+#undef QB_EXTRA_CASES
     }
 }
 

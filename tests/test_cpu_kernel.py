@@ -124,3 +124,18 @@ def test_programs_of_the_thorough_encoder_on_the_host_compiled_kernel(host_kerne
     assert n_prog >= 1
     assert_close(dev, want, f"thorough encoder, kernel vs oracle, {kind} n={n}")
     assert_close(dev, emu, "kernel vs program emulator")
+
+
+@pytest.mark.parametrize("kind,n,variant", [("layers", 14, 5), ("mixed", 13, 6), ("qft", 14, 9), ("layers", 13, 10)])
+def test_register_table_op_on_the_persistent_kernels(host_kernel, kind, n, variant, monkeypatch):
+    """Experimental RC_RTAB (QB_TILE_RTAB=1, persistent kernels only): unconditional phases on register bits merged into a
+    16-entry table indexed by the register number.  Programs through the emulator and through the kernel source."""
+    monkeypatch.setenv("QB_TILE_RTAB", "1")
+    ops = {"layers": circuits.random_circuit(n, 8, seed=n), "qft": circuits.qft_circuit(n), "mixed": circuits.mixed_circuit(n, 150, n)}[kind]
+    codes = [o["code"] for p in em.dump_programs(n, ops) if p[0] == "prog" for o in p[3]["ops"]]
+    if kind == "layers":
+        assert em.RC_RTAB in codes, "random layers have mergeable phases"
+    dev, emu, want, n_prog = _run(host_kernel, n, ops, 95 + n, persist_grid=2, variant=variant)
+    assert n_prog >= 1
+    assert_close(dev, want, f"RTAB, kernel {variant} vs oracle, {kind} n={n}")
+    assert_close(dev, emu, "kernel vs program emulator")

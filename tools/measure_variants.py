@@ -1,7 +1,8 @@
 """One GPU call that compares the tile-kernel variants: for each QB_OPT_FORCE_PATH value it first checks the result against
 the default kernel bit for bit on a small register (same arithmetic in every variant), then times the fused random-layer
 circuit and the QFT.  Usage: python tools/measure_variants.py [n=30] [depth=20] [variants=0,5,6,7,8,9,10]
-Writes gpurun_out/variants.json when the directory exists."""
+Run it a second time with QB_TILE_RTAB=1 in the environment to add the register-table op to the persistent kernels.
+Writes gpurun_out/variants.json (variants_rtab.json with QB_TILE_RTAB) when the directory exists."""
 import json
 import os
 import sys
@@ -52,4 +53,5 @@ for v in variants:
     rows.append(row)
     print(json.dumps(row), flush=True)
 if os.path.isdir("gpurun_out"):
-    json.dump({"n": n, "depth": depth, "rows": rows}, open("gpurun_out/variants.json", "w"), indent=1)
+    name = "variants_rtab.json" if os.environ.get("QB_TILE_RTAB") else "variants.json"
+    json.dump({"n": n, "depth": depth, "rtab": bool(os.environ.get("QB_TILE_RTAB")), "rows": rows}, open(os.path.join("gpurun_out", name), "w"), indent=1)
