@@ -149,4 +149,5 @@ def test_persistent_tile_kernels(engine, n, kind, variant):
     reg, ora = _run(engine, n, ops, 3000 + n, force=variant)
     assert_close(reg.state, ora.state, f"persistent kernel {variant} n={n} {kind}")
     ref, _ = _run(engine, n, ops, 3000 + n)
-    assert reg.max_abs_diff(ref) == 0.0, "same arithmetic as the default kernel: bit-identical"
+    if not os.environ.get("QB_TILE_RTAB"):        # the register-table op multiplies phases on the host: equal within tolerance only
+        assert reg.max_abs_diff(ref) == 0.0, "same arithmetic as the default kernel: bit-identical"
