@@ -549,10 +549,12 @@ static bool encode_rounds_with(const std::vector<Gate>& gates, const std::vector
         return R;
     };
     // fill R up to 4 bits with free bits, highest first (keeps HBM-facing rounds within bits 5..11)
-    auto fill_R = [&](uint32_t R, bool first_round) {
+    // (`avoid`: bits read by the round's diagonal ops -- as thread bits their phases merge into the per-thread tables)
+    auto fill_R = [&](uint32_t R, bool first_round, uint32_t avoid = 0) {
         const uint32_t allowed = first_round ? io_allowed : 0xfffu;
-        for (int b = RT - 1; b >= 0 && __builtin_popcount(R) < 4; --b)
-            if (!((R >> b) & 1) && ((allowed >> b) & 1)) R |= 1u << b;
+        for (int pref = 0; pref < 2; ++pref)
+            for (int b = RT - 1; b >= 0 && __builtin_popcount(R) < 4; --b)
+                if (!((R >> b) & 1) && ((allowed >> b) & 1) && (pref == 1 || !((avoid >> b) & 1))) R |= 1u << b;
         return R;
     };
     // low tile bits (0..4) that are ready: they can never be register bits of the HBM-facing first and last rounds, so
@@ -626,7 +628,33 @@ static bool encode_rounds_with(const std::vector<Gate>& gates, const std::vector
         std::vector<size_t> members;
         uint32_t R = pick_round(done, preset, first, &members);
         remaining -= members.size();
-        R = fill_R(R, first);
+        // A diagonal op costs 8-32 FP64 instructions plus an op slot per thread when one of its bits is a register bit of the
+        // round, and next to nothing (a factor in a merged per-thread table) when they are all thread / outer bits.  It may run
+        // in any later round as long as no gate after it writes one of its bits, so it is handed on to the next round when
+        // that cannot delay anybody: there is a next round (dense gates are left, or this round holds low bits and an
+        // HBM-facing round follows anyway) and no later gate of this round or of the rest writes its bits.
+        {
+            uint32_t diag_reads = 0;
+            for (size_t i : members)
+                if (!ops[i].dense) diag_reads |= ops[i].reads;
+            // when an HBM-facing round has to follow anyway (this one holds low bits), the free slots go to low bits: the
+            // high bits then stay thread bits and phases on them are free
+            R = fill_R(R, first, diag_reads);
+            bool more_dense = false;
+            for (size_t i = 0; i < ops.size() && !more_dense; ++i) more_dense = !done[i] && ops[i].dense;
+            if (more_dense || (R & ~io_allowed)) {
+                std::vector<char> here(ops.size(), 0);
+                for (size_t i : members) here[i] = 1;
+                std::vector<size_t> kept;
+                for (size_t i : members) {
+                    bool hand_on = !ops[i].dense && (ops[i].reads & R);
+                    for (size_t j = i + 1; j < ops.size() && hand_on; ++j)
+                        if ((here[j] || !done[j]) && (ops[j].dense & ops[i].reads)) hand_on = false;
+                    if (hand_on) { done[i] = 0; here[i] = 0; ++remaining; } else kept.push_back(i);
+                }
+                members.swap(kept);
+            }
+        }
         if (!emit_round(R, members)) return false;
         last_R = R;
         first = false;
