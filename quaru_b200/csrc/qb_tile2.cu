@@ -662,17 +662,29 @@ static bool encode_rounds_with(const std::vector<Gate>& gates, const std::vector
     if (n_rounds == 0 || (last_R & ~io_allowed)) {  // the storing round must have its register bits within 5..11
         if (!emit_round(0xf00, {})) return false;
     }
-    if (pass_scalar.x != 1.0 || pass_scalar.y != 0.0) {   // the pass's constant factor: one table op without selectors, last round
-        if (n_ops >= max_ops || n_mats + 1 > max_mats) return false;
+    if (pass_scalar.x != 1.0 || pass_scalar.y != 0.0) {   // the pass's constant factor, applied in the last round:
         RoundDesc& last = prog->rounds[n_rounds - 1];
-        ROp o;
-        memset(&o, 0, sizeof(o));
-        o.code = RC_TAB;
-        o.mat = (uint32_t)n_mats;
-        prog->mats[n_mats++] = pass_scalar;
-        prog->ops[n_ops++] = o;
-        last.op_end = (uint16_t)n_ops;
-        last.has_tph = 1;
+        bool absorbed = false;   // ... by a per-thread table that round already has (its entries are scaled), ...
+        for (uint32_t oi = last.op_begin; oi < last.op_end && !absorbed; ++oi) {
+            const ROp& t = prog->ops[oi];
+            if (t.code != RC_TAB) continue;
+            for (uint32_t e = 0; e < (1u << t.k); ++e) {
+                c64& v = prog->mats[t.mat + e];
+                v = make_double2(v.x * pass_scalar.x - v.y * pass_scalar.y, v.x * pass_scalar.y + v.y * pass_scalar.x);
+            }
+            absorbed = true;
+        }
+        if (!absorbed) {   // ... or as one table op without selectors
+            if (n_ops >= max_ops || n_mats + 1 > max_mats) return false;
+            ROp o;
+            memset(&o, 0, sizeof(o));
+            o.code = RC_TAB;
+            o.mat = (uint32_t)n_mats;
+            prog->mats[n_mats++] = pass_scalar;
+            prog->ops[n_ops++] = o;
+            last.op_end = (uint16_t)n_ops;
+            last.has_tph = 1;
+        }
     }
     prog->n_rounds = (uint32_t)n_rounds;
     prog->n_mats = (uint32_t)n_mats;
