@@ -151,3 +151,13 @@ def test_persistent_tile_kernels(engine, n, kind, variant):
     ref, _ = _run(engine, n, ops, 3000 + n)
     if not os.environ.get("QB_TILE_RTAB"):        # the register-table op multiplies phases on the host: equal within tolerance only
         assert reg.max_abs_diff(ref) == 0.0, "same arithmetic as the default kernel: bit-identical"
+
+
+@pytest.mark.parametrize("n,kind", [(14, "layers"), (16, "mixed"), (17, "qft"), (20, "layers")])
+def test_thorough_planning_forced_on_small_registers(engine, n, kind, monkeypatch):
+    """Registers of >= 26 / 28 local qubits (the bench) plan with a look-ahead over the tile bits and search the rounds;
+    QB_PLAN_LOOKAHEAD=1 forces the same host logic on at sizes whose state can be compared amplitude by amplitude."""
+    monkeypatch.setenv("QB_PLAN_LOOKAHEAD", "1")
+    ops = {"layers": circuits.random_circuit(n, 8, seed=n), "qft": circuits.qft_circuit(n), "mixed": circuits.mixed_circuit(n, 150, n)}[kind]
+    reg, ora = _run(engine, n, ops, 4000 + n)
+    assert_close(reg.state, ora.state, f"thorough planning n={n} {kind}")
