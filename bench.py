@@ -208,6 +208,21 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------------------------------
+# after the measurement: what the tile-kernel variants and planner switches cost on this GPU (outside every timed region)
+# --------------------------------------------------------------------------------------------------
+def diagnostics(n, budget_s=100.0):
+    """tools/bench_diagnostics.py in a child process (each configuration in a grandchild of its own): a faulting
+    experimental kernel can neither disturb the numbers above, which are final by now, nor keep the line from printing."""
+    try:
+        p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "bench_diagnostics.py"), str(n), str(budget_s)],
+                           cwd=ROOT, capture_output=True, text=True, timeout=budget_s + 60.0)
+        last = [ln for ln in p.stdout.splitlines() if ln.startswith("{")]
+        return json.loads(last[-1]) if last else {"error": (p.stderr.strip().splitlines() or [f"exit {p.returncode}"])[-1][:200]}
+    except Exception as e:
+        return {"error": repr(e)[:200]}
+
+
+# --------------------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------------------
 def run_ours(args):
@@ -379,14 +394,16 @@ def run_ours(args):
                           "peak_GBps_per_direction": nv_peak, "roofline_s_per_step": hbm_s + nv_s,
                           "roofline_hbm_s": hbm_s, "roofline_nvlink_s": nv_s,
                           "frac_of_roofline": (hbm_s + nv_s) / (ms / args.steps / 1e3)}
+    reg.close()    # frees the state (137 GB) before the diagnostics processes allocate theirs
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             try:
                 line["cpu_baseline"] = cpu_baseline(n, 1, budget_s=25.0)
             except Exception as e:  # the oracle is test infrastructure; never let it take the bench down
                 line["cpu_baseline"] = {"value": None, "unit": "gates/s", "cores": 0, "kind": "port", "sample": f"failed: {e}"}
+        if world == 1 and not args.no_diagnostics:
+            line["diagnostics"] = diagnostics(min(30, n))
         print(json.dumps(line), flush=True)
-    reg.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -399,6 +416,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--qubits", type=int, default=0, help="override the qubit count (default 33 + log2(gpus))")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-diagnostics", action="store_true", help="skip the kernel-variant table appended at N = 1")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
