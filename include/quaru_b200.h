@@ -182,6 +182,7 @@ int qb_set_option(qb_reg* reg, int32_t option, int64_t value);
 #define QB_STAT_TILE_NS 8         /* summed device time of the profiled tile-pass launches, ns */
 #define QB_STAT_ROUNDS 9          /* register rounds executed by the register-blocked tile kernel */
 #define QB_STAT_P2P_EXCHANGES 10  /* exchanges done by the peer-memory kernel (the rest went through NCCL send/recv) */
+#define QB_STAT_REMOTE_PASSES 11  /* tile passes that reached peers' shards directly (QB_SHARD_REMOTE=1; their NVLink bytes count in QB_STAT_SWAP_BYTES) */
 int qb_get_stat(qb_reg* reg, int32_t stat, int64_t* value);
 
 /* ---- planner introspection (host only, no GPU needed) ------------------------------------ */

@@ -19,7 +19,8 @@ QB_ERR_CUDA, QB_ERR_NCCL, QB_ERR_OOM, QB_ERR_NO_DEVICE, QB_ERR_UNSUPPORTED = 1, 
 
 QB_OPT_FUSION, QB_OPT_TILE_BITS, QB_OPT_MAX_QUEUE, QB_OPT_FORCE_PATH, QB_OPT_PROFILE = 1, 2, 3, 4, 5
 (QB_STAT_KERNEL_LAUNCHES, QB_STAT_PASSES, QB_STAT_GATES, QB_STAT_BYTES_MOVED, QB_STAT_SWAP_BYTES,
- QB_STAT_SWAPS, QB_STAT_TILE_LAUNCHES, QB_STAT_TILE_NS, QB_STAT_ROUNDS, QB_STAT_P2P_EXCHANGES) = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10
+ QB_STAT_SWAPS, QB_STAT_TILE_LAUNCHES, QB_STAT_TILE_NS, QB_STAT_ROUNDS, QB_STAT_P2P_EXCHANGES,
+ QB_STAT_REMOTE_PASSES) = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11
 
 
 QB_ERR_QASM = -6

@@ -474,6 +474,7 @@ int qb_get_stat(qb_reg* reg, int32_t stat, int64_t* value) try {
         case QB_STAT_TILE_LAUNCHES: QB_TRY(drain_tile_events(r)); *value = r->st_tile_launches; return QB_OK;
         case QB_STAT_ROUNDS: *value = r->st_rounds; return QB_OK;
         case QB_STAT_P2P_EXCHANGES: *value = r->st_p2p; return QB_OK;
+        case QB_STAT_REMOTE_PASSES: *value = r->st_remote_passes; return QB_OK;
         case QB_STAT_TILE_NS: QB_TRY(drain_tile_events(r)); *value = r->st_tile_ns; return QB_OK;
     }
     return set_error(QB_ERR_INVALID_ARGUMENT, stat, "unknown stat %d", stat);

@@ -94,7 +94,7 @@ struct Reg {
     int profile = 0;
     // stats
     int64_t st_launches = 0, st_passes = 0, st_gates = 0, st_bytes = 0, st_swap_bytes = 0, st_swaps = 0;
-    int64_t st_tile_launches = 0, st_tile_ns = 0, st_rounds = 0, st_p2p = 0;
+    int64_t st_tile_launches = 0, st_tile_ns = 0, st_rounds = 0, st_p2p = 0, st_remote_passes = 0;
     std::vector<cudaEvent_t> tile_events;  // start/stop pairs of profiled tile launches
     size_t tile_events_used = 0;
     // sharding

@@ -746,6 +746,39 @@ static int launch_rpass(Reg* r, const Prog& prog) {
     return QB_OK;
 }
 
+// Sharded registers, experimental (QB_SHARD_REMOTE=1): the pass runs on the virtual register formed by all shards; see
+// k2r_tile_pass_remote.  `bases[p]` = shard of rank p as mapped into this process.
+template <class Prog>
+static int launch_rpass_remote(Reg* r, const Prog& prog, uint32_t n_virtual, c64* const* bases) {
+    static std::atomic<uint64_t> attr_devs{0};
+    if (!((attr_devs.load() >> (r->device & 63)) & 1)) {
+        QB_CUDA(cudaFuncSetAttribute(k2r_tile_pass_remote<Prog>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(c64) << RT)));
+        attr_devs.fetch_or(1ull << (r->device & 63));
+    }
+    const uint32_t g = n_virtual - r->n_local;
+    RemoteArgs ra;
+    memset(&ra, 0, sizeof(ra));
+    for (uint32_t p = 0; p < (1u << g); ++p) ra.base[p] = bases[p];
+    ra.n_local = r->n_local;
+    ra.tile_or = remote_fixed_bits(prog.hp, prog.h, r->n_local, g, (uint32_t)r->rank) << (n_virtual - RT - g);
+    uint32_t in_tile = 0;   // rank bits among the tile bits: 1 - 2^-in_tile of the tile's amplitudes live on peers
+    for (uint32_t j = 0; j < prog.h; ++j) in_tile += prog.hp[j] >= r->n_local;
+    const uint64_t tiles = 1ull << (r->n_local - RT);
+    if (tiles > 0x7fffffffull) return set_error(QB_ERR_UNSUPPORTED, (int64_t)tiles, "too many tiles for one grid");
+    if (r->profile) QB_TRY(tile_profile_begin(r));
+    k2r_tile_pass_remote<Prog><<<(unsigned)tiles, RTHREADS, sizeof(c64) << RT, r->stream>>>(ra, prog);
+    QB_CUDA(cudaGetLastError());
+    if (r->profile) QB_TRY(tile_profile_end(r));
+    r->st_launches++;
+    r->st_passes++;
+    r->st_rounds += prog.n_rounds;
+    r->st_bytes += (int64_t)(32ull << r->n_local);
+    // NVLink accounting: what this rank stores into peers' shards (it loads as much from them)
+    r->st_swap_bytes += (int64_t)((16ull << r->n_local) - ((16ull << r->n_local) >> in_tile));
+    r->st_remote_passes += in_tile > 0;
+    return QB_OK;
+}
+
 // Experimental (QB_OPT_FORCE_PATH = 5..10): persistent CTAs with the coefficient tables staged in shared memory;
 // 6, 8, 10 also stage the op records, 7 and 8 prefetch the next tile into L2, 9 and 10 fetch op records one op ahead.
 template <class Prog, bool STAGE_OPS, bool PREFETCH, bool AHEAD>
@@ -847,6 +880,28 @@ int run_pass_v2(Reg* r, const std::vector<Gate>& gates, const std::vector<size_t
         return QB_OK;
     *handled = true;
     return launch_variant(r, large);
+}
+
+// Sharded registers (qb_shard.cu, QB_SHARD_REMOTE=1): one pass over the virtual register of n_virtual = n_local + g bits.
+// `gates` carry PHYSICAL positions in that register (rank bits included, nothing resolved per rank), `tile_pos` may contain
+// rank bits.  *handled = false (and nothing launched) if the register-blocked encoder cannot take the pass.
+int run_pass_remote(Reg* r, uint32_t n_virtual, const std::vector<Gate>& gates, const std::vector<size_t>& gate_idx,
+                    const std::vector<uint32_t>& tile_pos, uint32_t lc, c64* const* bases, bool* handled) {
+    *handled = false;
+    if (tile_pos.size() != RT || r->n_local < RT || n_virtual <= r->n_local || n_virtual - r->n_local > 3) return QB_OK;
+    size_t mats = 0;
+    for (size_t gi : gate_idx) mats += gates[gi].matrix.size();
+    if (gate_idx.size() <= 20 && mats <= 150) {
+        RProgSmall small;
+        if (encode_rounds(gates, gate_idx, tile_pos, lc, &small, thorough_encoding(n_virtual), false)) {
+            *handled = true;
+            return launch_rpass_remote(r, small, n_virtual, bases);
+        }
+    }
+    static thread_local RProgLarge large;
+    if (!encode_rounds(gates, gate_idx, tile_pos, lc, &large, thorough_encoding(n_virtual), false)) return QB_OK;
+    *handled = true;
+    return launch_rpass_remote(r, large, n_virtual, bases);
 }
 
 }  // namespace qb

@@ -286,6 +286,7 @@ __global__ void __launch_bounds__(RTHREADS, 2) k2r_tile_pass(c64* __restrict__ s
     QB_DYNAMIC_SMEM(smem_raw);
     c64* tile = reinterpret_cast<c64*>(smem_raw);
 #define QB_TILE_IX blockIdx.x
+#define QB_AMP(off) (st + (off))
 #define QB_MATS prog.mats
 #define QB_BEFORE_OPS
 #define QB_FETCH_OP const ROp& op = prog.ops[oi];
@@ -293,6 +294,7 @@ __global__ void __launch_bounds__(RTHREADS, 2) k2r_tile_pass(c64* __restrict__ s
 #define QB_EXTRA_CASES
 #include "qb_tile2_body.inc"
 #undef QB_TILE_IX
+#undef QB_AMP
 #undef QB_MATS
 #undef QB_BEFORE_OPS
 #undef QB_FETCH_OP
@@ -324,6 +326,7 @@ __global__ void __launch_bounds__(RTHREADS, 2) k2r_tile_pass_persist(c64* __rest
     __syncthreads();
     for (uint32_t tile_ix = blockIdx.x; tile_ix < n_tiles; tile_ix += gridDim.x) {
 #define QB_TILE_IX tile_ix
+#define QB_AMP(off) (st + (off))
 #define QB_MATS s_mats
 #define QB_OPS (STAGE_OPS ? s_ops : prog.ops)
     /* AHEAD: the record of op oi+1 is requested before op oi is executed, so the decode chain of the next op (record ->   \
@@ -350,6 +353,7 @@ __global__ void __launch_bounds__(RTHREADS, 2) k2r_tile_pass_persist(c64* __rest
     } break;
 #include "qb_tile2_body.inc"
 #undef QB_TILE_IX
+#undef QB_AMP
 #undef QB_MATS
 #undef QB_OPS
 #undef QB_BEFORE_OPS
@@ -357,6 +361,66 @@ __global__ void __launch_bounds__(RTHREADS, 2) k2r_tile_pass_persist(c64* __rest
 #undef QB_AFTER_FIRST_LOADS
 #undef QB_EXTRA_CASES
     }
+}
+
+// ---- sharded registers: a tile pass whose tile may contain RANK bits (experimental, QB_SHARD_REMOTE=1) --------------------
+// The P = 2^g shards of one register are treated as ONE virtual register of n = n_local + g index bits (amplitude index
+// `off`: rank = off >> n_local, offset in that rank's shard = the low n_local bits); every rank maps all shards (CUDA IPC,
+// qb_shard.cu).  The pass program is the one the planner and the encoder produce for an n-qubit register: rank bits can be
+// tile bits like any other high bit, so a gate with a dense target on a global qubit runs WITHOUT the global<->local
+// exchange that otherwise precedes it -- the tile's amplitudes that live on peers are loaded from and stored to peer memory
+// over NVLink by the same kernel that applies the gates, tile by tile, while the other resident CTA of the SM computes.
+// Work split: the virtual register has 2^(n - 12) tiles; each rank takes the 2^(n_local - 12) tiles whose top g tile-index
+// bits equal `fixed` (remote_fixed_bits): a rank bit outside the tile keeps this rank's value (all of the tile's
+// amplitudes with that bit are local), a rank bit inside the tile is replaced by the highest local non-tile bits, so that
+// the ranks' tile sets are disjoint and cover everything.  Controls and diagonal gates on rank bits outside the tile are
+// ordinary "outer" bits of the tile index.  No rank-dependent decision is taken anywhere but in `fixed`.
+struct RemoteArgs {
+    c64* base[8];        // shard of rank i (base[own rank] = own shard)
+    uint32_t n_local;    // index bits per shard
+    uint32_t tile_or;    // fixed << (n - 12 - g): OR-ed into blockIdx.x to give the tile index in the virtual register
+};
+
+// Host and device: the g fixed top bits of this rank's tile indices, from the high tile bits `hp` (ascending positions).
+// Bit order, LSB first: the rank bits that ARE tile bits (their substitutes are the highest local non-tile bits, which sit
+// right below the non-tile rank bits in tile-index space), then the rank bits that are not.
+inline uint32_t remote_fixed_bits(const uint8_t* hp, uint32_t h, uint32_t n_local, uint32_t g, uint32_t rank) {
+    uint32_t in_tile = 0;
+    for (uint32_t j = 0; j < h; ++j)
+        if (hp[j] >= n_local) in_tile |= 1u << (hp[j] - n_local);
+    uint32_t fixed = 0, pos = 0;
+    for (uint32_t J = 0; J < g; ++J)
+        if ((in_tile >> J) & 1u) fixed |= ((rank >> J) & 1u) << pos++;
+    for (uint32_t J = 0; J < g; ++J)
+        if (!((in_tile >> J) & 1u)) fixed |= ((rank >> J) & 1u) << pos++;
+    return fixed;
+}
+
+__device__ __forceinline__ c64* remote_amp(const RemoteArgs& ra, uint64_t lmask, uint64_t off) {
+    return ra.base[off >> ra.n_local] + (off & lmask);
+}
+
+template <class Prog>
+__global__ void __launch_bounds__(RTHREADS, 2) k2r_tile_pass_remote(const __grid_constant__ RemoteArgs ra, const __grid_constant__ Prog prog) {
+    QB_DYNAMIC_SMEM(smem_raw);
+    c64* tile = reinterpret_cast<c64*>(smem_raw);
+    const uint32_t tile_ix = blockIdx.x | ra.tile_or;
+    const uint64_t lmask = (1ull << ra.n_local) - 1ull;
+#define QB_TILE_IX tile_ix
+#define QB_AMP(off) remote_amp(ra, lmask, (off))
+#define QB_MATS prog.mats
+#define QB_BEFORE_OPS
+#define QB_FETCH_OP const ROp& op = prog.ops[oi];
+#define QB_AFTER_FIRST_LOADS
+#define QB_EXTRA_CASES
+#include "qb_tile2_body.inc"
+#undef QB_TILE_IX
+#undef QB_AMP
+#undef QB_MATS
+#undef QB_BEFORE_OPS
+#undef QB_FETCH_OP
+#undef QB_AFTER_FIRST_LOADS
+#undef QB_EXTRA_CASES
 }
 
 }  // namespace qb

@@ -126,3 +126,50 @@ extern "C" int k2r_host_run(double* state, uint32_t n, const unsigned char* prog
     }
     return 0;
 }
+
+// the remote tile pass (sharded registers): `bases[p]` = shard of rank p, a host buffer of 2^(n_virtual - g) amplitudes;
+// runs the tiles that rank `rank` of `world` = 2^g would process, with the product's own work split (remote_fixed_bits)
+template <class Prog>
+static void run_grid_remote(double* const* bases, uint32_t world, uint32_t rank, uint32_t n_virtual, const Prog& prog) {
+    uint32_t g = 0;
+    while ((1u << g) < world) ++g;
+    RemoteArgs ra;
+    memset(&ra, 0, sizeof(ra));
+    for (uint32_t p = 0; p < world; ++p) ra.base[p] = reinterpret_cast<c64*>(bases[p]);
+    ra.n_local = n_virtual - g;
+    ra.tile_or = remote_fixed_bits(prog.hp, prog.h, ra.n_local, g, rank) << (n_virtual - RT - g);
+    const uint32_t n_tiles = 1u << (ra.n_local - RT);
+    blockDim = {RTHREADS, 1, 1};
+    gridDim = {n_tiles, 1, 1};
+    pthread_barrier_init(&qb_emu_barrier, nullptr, RTHREADS);
+    std::vector<std::thread> threads;
+    for (unsigned t = 0; t < RTHREADS; ++t)
+        threads.emplace_back([=, &prog]() {
+            for (unsigned b = 0; b < n_tiles; ++b) {
+                threadIdx = {t, 0, 0};
+                blockIdx = {b, 0, 0};
+                k2r_tile_pass_remote<Prog>(ra, prog);
+                pthread_barrier_wait(&qb_emu_barrier);
+            }
+        });
+    for (std::thread& th : threads) th.join();
+    pthread_barrier_destroy(&qb_emu_barrier);
+}
+
+extern "C" int k2r_host_run_remote(double* const* bases, uint32_t world, uint32_t rank, uint32_t n_virtual, const unsigned char* program,
+                                   uint64_t len, int use_small) {
+    if (world < 2 || world > 8 || (world & (world - 1)) || rank >= world) return -1;
+    uint32_t g = 0;
+    while ((1u << g) < world) ++g;
+    if (n_virtual < RT + g) return -1;
+    if (use_small) {
+        static RProgSmall small;
+        if (!deserialise(program, len, &small)) return -2;
+        run_grid_remote(bases, world, rank, n_virtual, small);
+    } else {
+        static RProgLarge large;
+        if (!deserialise(program, len, &large)) return -2;
+        run_grid_remote(bases, world, rank, n_virtual, large);
+    }
+    return 0;
+}

@@ -35,6 +35,9 @@ def host_kernel():
     lib.k2r_host_run.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_char_p, ctypes.c_uint64, ctypes.c_int]
     lib.k2r_host_run_persist.restype = ctypes.c_int
     lib.k2r_host_run_persist.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_char_p, ctypes.c_uint64, ctypes.c_int, ctypes.c_uint32, ctypes.c_int]
+    lib.k2r_host_run_remote.restype = ctypes.c_int
+    lib.k2r_host_run_remote.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_char_p,
+                                        ctypes.c_uint64, ctypes.c_int]
     return lib
 
 
@@ -139,3 +142,41 @@ def test_register_table_op_on_the_persistent_kernels(host_kernel, kind, n, varia
     assert n_prog >= 1
     assert_close(dev, want, f"RTAB, kernel {variant} vs oracle, {kind} n={n}")
     assert_close(dev, emu, "kernel vs program emulator")
+
+
+@pytest.mark.parametrize("world,n,kind", [(2, 14, "layers"), (2, 13, "mixed"), (4, 15, "qft"), (4, 14, "mixed"), (8, 15, "layers"), (8, 16, "mixed")])
+def test_remote_tile_pass_on_the_host_compiled_kernel(host_kernel, world, n, kind):
+    """k2r_tile_pass_remote (QB_SHARD_REMOTE=1): the register is split into `world` shards (separate host buffers reached
+    through a pointer table, as the peer-mapped shards are on a GPU box); every rank runs its share of the tiles of the
+    n-qubit programs -- whose tiles may contain rank bits -- and together they must reproduce the single-register run bit
+    for bit: every tile processed exactly once, whatever mix of rank bits it contains."""
+    g = world.bit_length() - 1
+    nl = n - g
+    ops = {"layers": circuits.random_circuit(n, 5, seed=7 * n), "qft": circuits.qft_circuit(n), "mixed": circuits.mixed_circuit(n, 120, 3 * n)}[kind]
+    s0 = random_state(n, 40 + n)
+    ora = OracleRegister(s0.copy(), n)
+    for o in ops:
+        ora.apply(o)
+    ref = s0.copy()
+    shards = [np.ascontiguousarray(s0[r << nl:(r + 1) << nl]) for r in range(world)]   # separate allocations, like the real shards
+    bases = (ctypes.c_void_p * world)(*[sh.ctypes.data for sh in shards])
+    n_remote = 0
+    for p in em.dump_programs(n, ops):
+        if p[0] == "gates":
+            whole = np.concatenate(shards)
+            for st in (ref, whole):
+                tmp = OracleRegister(st, n)
+                for tag in p[1]:
+                    tmp.apply(ops[tag])
+                st[:] = tmp.state
+            for r in range(world):
+                shards[r][:] = whole[r << nl:(r + 1) << nl]
+            continue
+        n_remote += any(b >= nl for b in p[2])
+        assert host_kernel.k2r_host_run(ref.ctypes.data, n, p[3]["bytes"], len(p[3]["bytes"]), 0) == 0
+        for r in range(world):
+            assert host_kernel.k2r_host_run_remote(bases, world, r, n, p[3]["bytes"], len(p[3]["bytes"]), 0) == 0
+    assert n_remote >= 1, "at least one pass has a rank bit among its tile bits"
+    got = np.concatenate(shards)
+    assert np.array_equal(got, ref), "same tiles, same arithmetic as the single-register kernel"
+    assert_close(got, ora.state, f"remote tile pass vs oracle, world={world} n={n} {kind}")
