@@ -26,6 +26,7 @@
 #include <mutex>
 
 #include "qb_shard.h"
+#include "qb_tile.h"
 #include "qb_device.cuh"
 
 namespace qb {
@@ -541,9 +542,8 @@ static int shard_run_reordered(Reg* r, std::vector<Gate>& gates) {
     return QB_OK;
 }
 
-int shard_run(Reg* r, std::vector<Gate>& gates) {
-    const char* reorder = getenv("QB_SHARD_REORDER");
-    if (reorder && !strcmp(reorder, "1")) return shard_run_reordered(r, gates);
+// Default scheduler: the gate list is cut at every gate that needs an exchange.
+static int shard_run_default(Reg* r, std::vector<Gate>& gates) {
     std::vector<Gate> batch;
     for (size_t i = 0; i < gates.size(); ++i) {
         Gate m;
@@ -562,6 +562,114 @@ int shard_run(Reg* r, std::vector<Gate>& gates) {
     if (!batch.empty() && !r->shard->dry) QB_TRY(run_local(r, batch));
     if (!batch.empty() && r->shard->dry) r->shard->dry_passes += count_passes(r, batch);
     return QB_OK;
+}
+
+// Experimental (QB_SHARD_REMOTE=1, off by default until it has run on hardware): NO exchanges.  The P shards are planned as
+// one virtual register of n = n_local + g index bits: rank bits may become tile bits of a pass like any other high bit, and
+// such a pass runs through k2r_tile_pass_remote (qb_tile2_kernel.cuh), which loads and stores the tile's amplitudes that live
+// on peers through the CUDA-IPC mappings -- the transfer a global<->local exchange would do up front happens inside the
+// compute kernel, tile by tile, overlapped with the (compute-bound) gate work of the other resident CTAs, and the qubit
+// placement never changes.  Passes without a rank bit in their tile go through the ordinary local path (rank bits of
+// controls and diagonals resolved per rank, as always).  Every decision depends on the placement and the gate list only,
+// so all ranks launch the same sequence of passes and barriers.  Whatever the register-blocked encoder cannot take falls
+// back to the exchange scheduler for the rest of the list.
+static const int32_t kRemoteMark = -(1 << 30);   // dry-run event: [kRemoteMark, n_gates, tags..., 12 tile positions]
+static int barrier_all(Reg* r);
+static int shard_run_default(Reg* r, std::vector<Gate>& gates);
+static int shard_run_remote(Reg* r, std::vector<Gate>& gates) {
+    Shard* s = r->shard;
+    const uint32_t nl = r->n_local, n = r->n;
+    bool ok = (s->dry || s->p2p) && nl >= 12 && r->fusion && r->tile_bits == 12 && r->force_path == 0;
+    for (const Gate& g : gates) ok = ok && tile_supported(g);
+    if (!ok) return shard_run_default(r, gates);
+    std::vector<Gate> v(gates.size());   // the gates at their physical positions in the virtual register
+    for (size_t i = 0; i < gates.size(); ++i) {
+        const Gate& g = gates[i];
+        Gate& o = v[i];
+        o.kind = g.kind;
+        o.k = g.k;
+        o.matrix = g.matrix;
+        o.tag = (int64_t)i;
+        o.targets.resize(g.k);
+        for (uint32_t j = 0; j < g.k; ++j) o.targets[j] = r->phys_of[g.targets[j]];
+        o.ctrl_mask = 0;
+        for (uint64_t m = g.ctrl_mask; m; m &= m - 1) o.ctrl_mask |= 1ull << r->phys_of[__builtin_ctzll(m)];
+    }
+    std::vector<PlannedPass> passes;
+    plan_register_passes(v, n, &passes);
+    std::vector<char> done(gates.size(), 0);
+    std::vector<Gate> batch;   // mapped gates of consecutive passes whose tiles are local
+    bool dirty = false;        // a remote pass has been launched and no barrier has followed it yet
+    auto tag_of = [&](size_t gi) { return (int32_t)(gates[gi].tag >= 0 ? gates[gi].tag : (int64_t)gi); };
+    auto flush_local = [&]() -> int {
+        if (batch.empty()) return QB_OK;
+        if (s->dry) {
+            s->dry_passes += count_passes(r, batch);
+        } else {
+            if (dirty) { QB_TRY(barrier_all(r)); dirty = false; }   // peers may still be storing into this shard
+            QB_TRY(run_local(r, batch));
+        }
+        batch.clear();
+        return QB_OK;
+    };
+    auto fall_back = [&]() -> int {   // the exchange scheduler takes over for everything that has not run yet
+        QB_TRY(flush_local());
+        if (dirty && !s->dry) { QB_TRY(barrier_all(r)); dirty = false; }
+        std::vector<Gate> rest;
+        for (size_t i = 0; i < gates.size(); ++i)
+            if (!done[i]) { rest.push_back(gates[i]); if (rest.back().tag < 0) rest.back().tag = (int64_t)i; }
+        return shard_run_default(r, rest);
+    };
+    for (const PlannedPass& p : passes) {
+        bool remote = false;
+        for (uint32_t b : p.tile_pos) remote = remote || b >= nl;
+        if (!remote) {
+            std::vector<Gate> mapped;
+            for (size_t gi : p.gate_idx) {
+                Gate m;
+                const MapResult res = map_gate(r, gates[gi], &m);
+                if (res == MAP_NEEDS_SWAP) return fall_back();   // a gate the tile kernels cannot take with a dense rank-bit target
+                if (res == MAP_LOCAL) mapped.push_back(std::move(m));
+            }
+            for (size_t gi : p.gate_idx) {
+                done[gi] = 1;
+                if (s->dry) s->events.push_back(-1 - tag_of(gi));
+            }
+            for (Gate& m : mapped) batch.push_back(std::move(m));
+            continue;
+        }
+        QB_TRY(flush_local());
+        bool handled = false;
+        if (s->dry) {
+            std::vector<unsigned char> buf(64 << 10);
+            handled = encode_rounds_debug(n, v, p.gate_idx, p.tile_pos, p.lc, buf.data(), buf.size()) > 0;
+        } else {
+            QB_TRY(barrier_all(r));   // every peer has finished the kernels that wrote what this pass reads
+            dirty = false;
+            QB_TRY(run_pass_remote(r, n, v, p.gate_idx, p.tile_pos, p.lc, s->peer, &handled));
+            dirty = handled;
+        }
+        if (!handled) return fall_back();
+        if (s->dry) {
+            s->dry_passes++;
+            s->events.push_back(kRemoteMark);
+            s->events.push_back((int32_t)p.gate_idx.size());
+            for (size_t gi : p.gate_idx) s->events.push_back(tag_of(gi));
+            for (uint32_t j = 0; j < 12; ++j) s->events.push_back((int32_t)p.tile_pos[j]);
+        }
+        for (size_t gi : p.gate_idx) done[gi] = 1;
+    }
+    QB_TRY(flush_local());
+    if (dirty && !s->dry) QB_TRY(barrier_all(r));   // nobody reads or measures its shard while a peer is still storing into it
+    return QB_OK;
+}
+
+int shard_run(Reg* r, std::vector<Gate>& gates) {
+    const char* remote = getenv("QB_SHARD_REMOTE");
+    if (remote && !strcmp(remote, "1")) return shard_run_remote(r, gates);
+    const char* reorder = getenv("QB_SHARD_REORDER");
+    if (reorder && !strcmp(reorder, "1")) return shard_run_reordered(r, gates);
+    return shard_run_default(r, gates);
 }
 
 // Dry run of the placement logic for tests: which exchanges would a rank perform for this gate list?

@@ -152,17 +152,10 @@ __global__ void __launch_bounds__(TILE_THREADS) k2_tile_pass(c64* __restrict__ s
 // ------------------------------------------------------------------------------------------------
 // planner
 // ------------------------------------------------------------------------------------------------
-struct PlannedPass {
-    std::vector<uint32_t> tile_pos;  // ascending global positions of the tile bits
-    uint32_t lc = 0;
-    std::vector<size_t> gate_idx;    // indices into the gate list, in execution order
-    bool unfused = false;            // a single gate the tile kernel cannot take
-};
-
 constexpr uint32_t MIN_LC = 5;       // >= 512-byte contiguous segments
 constexpr uint32_t MAX_DIAG_K = 3;
 
-static bool tile_supported(const Gate& g) {
+bool tile_supported(const Gate& g) {
     if (g.kind == GK_DIAG) return g.k <= MAX_DIAG_K;
     return g.k >= 1 && g.k <= 2;
 }
@@ -439,6 +432,11 @@ int run_fused(Reg* r, std::vector<Gate>& gates) {
         }
     }
     return QB_OK;
+}
+
+// The plan for a register of n index bits with 2^12 tiles (qb_shard.cu plans the virtual register of all shards with it).
+void plan_register_passes(const std::vector<Gate>& gates, uint32_t n, std::vector<PlannedPass>* out) {
+    plan_passes(gates, n, 12, (int)(sizeof(PassLarge::ops) / sizeof(TileOp)), (int)(sizeof(PassLarge::mats) / sizeof(c64)), out);
 }
 
 int64_t plan_debug(uint32_t n, std::vector<Gate>& gates, uint32_t tile_bits, int32_t* pass_of_gate, int32_t* order_in_pass) {

@@ -4,6 +4,14 @@
 #include "qb_common.h"
 
 namespace qb {
+struct PlannedPass {
+    std::vector<uint32_t> tile_pos;  // ascending global positions of the tile bits
+    uint32_t lc = 0;
+    std::vector<size_t> gate_idx;    // indices into the gate list, in execution order
+    bool unfused = false;            // a single gate the tile kernel cannot take
+};
+bool tile_supported(const Gate& g);  // can go through a tile pass at all (dense k <= 2, diagonal k <= 3)
+void plan_register_passes(const std::vector<Gate>& gates, uint32_t n, std::vector<PlannedPass>* out);
 int tile_profile_begin(Reg* r);  // QB_OPT_PROFILE: CUDA-event bracket around one tile launch
 int tile_profile_end(Reg* r);
 int run_pass_v2(Reg* r, const std::vector<Gate>& gates, const std::vector<size_t>& gate_idx,

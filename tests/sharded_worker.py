@@ -34,6 +34,7 @@ def main():
         return bytes(uid.cpu().tolist())
 
     failures = []
+    remote_passes = [0]
     g = int(np.log2(world))
 
     def check(name, n, ops, fusion, measure=()):
@@ -61,6 +62,7 @@ def main():
         if abs(nrm - 1.0) > 1e-10:
             failures.append(f"{name}: norm2 {nrm}")
         swaps = reg.stat(_ffi.QB_STAT_SWAPS)
+        remote_passes[0] += reg.stat(_ffi.QB_STAT_REMOTE_PASSES)
         reg.close()
         return swaps
 
@@ -80,6 +82,15 @@ def main():
     swaps = check("layers n=20", 20, circuits.random_circuit(20, 3, seed=20), 1, measure=(19,))
     if rank == 0:
         print(f"exchanges in the n=20 run: {swaps}", flush=True)
+    if os.environ.get("QB_SHARD_REMOTE") == "1":
+        # experimental exchange-free scheduler: shards of >= 2^12 amplitudes, so that rank bits can be tile bits
+        n = 13 + g
+        check(f"remote: layers n={n}", n, circuits.random_circuit(n, 6, seed=3 * n), 1, measure=(n - 1, 0))
+        check(f"remote: qft n={n}", n, circuits.qft_circuit(n), 1)
+        ops = [o for o in circuits.mixed_circuit(n, 120, seed=n) if len(o[1]) <= 2]
+        check(f"remote: mixed n={n}", n, ops, 1, measure=(1, n - 2))
+        if rank == 0:
+            print(f"remote passes: {remote_passes[0]}", flush=True)
 
     if os.environ.get("QB_SHARDED_EXTRA") == "1":
         # in-place reset and raw state files on a register whose placement has been permuted by exchanges

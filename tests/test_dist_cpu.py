@@ -256,3 +256,106 @@ def test_reordering_scheduler_replay_matches_oracle(n, world, kind):
     swaps = sum(1 for e in events if e[0] == "swap")
     base = len(_plan_events(n, world, 0, ops)[0])
     assert swaps <= base, f"deferring must not need more exchanges ({swaps} vs {base})"
+
+
+# ---- experimental exchange-free scheduler (QB_SHARD_REMOTE=1): rank bits as tile bits of remote tile passes -----------
+REMOTE_MARK = -(1 << 30)
+
+
+def _plan_events_remote(n, world, rank, ops):
+    """Event stream of shard_run_remote in dry mode: ("run", i) = gate i through the local path, ("remote", [gates], tile bits) =
+    one pass of k2r_tile_pass_remote over the virtual register, ("swap", V, J) = exchange (fallback scheduler only)."""
+    from quaru_b200 import _ffi
+    L = _ffi.lib()
+    arr = (_ffi.QbGate * max(len(ops), 1))()
+    keep = []
+    for i, (m, t) in enumerate(ops):
+        mm = np.ascontiguousarray(m, dtype=np.complex128)
+        tt = (ctypes.c_uint32 * max(len(t), 1))(*t)
+        keep += [mm, tt]
+        arr[i].matrix = mm.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+        arr[i].targets = tt
+        arr[i].k = len(t)
+    cap = 64 * (len(ops) + 1)
+    ev = (ctypes.c_int32 * cap)()
+    phys = (ctypes.c_uint32 * n)()
+    os.environ["QB_SHARD_REMOTE"] = "1"
+    try:
+        cnt = L.qb_shard_plan_debug(n, world, rank, arr, len(ops), ev, cap, phys)
+    finally:
+        del os.environ["QB_SHARD_REMOTE"]
+    assert cnt >= 0, _ffi.last_error()
+    flat, out, i = list(ev)[:cnt], [], 0
+    while i < len(flat):
+        if flat[i] == REMOTE_MARK:
+            ng = flat[i + 1]
+            out.append(("remote", flat[i + 2:i + 2 + ng], flat[i + 2 + ng:i + 14 + ng]))
+            i += 14 + ng
+        elif flat[i] < 0:
+            out.append(("run", -1 - flat[i]))
+            i += 1
+        else:
+            gp = flat[i + 1]
+            out.append(("swap", flat[i + 2:i + 2 + gp], flat[i + 2 + gp:i + 2 + 2 * gp]))
+            i += 2 + 2 * gp
+    return out, list(phys)
+
+
+@pytest.mark.parametrize("n,world,kind", [(13, 2, "layers"), (14, 4, "layers"), (15, 8, "layers"), (14, 2, "qft"), (15, 4, "qft"),
+                                          (14, 4, "mixed"), (15, 8, "bench")])
+def test_remote_scheduler_replay_matches_oracle(n, world, kind):
+    """No exchanges: a gate with a dense target on a rank bit runs in a remote pass whose tile contains that rank bit.  All
+    ranks must derive the same sequence; replayed in numpy (placement stays the identity) it must reproduce the oracle, with
+    every dense target of a remote pass among its tile bits and every dense target of a local run on a local bit."""
+    g = int(np.log2(world))
+    nl = n - g
+    if kind == "layers":
+        ops = circuits.random_circuit(n, 6, seed=n + world)
+    elif kind == "qft":
+        ops = circuits.qft_circuit(n)
+    elif kind == "bench":
+        ops = circuits.qft_circuit(n) + circuits.random_circuit(n, 6, seed=2)
+    else:
+        ops = [o for o in circuits.mixed_circuit(n, 120, seed=n) if len(o[1]) <= 2]
+    per_rank = [_plan_events_remote(n, world, r, ops) for r in range(world)]
+    for ev, ph in per_rank[1:]:
+        assert ev == per_rank[0][0] and ph == per_rank[0][1], "ranks disagree on the schedule"
+    events, final_phys = per_rank[0]
+    assert final_phys == list(range(n)), "remote passes never change the placement"
+    assert not any(e[0] == "swap" for e in events), "no exchange is needed for tile-supported gates"
+    assert any(e[0] == "remote" for e in events)
+    s0 = random_state(n, n * 13 + world)
+    ora = OracleRegister(s0.copy(), n)
+    for o in ops:
+        ora.apply(o)
+    st, ran = s0.copy(), []
+    for e in events:
+        if e[0] == "run":
+            m, t = ops[e[1]]
+            for q in _dense_targets(m, t):
+                assert q < nl, f"gate {e[1]}: dense target {q} is on a rank bit in a local run"
+            st = oracle_np.apply_np(st, n, m, list(t))
+            ran.append(e[1])
+            continue
+        tags, tile = e[1], e[2]
+        assert tile == sorted(tile) and len(set(tile)) == 12 and any(b >= nl for b in tile)
+        for i in tags:
+            m, t = ops[i]
+            for q in _dense_targets(m, t):
+                assert q in tile, f"gate {i}: dense target {q} is not a tile bit of its remote pass"
+            st = oracle_np.apply_np(st, n, m, list(t))
+            ran.append(i)
+    identities = [i for i, (m, t) in enumerate(ops) if np.array_equal(np.asarray(m), np.eye(len(m)))]
+    assert sorted(ran + identities) == list(range(len(ops))), "every gate runs exactly once"
+    assert_close(st, ora.state, f"remote schedule replay n={n} P={world} {kind}")
+
+
+def test_remote_scheduler_falls_back_to_exchanges_for_wide_gates():
+    """A dense 3-qubit gate cannot go through a tile pass: the whole list goes to the exchange scheduler."""
+    from oracle import gates as og
+    n, world = 14, 4
+    rng = np.random.default_rng(5)
+    u8 = np.linalg.qr(rng.normal(size=(8, 8)) + 1j * rng.normal(size=(8, 8)))[0]
+    ops = [og.hadamard(13), (u8, [13, 2, 7]), og.cnot(12, 3)]
+    events, phys = _plan_events_remote(n, world, 0, ops)
+    assert any(e[0] == "swap" for e in events) and not any(e[0] == "remote" for e in events)
