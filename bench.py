@@ -391,6 +391,9 @@ def run_ours(args):
         line["nvlink"] = {"swap_bytes_sent_per_gpu_per_step": swap_bytes_step, "swaps_per_step": swaps_step,
                           "transport": "peer-memory kernel (CUDA IPC)" if reg.stat(_ffi.QB_STAT_P2P_EXCHANGES) > 0 else "NCCL send/recv + staging",
                           "p2p_exchanges_total": reg.stat(_ffi.QB_STAT_P2P_EXCHANGES), "exchanges_total": reg.stat(_ffi.QB_STAT_SWAPS),
+                          "remote_passes_total": reg.stat(_ffi.QB_STAT_REMOTE_PASSES),
+                          "scheduler": ("remote tile passes (QB_SHARD_REMOTE=1)" if os.environ.get("QB_SHARD_REMOTE") == "1" else
+                                        "reordering (QB_SHARD_REORDER=1)" if os.environ.get("QB_SHARD_REORDER") == "1" else "default"),
                           "peak_GBps_per_direction": nv_peak, "roofline_s_per_step": hbm_s + nv_s,
                           "roofline_hbm_s": hbm_s, "roofline_nvlink_s": nv_s,
                           "frac_of_roofline": (hbm_s + nv_s) / (ms / args.steps / 1e3)}
