@@ -167,8 +167,8 @@ int qb_timer_stop(qb_reg* reg, float* ms);
 #define QB_OPT_TILE_BITS 2     /* log2 amplitudes per shared-memory tile (default 12) */
 #define QB_OPT_MAX_QUEUE 3     /* auto-flush after this many buffered gates (default 4096) */
 #define QB_OPT_FORCE_PATH 4    /* tests only: 0 auto, 1 generic kernel, 2 shared-memory tile kernel, 4 tile kernels even for single gates,
-                                  5..10 experimental persistent tile kernels (coefficients staged in shared memory; 6, 8, 10: op
-                                  records too; 7, 8: L2 prefetch of the next tile; 9, 10: op records fetched one op ahead) */
+                                  5..11 experimental persistent tile kernels (coefficients staged in shared memory; 6, 8, 10, 11: op
+                                  records too; 7, 8, 11: L2 prefetch of the next tile; 9, 10, 11: op records fetched one op ahead) */
 #define QB_OPT_PROFILE 5       /* 1: bracket every tile-pass launch with CUDA events (QB_STAT_TILE_NS) */
 int qb_set_option(qb_reg* reg, int32_t option, int64_t value);
 

@@ -453,7 +453,7 @@ int qb_set_option(qb_reg* reg, int32_t option, int64_t value) try {
             return QB_OK;
         case QB_OPT_PROFILE: r->profile = value != 0; return QB_OK;
         case QB_OPT_FORCE_PATH:
-            if (value < 0 || value > 10) return set_error(QB_ERR_INVALID_ARGUMENT, value, "force path must be in [0, 10]");
+            if (value < 0 || value > 11) return set_error(QB_ERR_INVALID_ARGUMENT, value, "force path must be in [0, 11]");
             r->force_path = (int)value;
             return QB_OK;
     }

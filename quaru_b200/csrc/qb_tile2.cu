@@ -779,8 +779,8 @@ static int launch_rpass_remote(Reg* r, const Prog& prog, uint32_t n_virtual, c64
     return QB_OK;
 }
 
-// Experimental (QB_OPT_FORCE_PATH = 5..10): persistent CTAs with the coefficient tables staged in shared memory;
-// 6, 8, 10 also stage the op records, 7 and 8 prefetch the next tile into L2, 9 and 10 fetch op records one op ahead.
+// Experimental (QB_OPT_FORCE_PATH = 5..11): persistent CTAs with the coefficient tables staged in shared memory;
+// 6, 8, 10 also stage the op records, 7 and 8 prefetch the next tile into L2, 9 and 10 fetch op records one op ahead, 11 does all three.
 template <class Prog, bool STAGE_OPS, bool PREFETCH, bool AHEAD>
 static int launch_rpass_persist(Reg* r, const Prog& prog) {
     const uint32_t n_ops = prog.rounds[prog.n_rounds - 1].op_end;
@@ -856,6 +856,7 @@ static int launch_variant(Reg* r, const Prog& prog) {
         case 8: return launch_rpass_persist<Prog, true, true, false>(r, prog);
         case 9: return launch_rpass_persist<Prog, false, false, true>(r, prog);
         case 10: return launch_rpass_persist<Prog, true, false, true>(r, prog);
+        case 11: return launch_rpass_persist<Prog, true, true, true>(r, prog);
         default: return launch_rpass(r, prog);
     }
 }

@@ -91,14 +91,15 @@ static void run_variant(double* state, uint32_t n_tiles, uint32_t grid, const Pr
         case 7: run_grid_persist<Prog, false, true, false>(state, n_tiles, grid, prog); break;
         case 8: run_grid_persist<Prog, true, true, false>(state, n_tiles, grid, prog); break;
         case 9: run_grid_persist<Prog, false, false, true>(state, n_tiles, grid, prog); break;
-        default: run_grid_persist<Prog, true, false, true>(state, n_tiles, grid, prog); break;
+        case 10: run_grid_persist<Prog, true, false, true>(state, n_tiles, grid, prog); break;
+        default: run_grid_persist<Prog, true, true, true>(state, n_tiles, grid, prog); break;
     }
 }
 
-// the experimental persistent kernels (variant = the QB_OPT_FORCE_PATH value, 5..10) with `grid` CTAs walking the tiles
+// the experimental persistent kernels (variant = the QB_OPT_FORCE_PATH value, 5..11) with `grid` CTAs walking the tiles
 extern "C" int k2r_host_run_persist(double* state, uint32_t n, const unsigned char* program, uint64_t len, int use_small, uint32_t grid,
                                     int variant) {
-    if (n < RT || grid < 1 || variant < 5 || variant > 10) return -1;
+    if (n < RT || grid < 1 || variant < 5 || variant > 11) return -1;
     const uint32_t n_tiles = 1u << (n - RT);
     if (use_small) {
         static RProgSmall small;

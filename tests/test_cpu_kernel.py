@@ -101,7 +101,8 @@ def test_small_program_instantiation(host_kernel):
 
 
 @pytest.mark.parametrize("n,grid,kind,variant", [(14, 3, "layers", 5), (14, 1, "mixed", 6), (15, 5, "qft", 7), (13, 2, "mixed", 8),
-                                                 (12, 1, "layers", 6), (14, 3, "qft", 8), (14, 2, "mixed", 9), (13, 3, "layers", 10)])
+                                                 (12, 1, "layers", 6), (14, 3, "qft", 8), (14, 2, "mixed", 9), (13, 3, "layers", 10), (14, 3, "mixed", 11),
+                                                 (13, 2, "qft", 11)])
 def test_persistent_variants_on_the_host_compiled_kernel(host_kernel, n, grid, kind, variant):
     """The experimental persistent kernels (QB_OPT_FORCE_PATH = 5..10): `grid` CTAs walk 2^(n-12) tiles with the coefficient
     tables (and, for 6 / 8, the op records) staged in shared memory; grids that do not divide the tile count and a single

@@ -139,7 +139,7 @@ def test_register_blocked_qft_and_diagonals(engine, n):
 
 
 @pytest.mark.skipif(os.environ.get("QB_TEST_EXPERIMENTAL") != "1", reason="experimental kernel variants: set QB_TEST_EXPERIMENTAL=1")
-@pytest.mark.parametrize("variant", [5, 6, 7, 8, 9, 10])
+@pytest.mark.parametrize("variant", [5, 6, 7, 8, 9, 10, 11])
 @pytest.mark.parametrize("n,kind", [(12, "layers"), (14, "mixed"), (16, "qft"), (18, "layers"), (20, "mixed")])
 def test_persistent_tile_kernels(engine, n, kind, variant):
     """QB_OPT_FORCE_PATH = 5..10: persistent CTAs, coefficient tables (6, 8: op records too) staged in shared memory, 7 / 8 with

@@ -6,7 +6,7 @@ cost on THIS GPU, so that every bench run also answers "which kernel should be t
 Every configuration runs in its own process (an experimental kernel that faults cannot take the others or the caller
 down) under its own timeout:
   * force_path 0 (default kernel) with the planner / encoder look-ahead on (default) and off (QB_PLAN_LOOKAHEAD=0);
-  * force_path 5..10: the persistent tile kernels of qb_tile2_kernel.cuh (coefficients / op records in shared memory,
+  * force_path 5..11: the persistent tile kernels of qb_tile2_kernel.cuh (coefficients / op records in shared memory,
     L2 prefetch of the next tile, op records fetched one op ahead), with and without the register-table op (QB_TILE_RTAB=1).
 Per configuration: the result at n = 24 is compared with the default kernel's (max |diff|, 0.0 = bit-identical), then the
 bench circuit family is timed at n qubits: 20 random layers, the QFT, and two skeleton circuits (H on 4 / on 12 qubits =
@@ -22,12 +22,12 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-CONFIGS = [  # (label, force_path, extra environment)
+CONFIGS = [  # (label, force_path, extra environment); most informative first, the time budget may cut the tail
     ("default", 0, {}),
     ("default_no_lookahead", 0, {"QB_PLAN_LOOKAHEAD": "0"}),
-    ("persist_mats", 5, {}), ("persist_mats_ops", 6, {}), ("persist_mats_pf", 7, {}), ("persist_mats_ops_pf", 8, {}),
-    ("persist_mats_ahead", 9, {}), ("persist_mats_ops_ahead", 10, {}),
-    ("persist_mats_ops_rtab", 6, {"QB_TILE_RTAB": "1"}), ("persist_mats_ops_ahead_rtab", 10, {"QB_TILE_RTAB": "1"}),
+    ("persist_mats_ops", 6, {}), ("persist_mats_ops_ahead", 10, {}), ("persist_mats_ops_pf_ahead", 11, {}),
+    ("persist_mats_ops_pf", 8, {}), ("persist_mats", 5, {}), ("persist_mats_ahead", 9, {}), ("persist_mats_pf", 7, {}),
+    ("persist_mats_ops_ahead_rtab", 10, {"QB_TILE_RTAB": "1"}), ("persist_mats_ops_rtab", 6, {"QB_TILE_RTAB": "1"}),
 ]
 
 
@@ -85,7 +85,7 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == "--one":
         return one(int(sys.argv[2]), int(sys.argv[3]))
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 30
-    budget = float(sys.argv[2]) if len(sys.argv) > 2 else 100.0
+    budget = float(sys.argv[2]) if len(sys.argv) > 2 else 120.0
     t_end = time.time() + budget
     out = {"n": n, "unit": "ms", "note": "best of 3, CUDA events on the library stream; one process per configuration", "rows": []}
     for label, force, env in CONFIGS:

@@ -14,7 +14,7 @@ from tests.util import random_state  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 30
 depth = int(sys.argv[2]) if len(sys.argv) > 2 else 20
-variants = [int(x) for x in sys.argv[3].split(",")] if len(sys.argv) > 3 else [0, 5, 6, 7, 8, 9, 10]
+variants = [int(x) for x in sys.argv[3].split(",")] if len(sys.argv) > 3 else [0, 5, 6, 7, 8, 9, 10, 11]
 
 
 def small_check(variant):
