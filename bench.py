@@ -210,12 +210,12 @@ def run_reference(args):
 # --------------------------------------------------------------------------------------------------
 # after the measurement: what the tile-kernel variants and planner switches cost on this GPU (outside every timed region)
 # --------------------------------------------------------------------------------------------------
-def diagnostics(n, budget_s=120.0):
+def diagnostics(n, budget_s=90.0):
     """tools/bench_diagnostics.py in a child process (each configuration in a grandchild of its own): a faulting
     experimental kernel can neither disturb the numbers above, which are final by now, nor keep the line from printing."""
     try:
         p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "bench_diagnostics.py"), str(n), str(budget_s)],
-                           cwd=ROOT, capture_output=True, text=True, timeout=budget_s + 60.0)
+                           cwd=ROOT, capture_output=True, text=True, timeout=budget_s + 40.0)
         last = [ln for ln in p.stdout.splitlines() if ln.startswith("{")]
         return json.loads(last[-1]) if last else {"error": (p.stderr.strip().splitlines() or [f"exit {p.returncode}"])[-1][:200]}
     except Exception as e:

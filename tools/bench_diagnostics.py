@@ -1,7 +1,7 @@
 """Hardware diagnostics appended to the bench line (bench.py, N = 1): what the tile-pass variants and the planner switches
 cost on THIS GPU, so that every bench run also answers "which kernel should be the default".
 
-    python tools/bench_diagnostics.py [n=30] [budget_s=100]       # prints ONE JSON object on the last stdout line
+    python tools/bench_diagnostics.py [n=30] [budget_s=90]       # prints ONE JSON object on the last stdout line
 
 Every configuration runs in its own process (an experimental kernel that faults cannot take the others or the caller
 down) under its own timeout:
@@ -85,7 +85,7 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == "--one":
         return one(int(sys.argv[2]), int(sys.argv[3]))
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 30
-    budget = float(sys.argv[2]) if len(sys.argv) > 2 else 120.0
+    budget = float(sys.argv[2]) if len(sys.argv) > 2 else 90.0
     t_end = time.time() + budget
     out = {"n": n, "unit": "ms", "note": "best of 3, CUDA events on the library stream; one process per configuration", "rows": []}
     for label, force, env in CONFIGS:
@@ -99,7 +99,7 @@ def main():
         e.update(env)
         try:
             p = subprocess.run([sys.executable, os.path.abspath(__file__), "--one", str(n), str(force)], env=e, cwd=ROOT,
-                               capture_output=True, text=True, timeout=min(45.0, left))
+                               capture_output=True, text=True, timeout=min(30.0, left))
             rows = [ln[5:] for ln in p.stdout.splitlines() if ln.startswith("DIAG ")]
             if rows:
                 row = json.loads(rows[-1])
