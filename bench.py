@@ -397,6 +397,47 @@ def run_ours(args):
                           "peak_GBps_per_direction": nv_peak, "roofline_s_per_step": hbm_s + nv_s,
                           "roofline_hbm_s": hbm_s, "roofline_nvlink_s": nv_s,
                           "frac_of_roofline": (hbm_s + nv_s) / (ms / args.steps / 1e3)}
+    wd = None
+    if world > 1 and not args.no_diagnostics:
+        # The two experimental shard schedulers, one warm-up and one timed step each, AFTER every number above is final.
+        # They have never run on hardware: a watchdog (armed until the line has been printed) prints the line as it stands
+        # and ends the process if anything hangs; every rank has one, so torchrun still sees exit code 0.
+        sched_diag = {"note": "gates/s of one step after one warm-up step; outside every timed region", "default": value}
+        line["scheduler_diagnostics"] = sched_diag
+
+        def bail():
+            if rank == 0:
+                sched_diag.setdefault("error", "watchdog: the process did not finish after the last entry above")
+                print(json.dumps(line), flush=True)
+            os._exit(0)
+        wd = threading.Timer(150.0, bail)
+        wd.daemon = True
+        wd.start()
+        for label, var in (("reorder", "QB_SHARD_REORDER"), ("remote", "QB_SHARD_REMOTE")):
+            os.environ[var] = "1"        # read by the library at every flush (getenv)
+            try:
+                sw0, sb0, rp0, p0 = (reg.stat(_ffi.QB_STAT_SWAPS), reg.stat(_ffi.QB_STAT_SWAP_BYTES),
+                                     reg.stat(_ffi.QB_STAT_REMOTE_PASSES), reg.stat(_ffi.QB_STAT_PASSES))
+                reg.apply_batch(ops)
+                reg.sync()
+                barrier()
+                reg.timer_start()
+                reg.apply_batch(ops)
+                ms_x = maxr(reg.timer_stop())
+                sched_diag[label] = {"gates_per_s": n_gates / (ms_x / 1e3), "ms_per_step": ms_x,
+                                     "passes_2_steps": reg.stat(_ffi.QB_STAT_PASSES) - p0,
+                                     "exchanges_2_steps": reg.stat(_ffi.QB_STAT_SWAPS) - sw0,
+                                     "remote_passes_2_steps": reg.stat(_ffi.QB_STAT_REMOTE_PASSES) - rp0,
+                                     "nvlink_bytes_sent_2_steps": reg.stat(_ffi.QB_STAT_SWAP_BYTES) - sb0,
+                                     "norm2": reg.norm2()}
+            except Exception as e:
+                # an engine error on this rank (its peers may be waiting in a collective: their watchdogs end them)
+                sched_diag[label] = {"error": repr(e)[:200]}
+                if rank == 0:
+                    print(json.dumps(line), flush=True)
+                os._exit(0)
+            finally:
+                os.environ.pop(var, None)
     reg.close()    # frees the state (137 GB) before the diagnostics processes allocate theirs
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
@@ -407,6 +448,8 @@ def run_ours(args):
         if world == 1 and not args.no_diagnostics:
             line["diagnostics"] = diagnostics(min(30, n))
         print(json.dumps(line), flush=True)
+    if wd is not None:
+        wd.cancel()
     if world > 1:
         dist.destroy_process_group()
 
