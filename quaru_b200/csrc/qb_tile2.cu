@@ -56,7 +56,11 @@ static bool is_x(const Gate& g) {
 // tries all three and keeps the shortest program.
 template <class Prog>
 static bool encode_rounds_with(const std::vector<Gate>& gates, const std::vector<size_t>& gate_idx, const std::vector<uint32_t>& tile_pos,
-                               uint32_t lc, Prog* prog, int mode, bool allow_rtab) {
+                               uint32_t lc, Prog* prog, int mode, int extras) {
+    // extras: 0 = the ops of the default kernel only; 4..7 = the experimental ops of the persistent kernels as well: RC_RTAB, and
+    // merged phase tables over up to `extras` selector bits (RC_TABW above 4)
+    const bool allow_rtab = extras != 0;
+    const size_t max_sel = extras > 4 ? (size_t)extras : 4;
     const uint32_t T = (uint32_t)tile_pos.size();
     if (T != RT) return false;
     int8_t local_of[64];
@@ -362,7 +366,7 @@ static bool encode_rounds_with(const std::vector<Gate>& gates, const std::vector
                     dsel = (int)f->sel.size();
                     f->sel.push_back(o.src[0]);
                 }
-                if (f->sel.size() > 4) return false;
+                if (f->sel.size() > 4) return false;   // a single phase never has more (k <= 3 targets + a split-off bit)
                 const size_t nctl = ctl.size();
                 f->tab.assign(1u << f->sel.size(), make_double2(1.0, 0.0));
                 for (uint32_t x = 0; x < f->tab.size(); ++x) {
@@ -375,7 +379,7 @@ static bool encode_rounds_with(const std::vector<Gate>& gates, const std::vector
                 for (PhaseFn& t : *tabs) {
                     std::vector<uint8_t> uni = t.sel;
                     for (uint8_t sb : f.sel) if (std::find(uni.begin(), uni.end(), sb) == uni.end()) uni.push_back(sb);
-                    if (uni.size() > 4) continue;
+                    if (uni.size() > max_sel) continue;
                     std::vector<c64> nt(1u << uni.size());
                     auto sub = [&](const PhaseFn& g, uint32_t x) {
                         uint32_t ix = 0;
@@ -401,9 +405,16 @@ static bool encode_rounds_with(const std::vector<Gate>& gates, const std::vector
                     if (n_mats + t.tab.size() > max_mats) { overflow = true; return; }
                     ROp o;
                     memset(&o, 0, sizeof(o));
-                    o.code = code;
+                    const bool wide = t.sel.size() > 4;
+                    o.code = wide ? (code == RC_TAB ? RC_TABW : RC_TABW_ACC) : code;
                     o.k = (uint8_t)t.sel.size();
-                    for (size_t i = 0; i < t.sel.size(); ++i) { if (i < 3) o.src[i] = t.sel[i]; else o.b = t.sel[i]; }
+                    for (size_t i = 0; i < t.sel.size(); ++i) {
+                        if (i < 3) o.src[i] = t.sel[i];
+                        else if (i == 3) o.b = t.sel[i];
+                        else if (i == 4) o.tmask |= t.sel[i];
+                        else if (i == 5) o.tmask |= (uint16_t)(t.sel[i] << 8);
+                        else o.a = t.sel[i];
+                    }
                     o.mat = (uint32_t)n_mats;
                     memcpy(prog->mats + n_mats, t.tab.data(), t.tab.size() * sizeof(c64));
                     n_mats += t.tab.size();
@@ -667,7 +678,7 @@ static bool encode_rounds_with(const std::vector<Gate>& gates, const std::vector
         bool absorbed = false;   // ... by a per-thread table that round already has (its entries are scaled), ...
         for (uint32_t oi = last.op_begin; oi < last.op_end && !absorbed; ++oi) {
             const ROp& t = prog->ops[oi];
-            if (t.code != RC_TAB) continue;
+            if (t.code != RC_TAB && t.code != RC_TABW) continue;
             for (uint32_t e = 0; e < (1u << t.k); ++e) {
                 c64& v = prog->mats[t.mat + e];
                 v = make_double2(v.x * pass_scalar.x - v.y * pass_scalar.y, v.x * pass_scalar.y + v.y * pass_scalar.x);
@@ -715,15 +726,22 @@ static bool encode_rounds(const std::vector<Gate>& gates, const std::vector<size
                           uint32_t lc, Prog* prog, bool thorough, bool allow_rtab) {
     static thread_local Prog other;
     auto n_ops = [](const Prog& p) { return p.rounds[p.n_rounds - 1].op_end; };
-    bool have = encode_rounds_with(gates, gate_idx, tile_pos, lc, prog, 0, allow_rtab);
-    for (int mode = 1; thorough && mode <= 2; ++mode) {
-        if (!encode_rounds_with(gates, gate_idx, tile_pos, lc, &other, mode, allow_rtab)) continue;
-        if (!have || other.n_rounds < prog->n_rounds || (other.n_rounds == prog->n_rounds && n_ops(other) < n_ops(*prog))) {
-            *prog = other;
-            have = true;
+    // The experimental ops trade coefficient space for op count (a table over 7 selector bits has 128 entries): take the widest
+    // tables that still fit the pass, down to the default kernel's op set.
+    static const int kLevels[5] = {7, 6, 5, 4, 0};
+    for (int li = allow_rtab ? 0 : 4; li < 5; ++li) {
+        const int extras = kLevels[li];
+        bool have = encode_rounds_with(gates, gate_idx, tile_pos, lc, prog, 0, extras);
+        for (int mode = 1; thorough && mode <= 2; ++mode) {
+            if (!encode_rounds_with(gates, gate_idx, tile_pos, lc, &other, mode, extras)) continue;
+            if (!have || other.n_rounds < prog->n_rounds || (other.n_rounds == prog->n_rounds && n_ops(other) < n_ops(*prog))) {
+                *prog = other;
+                have = true;
+            }
         }
+        if (have) return true;
     }
-    return have;
+    return false;
 }
 
 template <class Prog>
@@ -826,7 +844,7 @@ int64_t encode_rounds_debug(uint32_t n_local, const std::vector<Gate>& gates, co
         uint32_t len = 4;
         if (o.code == RC_D2) len = 16;
         else if (o.code == RC_DG) len = 1u << o.k;
-        else if (o.code == RC_TAB || o.code == RC_TAB_ACC) len = 1u << o.k;
+        else if (o.code == RC_TAB || o.code == RC_TAB_ACC || o.code == RC_TABW || o.code == RC_TABW_ACC) len = 1u << o.k;
         else if (o.code == RC_LAYER) len = 8;
         else if (o.code == RC_RTAB) len = 16;
         n_mats = std::max(n_mats, o.mat + len);

@@ -19,8 +19,10 @@ enum RCode : uint8_t {
     RC_PH_FLUSH = 48,                              // + register bit: ... and apply the product to the 8 registers with that bit set
     RC_TAB = 52, RC_TAB_ACC = 53,                  // merged thread-uniform phases: table over <= 4 thread / outer bits -> tph
     RC_LAYER = 54,                                 // up to four real 2x2 gates, one per register bit, decoded once
-    RC_RTAB = 55                                   // experimental (persistent kernels only): unconditional diagonal over the register
+    RC_RTAB = 55,                                  // experimental (persistent kernels only): unconditional diagonal over the register
                                                    // bits, register j is multiplied by the j-th of 16 coefficients
+    RC_TABW = 56, RC_TABW_ACC = 57                 // experimental (persistent kernels only): RC_TAB / RC_TAB_ACC with 5..7 selector bits
+                                                   // (selectors 4, 5 in tmask's bytes, selector 6 in `a`): one op where two were needed
 };
 
 struct ROp {
@@ -350,6 +352,17 @@ __global__ void __launch_bounds__(RTHREADS, 2) k2r_tile_pass_persist(c64* __rest
     case RC_RTAB: {                                                                       \
         const c64* T = QB_MATS + op.mat;                                                  \
         _Pragma("unroll") for (int j = 0; j < 16; ++j) ip_cmul(v[j], T[j]);               \
+    } break;                                                                              \
+    case RC_TABW:                                                                         \
+    case RC_TABW_ACC: {                                                                   \
+        const uint32_t wsel[7] = {op.src[0], op.src[1], op.src[2], op.b, op.tmask & 0xffu, (uint32_t)op.tmask >> 8, op.a}; \
+        uint32_t widx = 0;                                                                \
+        _Pragma("unroll") for (int i = 0; i < 7; ++i) {                                   \
+            if (i >= op.k) break;                                                         \
+            const uint32_t sc = wsel[i];                                                  \
+            widx |= (((sc & 0x80) ? (QB_TILE_IX >> (sc & 0x3f)) : (tl >> (sc & 0x3f))) & 1u) << i; \
+        }                                                                                 \
+        ip_cmul(tph, QB_MATS[op.mat + widx]);                                             \
     } break;
 #include "qb_tile2_body.inc"
 #undef QB_TILE_IX
