@@ -413,7 +413,7 @@ static bool encode_rounds_with(const std::vector<Gate>& gates, const std::vector
                         else if (i == 3) o.b = t.sel[i];
                         else if (i == 4) o.tmask |= t.sel[i];
                         else if (i == 5) o.tmask |= (uint16_t)(t.sel[i] << 8);
-                        else o.a = t.sel[i];
+                        else o.rmask = t.sel[i];
                     }
                     o.mat = (uint32_t)n_mats;
                     memcpy(prog->mats + n_mats, t.tab.data(), t.tab.size() * sizeof(c64));
@@ -802,7 +802,7 @@ static int launch_rpass_remote(Reg* r, const Prog& prog, uint32_t n_virtual, c64
 template <class Prog, bool STAGE_OPS, bool PREFETCH, bool AHEAD>
 static int launch_rpass_persist(Reg* r, const Prog& prog) {
     const uint32_t n_ops = prog.rounds[prog.n_rounds - 1].op_end;
-    const size_t smem = (sizeof(c64) << RT) + (size_t)prog.n_mats * sizeof(c64) + (STAGE_OPS ? (size_t)n_ops * sizeof(ROp) : 0);
+    const size_t smem = (sizeof(c64) << RT) + (size_t)prog.n_mats * sizeof(c64) + (STAGE_OPS ? (size_t)n_ops * sizeof(SOp) : 0);
     static std::atomic<uint64_t> attr_devs{0};
     if (!((attr_devs.load() >> (r->device & 63)) & 1)) {
         QB_CUDA(cudaFuncSetAttribute(k2r_tile_pass_persist<Prog, STAGE_OPS, PREFETCH, AHEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize,

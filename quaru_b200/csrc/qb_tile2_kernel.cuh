@@ -22,7 +22,7 @@ enum RCode : uint8_t {
     RC_RTAB = 55,                                  // experimental (persistent kernels only): unconditional diagonal over the register
                                                    // bits, register j is multiplied by the j-th of 16 coefficients
     RC_TABW = 56, RC_TABW_ACC = 57                 // experimental (persistent kernels only): RC_TAB / RC_TAB_ACC with 5..7 selector bits
-                                                   // (selectors 4, 5 in tmask's bytes, selector 6 in `a`): one op where two were needed
+                                                   // (selectors 4, 5 in tmask's bytes, selector 6 in rmask): one op where two were needed
 };
 
 struct ROp {
@@ -275,6 +275,31 @@ __device__ __forceinline__ void r_d2_dispatch(c64 (&v)[16], const c64* M, uint32
     }
 }
 
+// Compact op record of the persistent kernels: the 24-byte ROp packed into one 128-bit word (one LDS.128 / four registers to
+// carry a record one op ahead), decoded with shifts and masks at the point of use.  Byte fields copied as a struct made ptxas
+// spill them one by one (ten STL.S16 / LDL.S16 / PRMT triples per op in the first version of the one-op-ahead kernels).
+struct __align__(16) SOp {
+    uint32_t x0;   // code | k << 8 | mat << 16 (12 bits) | a << 28
+    uint32_t x1;   // tmask | rmask << 16
+    uint32_t x2;   // src[0] | src[1] << 8 | src[2] << 16 | b << 24
+    uint32_t x3;   // omask (tile indices have fewer than 32 bits)
+};
+__device__ __forceinline__ SOp sop_pack(const ROp& o) {
+    SOp s;
+    s.x0 = (uint32_t)o.code | ((uint32_t)o.k << 8) | ((o.mat & 0xfffu) << 16) | (((uint32_t)o.a & 0xfu) << 28);
+    s.x1 = (uint32_t)o.tmask | ((uint32_t)o.rmask << 16);
+    s.x2 = (uint32_t)o.src[0] | ((uint32_t)o.src[1] << 8) | ((uint32_t)o.src[2] << 16) | ((uint32_t)o.b << 24);
+    s.x3 = (uint32_t)o.omask;
+    return s;
+}
+struct SOpView {   // the field names of ROp, as values
+    uint32_t code, k, mat, a, b, tmask, rmask, src[3];
+    uint64_t omask;
+    __device__ __forceinline__ explicit SOpView(const SOp& s)
+        : code(s.x0 & 0xffu), k((s.x0 >> 8) & 0xffu), mat((s.x0 >> 16) & 0xfffu), a(s.x0 >> 28), b(s.x2 >> 24), tmask(s.x1 & 0xffffu),
+          rmask(s.x1 >> 16), src{s.x2 & 0xffu, (s.x2 >> 8) & 0xffu, (s.x2 >> 16) & 0xffu}, omask(s.x3) {}
+};
+
 #ifdef QB_HOST_EMU
 #define QB_DYNAMIC_SMEM(name) unsigned char* name = qb_emu_shared()
 #else
@@ -312,32 +337,31 @@ __global__ void __launch_bounds__(RTHREADS, 2) k2r_tile_pass(c64* __restrict__ s
 // one op before its use.
 // Within a tile the transpose buffer is last read before a __syncthreads() (second barrier of a transpose), so the next
 // tile's first transpose store needs no extra barrier.
+// Op records reach the op loop as compact 128-bit words (SOp): from shared memory (STAGE_OPS) or packed on the fly from the
+// kernel-parameter bank.
 template <class Prog, bool STAGE_OPS, bool PREFETCH, bool AHEAD>
 __global__ void __launch_bounds__(RTHREADS, 2) k2r_tile_pass_persist(c64* __restrict__ st, const __grid_constant__ Prog prog, uint32_t n_tiles,
                                                                      uint32_t n_mats, uint32_t n_ops) {
     QB_DYNAMIC_SMEM(smem_raw);
     c64* tile = reinterpret_cast<c64*>(smem_raw);
     c64* s_mats = tile + (1u << RT);
-    ROp* s_ops = reinterpret_cast<ROp*>(s_mats + n_mats);   // 16-byte aligned; an ROp is three 8-byte words
+    SOp* s_ops = reinterpret_cast<SOp*>(s_mats + n_mats);   // 16-byte aligned
     for (uint32_t i = threadIdx.x; i < n_mats; i += RTHREADS) s_mats[i] = prog.mats[i];
-    if (STAGE_OPS) {
-        const uint64_t* src = reinterpret_cast<const uint64_t*>(prog.ops);
-        uint64_t* dst = reinterpret_cast<uint64_t*>(s_ops);
-        for (uint32_t i = threadIdx.x; i < 3u * n_ops; i += RTHREADS) dst[i] = src[i];
-    }
+    if (STAGE_OPS)
+        for (uint32_t i = threadIdx.x; i < n_ops; i += RTHREADS) s_ops[i] = sop_pack(prog.ops[i]);
     __syncthreads();
     for (uint32_t tile_ix = blockIdx.x; tile_ix < n_tiles; tile_ix += gridDim.x) {
 #define QB_TILE_IX tile_ix
 #define QB_AMP(off) (st + (off))
 #define QB_MATS s_mats
-#define QB_OPS (STAGE_OPS ? s_ops : prog.ops)
+#define QB_OPS(i) (STAGE_OPS ? s_ops[i] : sop_pack(prog.ops[i]))
     /* AHEAD: the record of op oi+1 is requested before op oi is executed, so the decode chain of the next op (record ->   \
        compare / branch -> coefficients) starts from registers instead of from a load */                                    \
-#define QB_BEFORE_OPS ROp op_next; if (AHEAD && rd.op_begin < rd.op_end) op_next = QB_OPS[rd.op_begin];
+#define QB_BEFORE_OPS SOp w_next = {0u, 0u, 0u, 0u}; if (AHEAD && rd.op_begin < rd.op_end) w_next = QB_OPS(rd.op_begin);
 #define QB_FETCH_OP                                                        \
-    ROp op_cur;                                                            \
-    if (AHEAD) { op_cur = op_next; if (oi + 1 < rd.op_end) op_next = QB_OPS[oi + 1]; } \
-    const ROp& op = AHEAD ? op_cur : QB_OPS[oi];
+    SOp w_cur;                                                             \
+    if (AHEAD) { w_cur = w_next; if (oi + 1 < rd.op_end) w_next = QB_OPS(oi + 1); } else { w_cur = QB_OPS(oi); } \
+    const SOpView op(w_cur);
 #define QB_AFTER_FIRST_LOADS                                                                         \
     if (PREFETCH) {                                                                                  \
         const uint32_t next_ix = tile_ix + gridDim.x;                                                \
@@ -355,7 +379,7 @@ __global__ void __launch_bounds__(RTHREADS, 2) k2r_tile_pass_persist(c64* __rest
     } break;                                                                              \
     case RC_TABW:                                                                         \
     case RC_TABW_ACC: {                                                                   \
-        const uint32_t wsel[7] = {op.src[0], op.src[1], op.src[2], op.b, op.tmask & 0xffu, (uint32_t)op.tmask >> 8, op.a}; \
+        const uint32_t wsel[7] = {op.src[0], op.src[1], op.src[2], op.b, op.tmask & 0xffu, (uint32_t)op.tmask >> 8, op.rmask & 0xffu}; \
         uint32_t widx = 0;                                                                \
         _Pragma("unroll") for (int i = 0; i < 7; ++i) {                                   \
             if (i >= op.k) break;                                                         \

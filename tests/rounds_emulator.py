@@ -186,8 +186,8 @@ def emulate_program(state, n, tile_pos, prog):
                     idx |= sel_bit(sels[i]) << i
                 tph = mats[mat + idx] * tph
             elif code in (RC_TABW, RC_TABW_ACC):                       # experimental: tables over 5..7 selector bits
-                assert rmask == 0 and op["omask"] == 0 and 4 < op["k"] <= 7
-                sels = op["src"] + [op["b"], tmask & 0xff, tmask >> 8, op["a"]]
+                assert op["omask"] == 0 and 4 < op["k"] <= 7
+                sels = op["src"] + [op["b"], tmask & 0xff, tmask >> 8, rmask & 0xff]
                 idx = np.zeros(N, dtype=np.int64)
                 for i in range(op["k"]):
                     idx |= sel_bit(sels[i]) << i
