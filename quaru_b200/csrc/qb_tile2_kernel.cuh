@@ -292,6 +292,13 @@ __device__ __forceinline__ SOp sop_pack(const ROp& o) {
     s.x3 = (uint32_t)o.omask;
     return s;
 }
+// an opaque copy: what is derived from it cannot be merged with (and hoisted next to) what is derived from the original
+__device__ __forceinline__ SOp sop_launder(SOp s) {
+#ifndef QB_HOST_EMU
+    asm volatile("" : "+r"(s.x0), "+r"(s.x1), "+r"(s.x2), "+r"(s.x3));
+#endif
+    return s;
+}
 struct SOpView {   // the field names of ROp, as values
     uint32_t code, k, mat, a, b, tmask, rmask, src[3];
     uint64_t omask;
@@ -319,7 +326,9 @@ __global__ void __launch_bounds__(RTHREADS, 2) k2r_tile_pass(c64* __restrict__ s
 #define QB_FETCH_OP const ROp& op = prog.ops[oi];
 #define QB_AFTER_FIRST_LOADS
 #define QB_EXTRA_CASES
+#define QB_CASE_OP
 #include "qb_tile2_body.inc"
+#undef QB_CASE_OP
 #undef QB_TILE_IX
 #undef QB_AMP
 #undef QB_MATS
@@ -362,6 +371,7 @@ __global__ void __launch_bounds__(RTHREADS, 2) k2r_tile_pass_persist(c64* __rest
     SOp w_cur;                                                             \
     if (AHEAD) { w_cur = w_next; if (oi + 1 < rd.op_end) w_next = QB_OPS(oi + 1); } else { w_cur = QB_OPS(oi); } \
     const SOpView op(w_cur);
+#define QB_CASE_OP const SOpView op(sop_launder(w_cur));
 #define QB_AFTER_FIRST_LOADS                                                                         \
     if (PREFETCH) {                                                                                  \
         const uint32_t next_ix = tile_ix + gridDim.x;                                                \
@@ -379,6 +389,7 @@ __global__ void __launch_bounds__(RTHREADS, 2) k2r_tile_pass_persist(c64* __rest
     } break;                                                                              \
     case RC_TABW:                                                                         \
     case RC_TABW_ACC: {                                                                   \
+        QB_CASE_OP                                                                        \
         const uint32_t wsel[7] = {op.src[0], op.src[1], op.src[2], op.b, op.tmask & 0xffu, (uint32_t)op.tmask >> 8, op.rmask & 0xffu}; \
         uint32_t widx = 0;                                                                \
         _Pragma("unroll") for (int i = 0; i < 7; ++i) {                                   \
@@ -393,6 +404,7 @@ __global__ void __launch_bounds__(RTHREADS, 2) k2r_tile_pass_persist(c64* __rest
 #undef QB_AMP
 #undef QB_MATS
 #undef QB_OPS
+#undef QB_CASE_OP
 #undef QB_BEFORE_OPS
 #undef QB_FETCH_OP
 #undef QB_AFTER_FIRST_LOADS
@@ -450,7 +462,9 @@ __global__ void __launch_bounds__(RTHREADS, 2) k2r_tile_pass_remote(const __grid
 #define QB_FETCH_OP const ROp& op = prog.ops[oi];
 #define QB_AFTER_FIRST_LOADS
 #define QB_EXTRA_CASES
+#define QB_CASE_OP
 #include "qb_tile2_body.inc"
+#undef QB_CASE_OP
 #undef QB_TILE_IX
 #undef QB_AMP
 #undef QB_MATS
