@@ -241,6 +241,14 @@ int64_t qb_shard_plan_debug(uint32_t n, int32_t world, int32_t rank, const qb_ga
 
 const char* qb_version(void);
 
+/* Dry run of the SWAP relabelling (registers of >= 28 local qubits, or QB_SWAP_RELABEL=1): a SWAP gate
+ * (src/operation.rs:427) only exchanges the names of two qubits inside the engine; later gates and measurements are
+ * translated, raw state access first undoes the permutation with real SWAP passes.  Output, one record per gate:
+ * [-2] exact identity (dropped), [-1] SWAP absorbed, or [k, engine qubit of targets[0], ..., of targets[k-1]]; then
+ * [-3, m, a_0, b_0, ..., a_{m-1}, b_{m-1}]: the engine-qubit pairs that are swapped, in order, before a raw read.
+ * Returns the number of int32 written or a negative error (tests/test_relabel.py replays it against the oracle). */
+int64_t qb_relabel_debug(uint32_t n, const qb_gate* gates, uint64_t count, int32_t* out, uint64_t capacity);
+
 #ifdef __cplusplus
 }
 #endif

@@ -95,6 +95,7 @@ SIGNATURES = {
                                          ctypes.c_uint64]),
     "qb_shard_plan_debug": (ctypes.c_int64, [ctypes.c_uint32, ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(QbGate),
                                              ctypes.c_uint64, _i32p, ctypes.c_uint64, _u32p]),
+    "qb_relabel_debug": (ctypes.c_int64, [ctypes.c_uint32, ctypes.POINTER(QbGate), ctypes.c_uint64, _i32p, ctypes.c_uint64]),
     "qb_plan_debug": (ctypes.c_int64, [ctypes.c_uint32, ctypes.POINTER(QbGate), ctypes.c_uint64, ctypes.c_uint32,
                                        _i32p, _i32p]),
 }

@@ -49,6 +49,11 @@ static int alloc_common(Reg* r) {
     }
     r->phys_of.resize(r->n);
     for (uint32_t q = 0; q < r->n; ++q) r->phys_of[q] = q;
+    r->label.resize(r->n);
+    for (uint32_t q = 0; q < r->n; ++q) r->label[q] = q;
+    // SWAP gates as relabelling: for registers whose sweeps are expensive (QB_SWAP_RELABEL=1 / 0 forces it on / off)
+    const char* rl = getenv("QB_SWAP_RELABEL");
+    r->relabel = rl ? rl[0] == '1' : r->n_local >= 28;
     return QB_OK;
 }
 
@@ -120,12 +125,46 @@ int run_local(Reg* r, std::vector<Gate>& gates) {
     return QB_OK;
 }
 
+// Common tail of every gate entry point: a plain SWAP only renames two qubits (when relabelling is on), everything else is
+// translated to engine qubits and queued.
+static int enqueue_gate(Reg* r, Gate&& g) {
+    if (r->relabel) {
+        if (is_plain_swap(g)) {
+            std::swap(r->label[g.targets[0]], r->label[g.targets[1]]);
+            return QB_OK;
+        }
+        relabel_gate(r->label, &g);
+    }
+    r->queue.push_back(std::move(g));
+    if (!r->fusion || r->queue.size() >= r->max_queue) return flush(r);
+    return QB_OK;
+}
+
 static int enqueue(Reg* r, const double* matrix, const uint32_t* targets, uint32_t k) {
     Gate g;
     r->st_gates++;
     if (!classify_gate(matrix, targets, k, &g)) return QB_OK;  // exact identity
-    r->queue.push_back(std::move(g));
-    if (!r->fusion || r->queue.size() >= r->max_queue) return flush(r);
+    return enqueue_gate(r, std::move(g));
+}
+
+static void reset_labels(Reg* r) {
+    for (uint32_t q = 0; q < r->n; ++q) r->label[q] = q;
+}
+
+// Before raw state access: pending gates launched, the caller's qubit q back in index bit q (real SWAP passes undo the
+// relabelling, then the sharded placement is restored).
+static int canonical(Reg* r) {
+    if (r->relabel) {
+        std::vector<uint32_t> pairs;
+        canonical_swaps(&r->label, &pairs);
+        for (size_t i = 0; i + 1 < pairs.size(); i += 2) {
+            Gate g;
+            make_swap_gate(pairs[i], pairs[i + 1], &g);
+            r->queue.push_back(std::move(g));
+        }
+    }
+    QB_TRY(flush(r));
+    if (r->world > 1) QB_TRY(shard_canonicalize(r));
     return QB_OK;
 }
 
@@ -218,6 +257,7 @@ int qb_clone(qb_reg* src_, qb_reg** out) try {
     if (rc != QB_OK) return rc;
     Reg* dst = REG(*out);
     dst->fusion = src->fusion; dst->tile_bits = src->tile_bits; dst->max_queue = src->max_queue; dst->force_path = src->force_path;
+    dst->relabel = src->relabel; dst->label = src->label;   // same amplitudes, same qubit names
     cudaError_t e = cudaMemcpyAsync(dst->state, src->state, sizeof(c64) << src->n_local, cudaMemcpyDeviceToDevice, src->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(src->stream);
     if (e != cudaSuccess) { free_reg(dst); *out = nullptr; return fail_cuda(e, "clone copy", __FILE__, __LINE__); }
@@ -232,6 +272,7 @@ int qb_reset(qb_reg* reg, uint64_t basis_index) try {
     if (basis_index >= (1ull << r->n)) return set_error(QB_ERR_INVALID_ARGUMENT, (int64_t)basis_index, "basis index out of range");
     r->queue.clear();
     shard_reset_placement(r);
+    reset_labels(r);
     const uint64_t owner = basis_index >> r->n_local;
     return k_init_basis(r, basis_index & ((1ull << r->n_local) - 1), owner == (uint64_t)r->rank);
 } QB_CATCH_ALL
@@ -262,9 +303,7 @@ int qb_apply_controlled(qb_reg* reg, const double* matrix, const uint32_t* targe
     r->st_gates++;
     if (!classify_gate(matrix, targets, k, &g)) return QB_OK;
     for (uint32_t i = 0; i < n_controls; ++i) g.ctrl_mask |= 1ull << controls[i];
-    r->queue.push_back(std::move(g));
-    if (!r->fusion || r->queue.size() >= r->max_queue) return flush(r);
-    return QB_OK;
+    return enqueue_gate(r, std::move(g));
 } QB_CATCH_ALL
 
 // Register::try_apply_all (register.rs:267-281) == the 2x2 gate on every qubit
@@ -296,8 +335,9 @@ int qb_probabilities(qb_reg* reg, uint32_t target, double* p0, double* p1) try {
     if (!p0 || !p1) return set_error(QB_ERR_INVALID_ARGUMENT, -1, "output pointer is NULL");
     if (target >= r->n) return set_error(QB_ERR_INVALID_TARGET, target, "InvalidTarget(%u): register has %u qubits", target, r->n);
     QB_TRY(flush(r));
-    if (r->world > 1) return shard_probabilities(r, target, p0, p1);
-    return k_probabilities(r, (int)target, p0, p1);
+    const uint32_t t = r->relabel ? r->label[target] : target;   // the engine qubit that holds the caller's qubit
+    if (r->world > 1) return shard_probabilities(r, t, p0, p1);
+    return k_probabilities(r, (int)t, p0, p1);
 } QB_CATCH_ALL
 
 // Register::try_measure (register.rs:297-342)
@@ -310,8 +350,9 @@ int qb_measure(qb_reg* reg, uint32_t target, double u, int32_t* outcome) try {
     const int res = u > p0;                    // :321 (strict)
     const double total = res ? p1 : p0;        // :323
     *outcome = res;
-    if (r->world > 1) return shard_collapse(r, target, res, total);
-    return k_collapse(r, target, res, total);
+    const uint32_t t = r->relabel ? r->label[target] : target;   // valid: qb_probabilities checked the range
+    if (r->world > 1) return shard_collapse(r, t, res, total);
+    return k_collapse(r, t, res, total);
 } QB_CATCH_ALL
 
 int qb_read_state(qb_reg* reg, uint64_t offset, uint64_t count, double* out) try {
@@ -320,8 +361,7 @@ int qb_read_state(qb_reg* reg, uint64_t offset, uint64_t count, double* out) try
     const uint64_t N = 1ull << r->n;
     if (offset > N || count > N - offset) return set_error(QB_ERR_INVALID_ARGUMENT, (int64_t)offset, "range exceeds the state");
     if (count && !out) return set_error(QB_ERR_INVALID_ARGUMENT, -1, "out is NULL");
-    QB_TRY(flush(r));
-    if (r->world > 1) QB_TRY(shard_canonicalize(r));
+    QB_TRY(canonical(r));
     const uint64_t lo = (uint64_t)r->rank << r->n_local, hi = lo + (1ull << r->n_local);
     const uint64_t a = std::max(offset, lo), b = std::min(offset + count, hi);
     if (a < b)
@@ -336,8 +376,7 @@ int qb_write_state(qb_reg* reg, uint64_t offset, uint64_t count, const double* i
     const uint64_t N = 1ull << r->n;
     if (offset > N || count > N - offset) return set_error(QB_ERR_INVALID_ARGUMENT, (int64_t)offset, "range exceeds the state");
     if (count && !in) return set_error(QB_ERR_INVALID_ARGUMENT, -1, "in is NULL");
-    QB_TRY(flush(r));
-    if (r->world > 1) QB_TRY(shard_canonicalize(r));
+    QB_TRY(canonical(r));
     const uint64_t lo = (uint64_t)r->rank << r->n_local, hi = lo + (1ull << r->n_local);
     const uint64_t a = std::max(offset, lo), b = std::min(offset + count, hi);
     if (a < b)
@@ -350,8 +389,7 @@ int qb_save_state(qb_reg* reg, const char* path) try {
     CHECK_REG(reg);
     Reg* r = REG(reg);
     if (!path) return set_error(QB_ERR_INVALID_ARGUMENT, -1, "path is NULL");
-    QB_TRY(flush(r));
-    if (r->world > 1) QB_TRY(shard_canonicalize(r));
+    QB_TRY(canonical(r));
     return state_save(r, path);
 } QB_CATCH_ALL
 
@@ -361,6 +399,7 @@ int qb_load_state(qb_reg* reg, const char* path) try {
     if (!path) return set_error(QB_ERR_INVALID_ARGUMENT, -1, "path is NULL");
     r->queue.clear();  // the loaded image replaces whatever the pending gates would have produced
     shard_reset_placement(r);  // files hold the identity placement
+    reset_labels(r);
     return state_load(r, path);
 } QB_CATCH_ALL
 
@@ -382,9 +421,8 @@ static int diff_impl(qb_reg* a_, qb_reg* b_, double* mx, double* l2) {
     Reg *a = REG(a_), *b = REG(b_);
     if (a->n != b->n || a->world != b->world || a->device != b->device)
         return set_error(QB_ERR_INVALID_ARGUMENT, -1, "registers differ in size, sharding or device");
-    QB_TRY(flush(a));
-    QB_TRY(flush(b));
-    if (a->world > 1) { QB_TRY(shard_canonicalize(a)); QB_TRY(shard_canonicalize(b)); }
+    QB_TRY(canonical(a));
+    QB_TRY(canonical(b));
     double m, l;
     QB_TRY(k_diff(a, b, &m, &l));
     if (a->world > 1) QB_TRY(shard_reduce_diff(a, &m, &l));
@@ -478,6 +516,44 @@ int qb_get_stat(qb_reg* reg, int32_t stat, int64_t* value) try {
         case QB_STAT_TILE_NS: QB_TRY(drain_tile_events(r)); *value = r->st_tile_ns; return QB_OK;
     }
     return set_error(QB_ERR_INVALID_ARGUMENT, stat, "unknown stat %d", stat);
+} QB_CATCH_ALL
+
+int64_t qb_relabel_debug(uint32_t n, const qb_gate* gates, uint64_t count, int32_t* out, uint64_t capacity) try {
+    if ((count && !gates) || !out) return set_error(QB_ERR_INVALID_ARGUMENT, -1, "NULL argument");
+    if (n == 0 || n > 40) return set_error(QB_ERR_INVALID_ARGUMENT, n, "1..40 qubits");
+    std::vector<uint32_t> label(n);
+    for (uint32_t q = 0; q < n; ++q) label[q] = q;
+    std::vector<int32_t> rec;
+    for (uint64_t i = 0; i < count; ++i) {
+        QB_TRY(validate_targets(n, gates[i].targets, gates[i].k));
+        Gate g;
+        if (!classify_gate(gates[i].matrix, gates[i].targets, gates[i].k, &g)) { rec.push_back(-2); continue; }
+        if (is_plain_swap(g)) {   // the same two steps as enqueue_gate
+            std::swap(label[g.targets[0]], label[g.targets[1]]);
+            rec.push_back(-1);
+            continue;
+        }
+        relabel_gate(label, &g);
+        // cross-check: classifying the gate on the translated qubits must give the same gate
+        std::vector<uint32_t> tt(gates[i].k);
+        for (uint32_t j = 0; j < gates[i].k; ++j) tt[j] = label[gates[i].targets[j]];
+        Gate c;
+        classify_gate(gates[i].matrix, tt.data(), gates[i].k, &c);
+        if (c.targets != g.targets || c.ctrl_mask != g.ctrl_mask || c.kind != g.kind || c.k != g.k)
+            return set_error(QB_ERR_UNSUPPORTED, (int64_t)i, "internal: relabelled gate %llu differs from the gate on the translated qubits", (unsigned long long)i);
+        rec.push_back((int32_t)gates[i].k);
+        for (uint32_t t : tt) rec.push_back((int32_t)t);
+    }
+    std::vector<uint32_t> pairs;
+    canonical_swaps(&label, &pairs);
+    for (uint32_t q = 0; q < n; ++q)
+        if (label[q] != q) return set_error(QB_ERR_UNSUPPORTED, q, "internal: canonical_swaps left qubit %u out of place", q);
+    rec.push_back(-3);
+    rec.push_back((int32_t)(pairs.size() / 2));
+    for (uint32_t p : pairs) rec.push_back((int32_t)p);
+    if (rec.size() > capacity) return set_error(QB_ERR_INVALID_ARGUMENT, (int64_t)rec.size(), "buffer too small");
+    for (size_t i = 0; i < rec.size(); ++i) out[i] = rec[i];
+    return (int64_t)rec.size();
 } QB_CATCH_ALL
 
 int64_t qb_plan_debug(uint32_t n, const qb_gate* gates, uint64_t count, uint32_t tile_bits, int32_t* pass_of_gate,

@@ -66,6 +66,17 @@ struct Gate {
 // Returns false if the gate is exactly the identity (nothing to do).
 bool classify_gate(const double* matrix, const uint32_t* targets, uint32_t k, Gate* out);
 
+// ---- SWAP gates as qubit relabelling (qb_gate.cu; pure host logic, checked on CPU through qb_relabel_debug) -------------
+// A SWAP of two qubits moves no amplitude if the engine simply exchanges the two qubits' names: `label[q]` is the engine
+// qubit that currently holds the caller's qubit q.  Later gates and measurements go through the map; raw state access first
+// restores the identity with real SWAP passes (canonical_swaps).  On the BASELINE circuit (QFT = 16 final SWAPs, each a dense
+// two-qubit gate whose two targets must both be tile bits) this removes 2 of 25 sweeps and the 16 heaviest ops of a step.
+bool is_plain_swap(const Gate& g);                                     // uncontrolled dense 2-qubit gate equal to SWAP, entry by entry
+void relabel_gate(const std::vector<uint32_t>& label, Gate* g);        // caller's qubits -> engine qubits (targets and controls)
+void canonical_swaps(std::vector<uint32_t>* label, std::vector<uint32_t>* pairs);  // engine qubit pairs (a0, b0, a1, b1, ...) to SWAP,
+                                                                                   // in order, to make the map the identity again
+void make_swap_gate(uint32_t a, uint32_t b, Gate* out);
+
 // ---- the handle ----------------------------------------------------------------------------------
 struct Shard;  // multi-GPU state (qb_shard.cu)
 
@@ -101,6 +112,9 @@ struct Reg {
     int rank = 0, world = 1;
     Shard* shard = nullptr;
     std::vector<uint32_t> phys_of;  // logical qubit -> physical bit position
+    // SWAP relabelling (above the placement): caller's qubit q is engine ("logical") qubit label[q]
+    bool relabel = false;
+    std::vector<uint32_t> label;
 };
 
 // ---- kernels' host launchers (qb_kernels.cu) -------------------------------------------------------

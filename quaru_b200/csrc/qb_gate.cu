@@ -125,4 +125,43 @@ bool classify_gate(const double* M, const uint32_t* targets, uint32_t k, Gate* o
     return true;
 }
 
+
+// ---- SWAP relabelling ---------------------------------------------------------------------------------------------------
+static const double kSwap[32] = {1, 0, 0, 0, 0, 0, 0, 0,  0, 0, 0, 0, 1, 0, 0, 0,  0, 0, 1, 0, 0, 0, 0, 0,  0, 0, 0, 0, 0, 0, 1, 0};
+
+bool is_plain_swap(const Gate& g) {
+    if (g.kind != GK_DENSE || g.k != 2 || g.ctrl_mask != 0 || g.targets.size() != 2 || g.matrix.size() != 16) return false;
+    for (int i = 0; i < 16; ++i)
+        if (g.matrix[i].x != kSwap[2 * i] || g.matrix[i].y != kSwap[2 * i + 1]) return false;
+    return true;
+}
+
+void relabel_gate(const std::vector<uint32_t>& label, Gate* g) {
+    for (uint32_t& t : g->targets) t = label[t];
+    uint64_t c = 0;
+    for (uint64_t m = g->ctrl_mask; m; m &= m - 1) c |= 1ull << label[__builtin_ctzll(m)];
+    g->ctrl_mask = c;
+}
+
+void canonical_swaps(std::vector<uint32_t>* label, std::vector<uint32_t>* pairs) {
+    std::vector<uint32_t>& L = *label;
+    const uint32_t n = (uint32_t)L.size();
+    std::vector<uint32_t> at(n);   // engine qubit -> caller's qubit held there
+    for (uint32_t q = 0; q < n; ++q) at[L[q]] = q;
+    for (uint32_t q = 0; q < n; ++q) {
+        if (L[q] == q) continue;
+        const uint32_t p = L[q];       // the caller's qubit q lives in engine qubit p: exchange the contents of p and q
+        const uint32_t other = at[q];  // the caller's qubit that lives in engine qubit q moves to p
+        pairs->push_back(q);
+        pairs->push_back(p);
+        L[q] = q; at[q] = q;
+        L[other] = p; at[p] = other;
+    }
+}
+
+void make_swap_gate(uint32_t a, uint32_t b, Gate* out) {
+    const uint32_t t[2] = {a, b};
+    classify_gate(kSwap, t, 2, out);
+}
+
 }  // namespace qb
