@@ -5,7 +5,8 @@ cost on THIS GPU, so that every bench run also answers "which kernel should be t
 
 Every configuration runs in its own process (an experimental kernel that faults cannot take the others or the caller
 down) under its own timeout:
-  * force_path 0 (default kernel) with the planner / encoder look-ahead on (default) and off (QB_PLAN_LOOKAHEAD=0);
+  * force_path 0 (default kernel) with the planner / encoder look-ahead on (default) and off (QB_PLAN_LOOKAHEAD=0), and with
+    SWAP gates executed instead of absorbed into the qubit names (QB_SWAP_RELABEL=0);
   * force_path 5..11: the persistent tile kernels of qb_tile2_kernel.cuh (coefficients / op records in shared memory,
     L2 prefetch of the next tile, op records fetched one op ahead), with and without the register-table op (QB_TILE_RTAB=1).
 Per configuration: the result at n = 24 is compared with the default kernel's (max |diff|, 0.0 = bit-identical), then the
@@ -25,6 +26,7 @@ sys.path.insert(0, ROOT)
 CONFIGS = [  # (label, force_path, extra environment); most informative first, the time budget may cut the tail
     ("default", 0, {}),
     ("default_no_lookahead", 0, {"QB_PLAN_LOOKAHEAD": "0"}),
+    ("default_no_swap_relabel", 0, {"QB_SWAP_RELABEL": "0"}),
     ("persist_mats_ops", 6, {}), ("persist_mats_ops_ahead", 10, {}), ("persist_mats_ops_pf_ahead", 11, {}),
     ("persist_mats_ops_pf", 8, {}), ("persist_mats", 5, {}), ("persist_mats_ahead", 9, {}), ("persist_mats_pf", 7, {}),
     ("persist_mats_ops_ahead_rtab", 10, {"QB_TILE_RTAB": "1"}), ("persist_mats_ops_rtab", 6, {"QB_TILE_RTAB": "1"}),
@@ -94,7 +96,7 @@ def main():
             out["rows"].append({"label": label, "skipped": "time budget"})
             continue
         e = dict(os.environ)
-        for k in ("QB_PLAN_LOOKAHEAD", "QB_TILE_RTAB", "QB_OPT_FORCE_PATH"):
+        for k in ("QB_PLAN_LOOKAHEAD", "QB_TILE_RTAB", "QB_OPT_FORCE_PATH", "QB_SWAP_RELABEL"):
             e.pop(k, None)
         e.update(env)
         try:
