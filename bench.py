@@ -210,7 +210,7 @@ def run_reference(args):
 # --------------------------------------------------------------------------------------------------
 # after the measurement: what the tile-kernel variants and planner switches cost on this GPU (outside every timed region)
 # --------------------------------------------------------------------------------------------------
-def diagnostics(n, budget_s=90.0):
+def diagnostics(n, budget_s=110.0):
     """tools/bench_diagnostics.py in a child process (each configuration in a grandchild of its own): a faulting
     experimental kernel can neither disturb the numbers above, which are final by now, nor keep the line from printing."""
     try:

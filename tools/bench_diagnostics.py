@@ -1,7 +1,7 @@
 """Hardware diagnostics appended to the bench line (bench.py, N = 1): what the tile-pass variants and the planner switches
 cost on THIS GPU, so that every bench run also answers "which kernel should be the default".
 
-    python tools/bench_diagnostics.py [n=30] [budget_s=90]       # prints ONE JSON object on the last stdout line
+    python tools/bench_diagnostics.py [n=30] [budget_s=110]       # prints ONE JSON object on the last stdout line
 
 Every configuration runs in its own process (an experimental kernel that faults cannot take the others or the caller
 down) under its own timeout:
@@ -27,9 +27,10 @@ CONFIGS = [  # (label, force_path, extra environment); most informative first, t
     ("default", 0, {}),
     ("default_no_lookahead", 0, {"QB_PLAN_LOOKAHEAD": "0"}),
     ("default_no_swap_relabel", 0, {"QB_SWAP_RELABEL": "0"}),
-    ("persist_mats_ops", 6, {}), ("persist_mats_ops_ahead", 10, {}), ("persist_mats_ops_pf_ahead", 11, {}),
-    ("persist_mats_ops_pf", 8, {}), ("persist_mats", 5, {}), ("persist_mats_ahead", 9, {}), ("persist_mats_pf", 7, {}),
-    ("persist_mats_ops_ahead_rtab", 10, {"QB_TILE_RTAB": "1"}), ("persist_mats_ops_rtab", 6, {"QB_TILE_RTAB": "1"}),
+    ("persist_mats_ops", 6, {}), ("persist_mats_ops_rtab", 6, {"QB_TILE_RTAB": "1"}),
+    ("persist_mats_ops_ahead", 10, {}), ("persist_mats_ops_pf", 8, {}), ("persist_mats_ops_pf_ahead", 11, {}),
+    ("persist_mats_ops_pf_ahead_rtab", 11, {"QB_TILE_RTAB": "1"}),
+    ("persist_mats", 5, {}), ("persist_mats_pf", 7, {}), ("persist_mats_ahead", 9, {}),
 ]
 
 
@@ -87,7 +88,7 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == "--one":
         return one(int(sys.argv[2]), int(sys.argv[3]))
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 30
-    budget = float(sys.argv[2]) if len(sys.argv) > 2 else 90.0
+    budget = float(sys.argv[2]) if len(sys.argv) > 2 else 110.0
     t_end = time.time() + budget
     out = {"n": n, "unit": "ms", "note": "best of 3, CUDA events on the library stream; one process per configuration", "rows": []}
     for label, force, env in CONFIGS:
