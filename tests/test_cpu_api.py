@@ -1,0 +1,108 @@
+"""The engine's C ABI host logic on a machine without a GPU.
+
+tests/cpu_api/ builds the engine's own host translation units (quaru_b200/csrc/qb_api.cu, qb_gate.cu, qb_qasm.cu) with g++
+against a stand-in for the CUDA runtime (device memory = host memory) and a host restatement of the kernel-launcher layer
+(host_backend.cpp).  Everything above the kernels is the product's code: argument validation and error payloads, the gate
+queue, SWAP relabelling and its canonicalisation before raw access, measurement plumbing, clone / reset / diff / state
+files, options and stats.  The Python mirror (quaru_b200.Register) is pointed at that library for the duration of a test.
+What the kernels compute is NOT covered here (tests/test_cpu_kernel.py, tests/test_rounds_emulator.py and the -m gpu
+tests do that)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from tests import reference_suite as rs
+from tests import test_gpu_relabel as relabel_cases
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HERE = os.path.join(ROOT, "tests", "cpu_api")
+OUT = os.path.join(HERE, "_build", "libquaru_hostapi.so")
+CSRC = os.path.join(ROOT, "quaru_b200", "csrc")
+SOURCES = [os.path.join(CSRC, f) for f in ("qb_api.cu", "qb_gate.cu", "qb_qasm.cu")] + [os.path.join(HERE, "host_backend.cpp")]
+
+
+@pytest.fixture(scope="module")
+def host_lib():
+    deps = SOURCES + [os.path.join(HERE, "fake", "cuda_runtime.h"), os.path.join(ROOT, "include", "quaru_b200.h")] + \
+        [os.path.join(CSRC, f) for f in ("qb_common.h", "qb_shard.h", "qb_tile.h")]
+    if not os.path.exists(OUT) or any(os.path.getmtime(d) > os.path.getmtime(OUT) for d in deps):
+        os.makedirs(os.path.dirname(OUT), exist_ok=True)
+        subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O1", "-shared", "-fPIC", "-I", os.path.join(HERE, "fake"), "-I", CSRC,
+                               "-x", "c++"] + SOURCES + ["-o", OUT])
+    return OUT
+
+
+@pytest.fixture()
+def engine(host_lib, monkeypatch):
+    """quaru_b200 with its loader pointed at the host build (restored afterwards: other tests use the real library)."""
+    import quaru_b200
+    from quaru_b200 import _ffi
+    monkeypatch.setattr(_ffi, "LIB_PATH", host_lib)
+    monkeypatch.setattr(_ffi, "_lib", None)
+    return quaru_b200
+
+
+@pytest.fixture()
+def relabel(monkeypatch):
+    monkeypatch.setenv("QB_SWAP_RELABEL", "1")
+
+
+@pytest.mark.parametrize("relabel_env", ["1", "0"])
+@pytest.mark.parametrize("fusion", [1, 0])
+@pytest.mark.parametrize("test", rs.ALL, ids=lambda t: t.__name__)
+def test_reference_suite_through_the_api_layer(engine, monkeypatch, test, fusion, relabel_env):
+    """Quaru's own tests (ported in tests/reference_suite.py) through the real C ABI entry points, with SWAP relabelling
+    forced on and off."""
+    monkeypatch.setenv("QB_SWAP_RELABEL", relabel_env)
+    test(rs.EngineBackend(engine, fusion), np.random.default_rng(12345))
+
+
+@pytest.mark.parametrize("n,kind,fusion", [(8, "qft", 1), (10, "swaps", 1), (9, "bench", 1), (9, "swaps", 0)])
+def test_relabelled_state_and_outcomes(engine, relabel, n, kind, fusion):
+    relabel_cases.test_state_and_outcomes_match_the_oracle(engine, relabel, n, kind, fusion)
+
+
+def test_relabelled_swaps_cost_no_sweep(engine, relabel):
+    relabel_cases.test_swaps_cost_no_sweep(engine, relabel)
+
+
+def test_relabelled_clone_diff_reset_write_and_files(engine, relabel, tmp_path):
+    relabel_cases.test_clone_diff_reset_write_and_files_see_callers_qubits(engine, relabel, tmp_path)
+
+
+def test_relabelling_is_off_for_small_registers_by_default(engine, monkeypatch):
+    from oracle import gates as og
+    monkeypatch.delenv("QB_SWAP_RELABEL", raising=False)
+    reg = engine.Register.new([False] * 6)
+    reg.apply(engine.Operation(*og.hadamard(1)))
+    reg.flush()
+    before = reg.stat(2)
+    reg.apply(engine.Operation(*og.swap(1, 4)))
+    reg.flush()
+    assert reg.stat(2) == before + 1, "below 28 local qubits a SWAP is an ordinary gate"
+    p = reg.probabilities(4)
+    assert abs(p[0] - 0.5) < 1e-12
+    reg.close()
+
+
+def test_error_payloads_and_options(engine):
+    from quaru_b200 import _ffi
+    from quaru_b200.register import OperationError
+    from oracle import gates as og
+    reg = engine.Register.new([False] * 3)
+    with pytest.raises(OperationError) as e:
+        reg.try_apply_fast(engine.Operation(og.hadamard(0)[0], [3]))
+    assert e.value == OperationError("InvalidTarget", 3)
+    with pytest.raises(OperationError) as e:
+        reg.try_apply_fast(engine.Operation(og.cnot(0, 1)[0], [1, 1]))
+    assert e.value == OperationError("InvalidTarget", 1)
+    with pytest.raises(OperationError):
+        reg.try_measure(7, u=0.5)
+    with pytest.raises(Exception):
+        reg.set_option(_ffi.QB_OPT_FORCE_PATH, 12)
+    reg.set_option(_ffi.QB_OPT_FORCE_PATH, 11)
+    reg.set_option(_ffi.QB_OPT_FORCE_PATH, 0)
+    assert reg.stat(_ffi.QB_STAT_REMOTE_PASSES) == 0
+    reg.close()
