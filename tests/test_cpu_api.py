@@ -106,3 +106,19 @@ def test_error_payloads_and_options(engine):
     reg.set_option(_ffi.QB_OPT_FORCE_PATH, 0)
     assert reg.stat(_ffi.QB_STAT_REMOTE_PASSES) == 0
     reg.close()
+
+
+def test_bench_diagnostics_row_on_the_host_build(engine, capsys):
+    """tools/bench_diagnostics.py (the table bench.py appends to its JSON line): one configuration, in process, on the host
+    build -- the happy path of the script itself (circuits, stats, timers, JSON row)."""
+    import importlib.util
+    import json
+    spec = importlib.util.spec_from_file_location("bench_diagnostics", os.path.join(ROOT, "tools", "bench_diagnostics.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    mod.one(12, 0)
+    out = [ln for ln in capsys.readouterr().out.splitlines() if ln.startswith("DIAG ")]
+    row = json.loads(out[-1][5:])
+    assert row["max_abs_diff_vs_default_n24"] == 0.0 and abs(row["norm2_end"] - 1.0) < 1e-9
+    for kind in ("layers", "qft", "h4", "h12"):
+        assert row[kind]["passes"] >= 1 and row[kind]["gates"] >= 4

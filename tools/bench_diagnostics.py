@@ -51,7 +51,7 @@ def one(n, force):
 
     row = {"force_path": force}
     # correctness first: same circuit through the default kernel and through this configuration, 4096 tiles
-    nc = 24
+    nc = min(24, n)
     ops = [Operation(m, t) for m, t in bench.build_circuit(nc, layers=6, seed=1, qft=True)]
     regs = []
     for f in (0, force):
@@ -65,7 +65,7 @@ def one(n, force):
         r.close()
     reg = Register.new([False] * n)
     reg.set_option(4, force)
-    for kind in ("layers", "qft", "h4", "h12"):
+    for kind in ("layers", "qft", "h4", "h12") if n >= 12 else ("layers", "qft"):
         ops = [Operation(m, t) for m, t in circuit(kind, n)]
         reg.apply_batch(ops[:min(len(ops), 100)])   # first launches, function attributes
         reg.sync()
