@@ -107,13 +107,22 @@ static int create_impl(uint32_t n, uint64_t basis_index, int rank, int world, co
     return QB_OK;
 }
 
-// Launch everything queued.  Fusion on: plan tile passes (qb_tile.cu); off: one kernel per gate.
-static int flush(Reg* r) {
+// Launch everything queued.  Fusion on: plan tile passes (qb_tile.cu); off: one kernel per gate.  `more_coming`: the queue
+// overflowed in the middle of a gate stream -- the last planned pass, usually half empty, stays queued for the next flush.
+static int flush(Reg* r, bool more_coming = false) {
     if (r->queue.empty()) return QB_OK;
     QB_CUDA(cudaSetDevice(r->device));
     std::vector<Gate> gates;
     gates.swap(r->queue);
+    r->held = 0;
     if (r->world > 1) return shard_run(r, gates);
+    if (r->fusion && more_coming) {
+        std::vector<Gate> hold;
+        QB_TRY(run_fused(r, gates, &hold));
+        r->queue.insert(r->queue.begin(), hold.begin(), hold.end());   // already in engine qubits: not through enqueue_gate again
+        r->held = hold.size();
+        return QB_OK;
+    }
     if (r->fusion) return run_fused(r, gates);
     for (const Gate& g : gates) QB_TRY(k_apply_gate_unfused(r, g));
     return QB_OK;
@@ -136,7 +145,9 @@ static int enqueue_gate(Reg* r, Gate&& g) {
         relabel_gate(r->label, &g);
     }
     r->queue.push_back(std::move(g));
-    if (!r->fusion || r->queue.size() >= r->max_queue) return flush(r);
+    if (!r->fusion) return flush(r);
+    if (r->queue.size() >= r->max_queue + r->held) return flush(r, true);   // `held` gates came back from the last overflow
+                                                                             // flush: only new ones count
     return QB_OK;
 }
 
@@ -271,6 +282,7 @@ int qb_reset(qb_reg* reg, uint64_t basis_index) try {
     Reg* r = REG(reg);
     if (basis_index >= (1ull << r->n)) return set_error(QB_ERR_INVALID_ARGUMENT, (int64_t)basis_index, "basis index out of range");
     r->queue.clear();
+    r->held = 0;
     shard_reset_placement(r);
     reset_labels(r);
     const uint64_t owner = basis_index >> r->n_local;
@@ -398,6 +410,7 @@ int qb_load_state(qb_reg* reg, const char* path) try {
     Reg* r = REG(reg);
     if (!path) return set_error(QB_ERR_INVALID_ARGUMENT, -1, "path is NULL");
     r->queue.clear();  // the loaded image replaces whatever the pending gates would have produced
+    r->held = 0;
     shard_reset_placement(r);  // files hold the identity placement
     reset_labels(r);
     return state_load(r, path);

@@ -399,13 +399,19 @@ int drain_tile_events(Reg* r) {
     return QB_OK;
 }
 
-int run_fused(Reg* r, std::vector<Gate>& gates) {
+int run_fused(Reg* r, std::vector<Gate>& gates, std::vector<Gate>* hold) {
     std::vector<PlannedPass> passes;
     const int max_ops = (int)(sizeof(PassLarge::ops) / sizeof(TileOp));
     const int max_mats = (int)(sizeof(PassLarge::mats) / sizeof(c64));
     plan_passes(gates, r->n_local, r->tile_bits, max_ops, max_mats, &passes);
     static thread_local PassLarge large;  // host staging; thread_local: different handles may run on different threads
-    for (const PlannedPass& p : passes) {
+    size_t n_launch = passes.size();
+    if (hold && passes.size() > 1) {   // keep the last pass's gates for the next flush (they come before every future gate)
+        --n_launch;
+        for (size_t gi : passes.back().gate_idx) hold->push_back(gates[gi]);
+    }
+    for (size_t pi = 0; pi < n_launch; ++pi) {
+        const PlannedPass& p = passes[pi];
         if (p.unfused) {
             QB_TRY(k_apply_gate_unfused(r, gates[p.gate_idx[0]]));
             continue;

@@ -122,3 +122,34 @@ def test_bench_diagnostics_row_on_the_host_build(engine, capsys):
     assert row["max_abs_diff_vs_default_n24"] == 0.0 and abs(row["norm2_end"] - 1.0) < 1e-9
     for kind in ("layers", "qft", "h4", "h12"):
         assert row[kind]["passes"] >= 1 and row[kind]["gates"] >= 4
+
+
+@pytest.mark.parametrize("relabel_env,max_queue", [("1", 16), ("0", 16), ("1", 9), ("0", 40)])
+def test_overflow_flush_hands_the_last_pass_back(engine, monkeypatch, relabel_env, max_queue):
+    """When the queue overflows in the middle of a gate stream the gates of the last planned pass stay queued (in front of
+    whatever comes next) instead of being launched half empty.  The host stand-in's run_fused hands back the trailing gates the
+    same way, so the queue bookkeeping of the API layer -- order, the `held` count, full flushes at measurements and reads,
+    relabelled gates not translated twice -- is what is checked here against the oracle."""
+    from quaru_b200 import _ffi
+    from oracle import gates as og
+    from oracle.oracle import OracleRegister
+    from tests import circuits
+    from tests.util import assert_close
+    monkeypatch.setenv("QB_SWAP_RELABEL", relabel_env)
+    n = 9
+    ops = relabel_cases._swap_heavy(n, 150, 11) + circuits.qft_circuit(n) + circuits.random_circuit(n, 5, seed=4)
+    reg = engine.Register.new([False] * n)
+    reg.set_option(_ffi.QB_OPT_MAX_QUEUE, max_queue)
+    ora = OracleRegister.new([False] * n)
+    rng = np.random.default_rng(8)
+    for i, (m, t) in enumerate(ops):
+        reg.apply(engine.Operation(m, t))
+        ora.apply((m, t))
+        if i % 97 == 96:                              # a full flush in the middle of the stream
+            q = int(rng.integers(n))
+            u = float(rng.random())
+            assert reg.measure(q, u=u) == ora.measure(q, u)
+        if i % 131 == 130:
+            assert_close(reg.state, ora.state, f"after gate {i}")
+    assert_close(reg.state, ora.state, "end of the stream")
+    reg.close()
