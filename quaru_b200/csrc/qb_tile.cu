@@ -261,8 +261,13 @@ static void plan_passes(const std::vector<Gate>& gates, uint32_t n_local, uint32
                 }
                 if (mi == 0) cands.push_back(top_bits(h_max));
                 uint64_t centre = g0.high;
-                for (int climb = 0; climb < 3; ++climb) {   // hill climbing over one-bit exchanges of the best set so far
-                    const uint64_t pool = top_bits(12) & ~centre;
+                // hill climbing over one-bit exchanges of the best set so far; registers of >= 30 local qubits, whose sweeps cost
+                // ~100 ms, search every candidate bit and climb longer (bench, 2 steps at 33 qubits: 45 -> 41 sweeps, same rounds and ops;
+                // ~0.26 s of planning per 4096 gates instead of 0.10 s, hidden behind the seconds of GPU work they represent)
+                const int max_climbs = two_step ? 6 : 3;
+                const uint32_t pool_bits = two_step ? 64 : 12;
+                for (int climb = 0; climb < max_climbs; ++climb) {
+                    const uint64_t pool = top_bits(pool_bits) & ~centre;
                     for (uint64_t out_b = centre; out_b; out_b &= out_b - 1)
                         for (uint64_t in_b = pool; in_b; in_b &= in_b - 1)
                             cands.push_back((centre & ~(out_b & -out_b)) | (in_b & -in_b));
