@@ -34,7 +34,11 @@ def _plan_events(n, world, rank, ops):
     cap = 64 * (len(ops) + 1)
     ev = (ctypes.c_int32 * cap)()
     phys = (ctypes.c_uint32 * n)()
-    cnt = L.qb_shard_plan_debug(n, world, rank, arr, len(ops), ev, cap, phys)
+    os.environ["QB_SHARD_REORDER"] = "0"          # the first scheduler: exchange records only
+    try:
+        cnt = L.qb_shard_plan_debug(n, world, rank, arr, len(ops), ev, cap, phys)
+    finally:
+        del os.environ["QB_SHARD_REORDER"]
     assert cnt >= 0, _ffi.last_error()
     flat = list(ev)[:cnt]
     events, i = [], 0
@@ -140,9 +144,10 @@ def _worker(rank, world, port, n, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         ops = circuits.random_circuit(n, 5, seed=3) + circuits.qft_circuit(n)
-        events, phys = _plan_events(n, world, rank, ops)
+        events, phys = _plan_events(n, world, rank, ops)                        # the first scheduler
+        events2, phys2 = _plan_events_reordered(n, world, rank, ops)            # the default one
         gathered = [None] * world
-        dist.all_gather_object(gathered, (events, phys))
+        dist.all_gather_object(gathered, (events, phys, events2, phys2))
         ok = all(x == gathered[0] for x in gathered)
         # the bench's cross-rank timing reduction (max over ranks), over gloo
         import torch
@@ -170,7 +175,7 @@ def test_ranks_agree_over_gloo(world):
     assert len({cnt for _, _, cnt in res}) == 1
 
 
-# ---- experimental commutation-aware scheduler (QB_SHARD_REORDER=1) ---------------------------------------------------
+# ---- commutation-aware scheduler (the default) -------------------------------------------------------------------------
 def _plan_events_reordered(n, world, rank, ops):
     """Event stream with run records: a negative entry -1 - i means "gate i runs now"; exchange records as before."""
     from quaru_b200 import _ffi
@@ -187,11 +192,8 @@ def _plan_events_reordered(n, world, rank, ops):
     cap = 64 * (len(ops) + 1)
     ev = (ctypes.c_int32 * cap)()
     phys = (ctypes.c_uint32 * n)()
-    os.environ["QB_SHARD_REORDER"] = "1"
-    try:
-        cnt = L.qb_shard_plan_debug(n, world, rank, arr, len(ops), ev, cap, phys)
-    finally:
-        del os.environ["QB_SHARD_REORDER"]
+    assert "QB_SHARD_REORDER" not in os.environ and "QB_SHARD_REMOTE" not in os.environ
+    cnt = L.qb_shard_plan_debug(n, world, rank, arr, len(ops), ev, cap, phys)
     assert cnt >= 0, _ffi.last_error()
     flat, out, i = list(ev)[:cnt], [], 0
     while i < len(flat):

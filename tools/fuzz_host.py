@@ -2,7 +2,7 @@
 
     python tools/fuzz_host.py rounds  SECONDS [SEED0]   pass planner + round encoder, replayed by tests/rounds_emulator.py
     python tools/fuzz_host.py shard   SECONDS [SEED0]   exchange schedule of the sharded path (qb_shard_plan_debug), all ranks
-    python tools/fuzz_host.py shard-reorder SECONDS [SEED0]   the same for the experimental scheduler (QB_SHARD_REORDER=1)
+    python tools/fuzz_host.py shard-reorder SECONDS [SEED0]   the same for the commutation-aware scheduler (the default since the end of round 1)
     python tools/fuzz_host.py qasm    COUNT   [SEED0]   mutated OpenQASM programs: the parser must return, never crash
 
 Round 1: 2700 `rounds`, 26000 `shard` and 160000 `qasm` cases without a finding after the fixes they prompted
