@@ -153,3 +153,15 @@ def test_overflow_flush_hands_the_last_pass_back(engine, monkeypatch, relabel_en
             assert_close(reg.state, ora.state, f"after gate {i}")
     assert_close(reg.state, ora.state, "end of the stream")
     reg.close()
+
+
+@pytest.mark.parametrize("relabel_env", ["0", "1"])
+def test_cpp_mirror_through_the_api_layer(host_lib, relabel_env, tmp_path):
+    """include/quaru_b200.hpp (the C++ RAII mirror of Register) and its test program, linked against the host build: the whole
+    program, not only its --host-only part."""
+    exe = str(tmp_path / "test_register_host")
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O1", "-Wall", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cpp", "test_register.cpp"), "-o", exe, "-L", os.path.dirname(host_lib),
+                           "-lquaru_hostapi", f"-Wl,-rpath,{os.path.dirname(host_lib)}"])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120, env=dict(os.environ, QB_SWAP_RELABEL=relabel_env))
+    assert out.returncode == 0 and "CPP_OK" in out.stdout, out.stdout + out.stderr
