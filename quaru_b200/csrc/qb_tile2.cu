@@ -99,7 +99,13 @@ static bool encode_rounds_with(const std::vector<Gate>& gates, const std::vector
     size_t remaining = ops.size(), n_ops = 0, n_mats = 4, n_rounds = 0;
     prog->mats[0] = prog->mats[3] = make_double2(1.0, 0.0);
     prog->mats[1] = prog->mats[2] = make_double2(0.0, 0.0);
-    const uint32_t io_allowed = 0xfe0;  // tile bits 5..11: register bits of the HBM-facing rounds
+    // register bits of the HBM-facing rounds: tile bits 5..11, so that a warp's lanes are tile bits 0..4 = one contiguous 512-byte
+    // segment per access.  Experimental (QB_TILE_IO_LOW=4 or 3, not yet measured): bits 4 / 3 may be register bits there too -- a
+    // warp access then covers two 256-byte / four 128-byte pieces (still whole lines), and fewer passes need an extra round whose only
+    // purpose is the transpose into a storable layout (bench, 3 steps at 33 qubits: 201 -> 193 / 189 rounds)
+    const char* io_env = getenv("QB_TILE_IO_LOW");
+    const uint32_t io_low = (io_env && (io_env[0] == '3' || io_env[0] == '4') && !io_env[1]) ? (uint32_t)(io_env[0] - '0') : 5u;
+    const uint32_t io_allowed = 0xfffu & ~((1u << io_low) - 1u);
     // Unconditional constant factors (the deferred 1/sqrt(2) of every Hadamard, the common factor d0 of a one-qubit diagonal
     // diag(d0, d1) on a register bit, global phases) commute with everything: they are multiplied together on the host
     // over the whole pass and applied once, in its last round, instead of costing a table op and 16 complex multiplies

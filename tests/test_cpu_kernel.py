@@ -183,3 +183,18 @@ def test_remote_tile_pass_on_the_host_compiled_kernel(host_kernel, world, n, kin
     got = np.concatenate(shards)
     assert np.array_equal(got, ref), "same tiles, same arithmetic as the single-register kernel"
     assert_close(got, ora.state, f"remote tile pass vs oracle, world={world} n={n} {kind}")
+
+
+@pytest.mark.parametrize("io_low,kind,n", [("3", "layers", 14), ("4", "mixed", 13), ("3", "qft", 14)])
+def test_relaxed_io_rounds_on_the_host_compiled_kernel(host_kernel, io_low, kind, n, monkeypatch):
+    """Experimental QB_TILE_IO_LOW = 4 / 3: tile bits 4 / 3 may be register bits of the HBM-facing rounds (a warp access then
+    covers 256- / 128-byte pieces instead of one 512-byte segment), which saves the extra round some passes need only to get
+    into a storable layout.  Same kernel, other host-computed offsets and lane mappings."""
+    monkeypatch.setenv("QB_TILE_IO_LOW", io_low)
+    ops = {"layers": circuits.random_circuit(n, 6, seed=5 * n), "qft": circuits.qft_circuit(n), "mixed": circuits.mixed_circuit(n, 120, 4 * n)}[kind]
+    low = [r["R"] for p in em.dump_programs(n, ops) if p[0] == "prog" for r in (p[3]["rounds"][0], p[3]["rounds"][-1])]
+    assert any(min(R) < 5 for R in low), "some HBM-facing round uses a register bit below 5"
+    dev, emu, want, n_prog = _run(host_kernel, n, ops, 120 + n)
+    assert n_prog >= 1
+    assert_close(dev, want, f"relaxed io rounds, kernel vs oracle, {kind} n={n}")
+    assert_close(dev, emu, "kernel vs program emulator")

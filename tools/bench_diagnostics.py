@@ -27,6 +27,7 @@ CONFIGS = [  # (label, force_path, extra environment); most informative first, t
     ("default", 0, {}),
     ("default_no_lookahead", 0, {"QB_PLAN_LOOKAHEAD": "0"}),
     ("default_no_swap_relabel", 0, {"QB_SWAP_RELABEL": "0"}),
+    ("default_io_low3", 0, {"QB_TILE_IO_LOW": "3"}),
     ("persist_mats_ops", 6, {}), ("persist_mats_ops_rtab", 6, {"QB_TILE_RTAB": "1"}),
     ("persist_mats_ops_ahead", 10, {}), ("persist_mats_ops_pf", 8, {}), ("persist_mats_ops_pf_ahead", 11, {}),
     ("persist_mats_ops_pf_ahead_rtab", 11, {"QB_TILE_RTAB": "1"}),
@@ -97,7 +98,7 @@ def main():
             out["rows"].append({"label": label, "skipped": "time budget"})
             continue
         e = dict(os.environ)
-        for k in ("QB_PLAN_LOOKAHEAD", "QB_TILE_RTAB", "QB_OPT_FORCE_PATH", "QB_SWAP_RELABEL"):
+        for k in ("QB_PLAN_LOOKAHEAD", "QB_TILE_RTAB", "QB_OPT_FORCE_PATH", "QB_SWAP_RELABEL", "QB_TILE_IO_LOW"):
             e.pop(k, None)
         e.update(env)
         try:
