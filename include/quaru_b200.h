@@ -170,6 +170,12 @@ int qb_timer_stop(qb_reg* reg, float* ms);
                                   5..11 experimental persistent tile kernels (coefficients staged in shared memory; 6, 8, 10, 11: op
                                   records too; 7, 8, 11: L2 prefetch of the next tile; 9, 10, 11: op records fetched one op ahead) */
 #define QB_OPT_PROFILE 5       /* 1: bracket every tile-pass launch with CUDA events (QB_STAT_TILE_NS) */
+#define QB_OPT_JIT 6           /* specialised tile kernels (one NVRTC-compiled kernel per distinct pass program, cached by program hash):
+                                  0 off; 1 (default, env QB_JIT) asynchronous -- a pass runs through the interpreter kernel until its
+                                  kernel is ready; 2 synchronous -- wait for the compiler, a compile failure is an error (tests) */
+#define QB_OPT_JIT_MIN_QUBITS 7 /* local qubits from which passes are specialised (default 26, env QB_JIT_MIN_QUBITS) */
+#define QB_OPT_JIT_VARIANT 8   /* kernel shape: bits 0-3 = CTAs per SM the register budget is set for (2 -> 128 registers, 3 -> 80),
+                                  bit 4 = persistent CTAs walking the tiles, bit 5 = with an L2 prefetch of the next tile */
 int qb_set_option(qb_reg* reg, int32_t option, int64_t value);
 
 #define QB_STAT_KERNEL_LAUNCHES 1 /* kernels launched by this handle since creation */
@@ -183,7 +189,17 @@ int qb_set_option(qb_reg* reg, int32_t option, int64_t value);
 #define QB_STAT_ROUNDS 9          /* register rounds executed by the register-blocked tile kernel */
 #define QB_STAT_P2P_EXCHANGES 10  /* exchanges done by the peer-memory kernel (the rest went through NCCL send/recv) */
 #define QB_STAT_REMOTE_PASSES 11  /* tile passes that reached peers' shards directly (QB_SHARD_REMOTE=1; their NVLink bytes count in QB_STAT_SWAP_BYTES) */
+#define QB_STAT_JIT_LAUNCHES 12   /* tile passes run by a specialised kernel */
+#define QB_STAT_JIT_COMPILES 13   /* distinct pass programs this handle handed to the compiler */
+#define QB_STAT_JIT_MISSES 14     /* passes the interpreter kernel ran because the specialised kernel was not ready (or failed) */
+#define QB_STAT_JIT_COMPILE_MS 15 /* process-wide: summed NVRTC time, ms */
+#define QB_STAT_JIT_PENDING 16    /* process-wide: compiles queued or running */
+#define QB_STAT_JIT_FAILED 17     /* process-wide: compiles that failed */
 int qb_get_stat(qb_reg* reg, int32_t stat, int64_t* value);
+
+/* Blocks until no specialised kernel is being compiled (process-wide).  A driver that is about to time a circuit it has
+ * already applied once calls this so that every pass finds its kernel in the cache. */
+int qb_jit_drain(void);
 
 /* ---- planner introspection (host only, no GPU needed) ------------------------------------ */
 /* Plans `count` gates for an n-qubit register with the given tile parameters exactly as
@@ -238,6 +254,13 @@ int64_t qb_rounds_debug(uint32_t n, const qb_gate* gates, uint64_t count, void* 
  * list (tests/test_dist_cpu.py checks this over gloo). */
 int64_t qb_shard_plan_debug(uint32_t n, int32_t world, int32_t rank, const qb_gate* gates, uint64_t count,
                             int32_t* events, uint64_t capacity, uint32_t* final_phys_of);
+
+/* The CUDA source of the specialised kernel for one serialised round program (a `kind 0` record of qb_rounds_debug), and
+ * an NVRTC compile of such a source for sm_100a; neither needs a GPU.  tests/test_jit_cpu.py builds the source as host C++
+ * (-DQB_HOST_EMU) and replays it against the oracle. */
+int64_t qb_jit_source_debug(const void* program, uint64_t len, int32_t min_blocks, int32_t persistent, int32_t prefetch,
+                            int32_t remote, char* out, uint64_t capacity);
+int64_t qb_jit_compile_debug(const char* source, double* ms, void* cubin_out, uint64_t capacity);
 
 const char* qb_version(void);
 

@@ -8,6 +8,7 @@
 #include <new>
 
 #include "qb_common.h"
+#include "qb_jit.h"
 #include "qb_shard.h"
 #include "qb_tile.h"
 
@@ -54,6 +55,12 @@ static int alloc_common(Reg* r) {
     // SWAP gates as relabelling: for registers whose sweeps are expensive (QB_SWAP_RELABEL=1 / 0 forces it on / off)
     const char* rl = getenv("QB_SWAP_RELABEL");
     r->relabel = rl ? rl[0] == '1' : r->n_local >= 28;
+    if (const char* j = getenv("QB_JIT")) r->jit = (j[0] >= '0' && j[0] <= '2') ? j[0] - '0' : 1;
+    if (const char* j = getenv("QB_JIT_MIN_QUBITS")) r->jit_min_qubits = (uint32_t)atoi(j);
+    if (const char* j = getenv("QB_JIT_VARIANT")) {
+        const int v = atoi(j);
+        r->jit_min_blocks = (v & 15) ? (v & 15) : 2; r->jit_persistent = (v >> 4) & 1; r->jit_prefetch = (v >> 5) & 1;
+    }
     return QB_OK;
 }
 
@@ -268,6 +275,8 @@ int qb_clone(qb_reg* src_, qb_reg** out) try {
     if (rc != QB_OK) return rc;
     Reg* dst = REG(*out);
     dst->fusion = src->fusion; dst->tile_bits = src->tile_bits; dst->max_queue = src->max_queue; dst->force_path = src->force_path;
+    dst->jit = src->jit; dst->jit_min_qubits = src->jit_min_qubits; dst->jit_min_blocks = src->jit_min_blocks;
+    dst->jit_persistent = src->jit_persistent; dst->jit_prefetch = src->jit_prefetch;
     dst->relabel = src->relabel; dst->label = src->label;   // same amplitudes, same qubit names
     cudaError_t e = cudaMemcpyAsync(dst->state, src->state, sizeof(c64) << src->n_local, cudaMemcpyDeviceToDevice, src->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(src->stream);
@@ -503,6 +512,15 @@ int qb_set_option(qb_reg* reg, int32_t option, int64_t value) try {
             r->max_queue = (uint64_t)value;
             return QB_OK;
         case QB_OPT_PROFILE: r->profile = value != 0; return QB_OK;
+        case QB_OPT_JIT:
+            if (value < 0 || value > 2) return set_error(QB_ERR_INVALID_ARGUMENT, value, "jit must be 0, 1 or 2");
+            r->jit = (int)value;
+            return QB_OK;
+        case QB_OPT_JIT_MIN_QUBITS: r->jit_min_qubits = (uint32_t)std::max<int64_t>(value, 12); return QB_OK;
+        case QB_OPT_JIT_VARIANT:
+            if ((value & 15) < 1 || (value & 15) > 4 || value > 63) return set_error(QB_ERR_INVALID_ARGUMENT, value, "bad jit variant");
+            r->jit_min_blocks = (int)(value & 15); r->jit_persistent = (int)((value >> 4) & 1); r->jit_prefetch = (int)((value >> 5) & 1);
+            return QB_OK;
         case QB_OPT_FORCE_PATH:
             if (value < 0 || value > 11) return set_error(QB_ERR_INVALID_ARGUMENT, value, "force path must be in [0, 11]");
             r->force_path = (int)value;
@@ -527,6 +545,17 @@ int qb_get_stat(qb_reg* reg, int32_t stat, int64_t* value) try {
         case QB_STAT_P2P_EXCHANGES: *value = r->st_p2p; return QB_OK;
         case QB_STAT_REMOTE_PASSES: *value = r->st_remote_passes; return QB_OK;
         case QB_STAT_TILE_NS: QB_TRY(drain_tile_events(r)); *value = r->st_tile_ns; return QB_OK;
+        case QB_STAT_JIT_LAUNCHES: *value = r->st_jit_launches; return QB_OK;
+        case QB_STAT_JIT_COMPILES: *value = r->st_jit_compiles; return QB_OK;
+        case QB_STAT_JIT_MISSES: *value = r->st_jit_misses; return QB_OK;
+        case QB_STAT_JIT_COMPILE_MS:
+        case QB_STAT_JIT_PENDING:
+        case QB_STAT_JIT_FAILED: {
+            int64_t c, f, p, ms;
+            jit_global_stats(&c, &f, &p, &ms);
+            *value = stat == QB_STAT_JIT_COMPILE_MS ? ms : stat == QB_STAT_JIT_PENDING ? p : f;
+            return QB_OK;
+        }
     }
     return set_error(QB_ERR_INVALID_ARGUMENT, stat, "unknown stat %d", stat);
 } QB_CATCH_ALL

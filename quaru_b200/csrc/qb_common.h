@@ -104,9 +104,15 @@ struct Reg {
     uint64_t max_queue = 4096;
     int force_path = 0;
     int profile = 0;
+    // specialised (JIT-compiled) tile kernels, qb_jit.cu: 0 off, 1 asynchronous (the interpreter kernel runs a pass until its
+    // specialised kernel is ready), 2 synchronous (wait for the compiler; failures are errors)
+    int jit = 1;
+    uint32_t jit_min_qubits = 26;   // local qubits from which a pass is worth a compile (its sweeps take >= ~1 ms)
+    int jit_min_blocks = 2, jit_persistent = 0, jit_prefetch = 0;
     // stats
     int64_t st_launches = 0, st_passes = 0, st_gates = 0, st_bytes = 0, st_swap_bytes = 0, st_swaps = 0;
     int64_t st_tile_launches = 0, st_tile_ns = 0, st_rounds = 0, st_p2p = 0, st_remote_passes = 0;
+    int64_t st_jit_launches = 0, st_jit_compiles = 0, st_jit_misses = 0;
     std::vector<cudaEvent_t> tile_events;  // start/stop pairs of profiled tile launches
     size_t tile_events_used = 0;
     // sharding

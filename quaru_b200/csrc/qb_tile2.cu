@@ -23,6 +23,7 @@
 
 #include "qb_common.h"
 #include "qb_device.cuh"
+#include "qb_jit.h"
 #include "qb_tile.h"
 #include "qb_tile2_kernel.cuh"
 
@@ -759,10 +760,14 @@ static int launch_rpass(Reg* r, const Prog& prog) {
     }
     const uint64_t tiles = 1ull << (r->n_local - RT);
     if (tiles > 0x7fffffffull) return set_error(QB_ERR_UNSUPPORTED, (int64_t)tiles, "too many tiles for one grid");
-    if (r->profile) QB_TRY(tile_profile_begin(r));
-    k2r_tile_pass<Prog><<<(unsigned)tiles, RTHREADS, sizeof(c64) << RT, r->stream>>>(r->state, prog);
-    QB_CUDA(cudaGetLastError());
-    if (r->profile) QB_TRY(tile_profile_end(r));
+    bool jitted = false;   // the pass's specialised kernel, if it is ready (qb_jit.cu); else the interpreter kernel below
+    QB_TRY(jit_try_launch(r, make_view(prog), nullptr, &jitted));
+    if (!jitted) {
+        if (r->profile) QB_TRY(tile_profile_begin(r));
+        k2r_tile_pass<Prog><<<(unsigned)tiles, RTHREADS, sizeof(c64) << RT, r->stream>>>(r->state, prog);
+        QB_CUDA(cudaGetLastError());
+        if (r->profile) QB_TRY(tile_profile_end(r));
+    }
     r->st_launches++;
     r->st_passes++;
     r->st_rounds += prog.n_rounds;

@@ -1,0 +1,132 @@
+"""The specialised tile kernels (K2j, quaru_b200/csrc/qb_jit_gen.cu) without a GPU.
+
+For every fused pass of a circuit the library hands out the CUDA source it would compile with NVRTC
+(qb_jit_source_debug).  Here that very text is built as host C++ (g++ -DQB_HOST_EMU: one OS thread per CUDA thread, a
+pthread barrier for __syncthreads, tests/cpu_kernel/qb_jit_emu.h) and run over a host state vector; the result must match the
+CPU oracle (the reference's try_apply_fast, /root/reference/src/register.rs:140-191, restated in oracle/).  A second test
+compiles the same text for sm_100a with NVRTC (no device needed) -- what the launch path does on the GPU box.
+"""
+import ctypes
+import hashlib
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import gates as og
+from oracle.oracle import OracleRegister
+from tests import circuits
+from tests import rounds_emulator as em
+from tests.util import assert_close, random_state
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+KDIR = os.path.join(ROOT, "tests", "cpu_kernel")
+BUILD = os.path.join(KDIR, "_build", "jit")
+
+
+def jit_source(prog_bytes, min_blocks=2, persistent=0, prefetch=0, remote=0):
+    from quaru_b200 import _ffi
+    L = _ffi.lib()
+    cap = 8 << 20
+    buf = ctypes.create_string_buffer(cap)
+    got = L.qb_jit_source_debug(prog_bytes, len(prog_bytes), min_blocks, persistent, prefetch, remote, buf, cap)
+    assert got > 0, _ffi.last_error()
+    return buf.raw[:got].decode()
+
+
+def build_host(src, remote=False):
+    os.makedirs(BUILD, exist_ok=True)
+    tag = hashlib.sha1((src + str(remote)).encode()).hexdigest()[:16]
+    cu, so = os.path.join(BUILD, tag + ".cu"), os.path.join(BUILD, tag + ".so")
+    if not os.path.exists(so):
+        with open(cu, "w") as f:
+            f.write(src)
+        cmd = ["/usr/bin/g++", "-std=c++17", "-O1", "-ffp-contract=off", "-DQB_HOST_EMU", f'-DQB_JIT_SRC="{cu}"', "-shared", "-fPIC", "-pthread",
+               "-I", KDIR, os.path.join(KDIR, "jit_host_runner.cpp"), "-o", so]
+        if remote:
+            cmd.insert(5, "-DQB_JIT_REMOTE")
+        subprocess.check_call(cmd)
+    lib = ctypes.CDLL(so)
+    lib.jit_host_run.restype = ctypes.c_int
+    lib.jit_host_run.argtypes = [ctypes.c_void_p, ctypes.c_uint, ctypes.c_uint, ctypes.c_uint, ctypes.POINTER(ctypes.c_void_p), ctypes.c_uint, ctypes.c_uint]
+    return lib
+
+
+def run_circuit(n, ops, seed, grid=0, **gen):
+    s0 = random_state(n, seed)
+    ora = OracleRegister(s0.copy(), n)
+    for o in ops:
+        ora.apply(o)
+    dev = s0.copy()
+    n_prog = 0
+    for p in em.dump_programs(n, ops):
+        if p[0] == "gates":
+            tmp = OracleRegister(dev, n)
+            for tag in p[1]:
+                tmp.apply(ops[tag])
+            dev[:] = tmp.state
+            continue
+        n_prog += 1
+        lib = build_host(jit_source(p[3]["bytes"], **gen))
+        assert lib.jit_host_run(dev.ctypes.data, 1 << (n - 12), grid, 0, None, 0, 0) == 0
+    return dev, ora.state, n_prog
+
+
+@pytest.mark.parametrize("n,depth,seed", [(12, 6, 1), (13, 5, 2), (14, 4, 3)])
+def test_random_layers(n, depth, seed):
+    dev, want, n_prog = run_circuit(n, circuits.random_circuit(n, depth, seed=seed), 50 + seed)
+    assert n_prog >= 1
+    assert_close(dev, want, f"generated kernel vs oracle, layers n={n}")
+
+
+@pytest.mark.parametrize("n", [12, 14])
+def test_qft(n):
+    dev, want, n_prog = run_circuit(n, circuits.qft_circuit(n), 60 + n)
+    assert n_prog >= 1
+    assert_close(dev, want, f"generated kernel vs oracle, qft n={n}")
+
+
+@pytest.mark.parametrize("n,seed", [(12, 5), (13, 6), (14, 7)])
+def test_mixed_gates(n, seed):
+    """Every op kind: dense complex / real / two-qubit gates, controls on register, thread and outer bits, wide diagonals,
+    X / CNOT / SWAP (renamings when uncontrolled)."""
+    dev, want, n_prog = run_circuit(n, circuits.mixed_circuit(n, 120, seed), 70 + seed)
+    assert n_prog >= 1
+    assert_close(dev, want, f"generated kernel vs oracle, mixed n={n}")
+
+
+@pytest.mark.parametrize("n,grid,kind,prefetch", [(14, 3, "layers", 1), (13, 1, "mixed", 0), (14, 2, "qft", 1)])
+def test_persistent_variant(n, grid, kind, prefetch):
+    ops = {"layers": circuits.random_circuit(n, 4, seed=n), "qft": circuits.qft_circuit(n), "mixed": circuits.mixed_circuit(n, 100, n)}[kind]
+    dev, want, n_prog = run_circuit(n, ops, 80 + n, grid=grid, persistent=1, prefetch=prefetch)
+    assert n_prog >= 1
+    assert_close(dev, want, f"persistent generated kernel vs oracle, {kind} n={n} grid={grid}")
+
+
+def test_permutation_gates_are_renamings():
+    """X, CNOT and SWAP between register bits move no data: the generator only renames the variables a later store reads."""
+    n = 12
+    ops = [og.hadamard(8), og.hadamard(9), og.not_(9), og.cnot(8, 9), og.rz(0.3, 9), og.hadamard(10), og.swap(9, 10), og.hadamard(9)]
+    progs = [p for p in em.dump_programs(n, ops) if p[0] == "prog"]
+    assert progs
+    src = jit_source(progs[0][3]["bytes"])
+    body = src[src.index("QB_KERNEL(qb_jit_pass"):]
+    dev, want, _ = run_circuit(n, ops, 5)
+    assert_close(dev, want)
+    assert " * " not in body.split("// ---- round 0")[0], "no arithmetic before the first round"
+
+
+def test_nvrtc_compiles_the_generated_source():
+    """The text compiles for sm_100a with NVRTC (libnvrtc is loaded with dlopen; no device needed): the launch path's first half."""
+    from quaru_b200 import _ffi
+    L = _ffi.lib()
+    n = 14
+    ops = circuits.mixed_circuit(n, 120, 3) + circuits.qft_circuit(n)
+    progs = [p for p in em.dump_programs(n, ops) if p[0] == "prog"]
+    assert progs
+    for variant in ({}, {"persistent": 1, "prefetch": 1}, {"min_blocks": 3}):
+        src = jit_source(progs[0][3]["bytes"], **variant)
+        ms = ctypes.c_double(0)
+        got = L.qb_jit_compile_debug(src.encode(), ctypes.byref(ms), None, 0)
+        assert got > 0, _ffi.last_error()
