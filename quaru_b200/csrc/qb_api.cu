@@ -8,7 +8,6 @@
 #include <new>
 
 #include "qb_common.h"
-#include "qb_jit.h"
 #include "qb_shard.h"
 #include "qb_tile.h"
 
@@ -278,8 +277,11 @@ int qb_clone(qb_reg* src_, qb_reg** out) try {
     dst->jit = src->jit; dst->jit_min_qubits = src->jit_min_qubits; dst->jit_min_blocks = src->jit_min_blocks;
     dst->jit_persistent = src->jit_persistent; dst->jit_prefetch = src->jit_prefetch;
     dst->relabel = src->relabel; dst->label = src->label;   // same amplitudes, same qubit names
-    cudaError_t e = cudaMemcpyAsync(dst->state, src->state, sizeof(c64) << src->n_local, cudaMemcpyDeviceToDevice, src->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(src->stream);
+    // create_impl queued dst's initialisation (memset + the single 1) on dst->stream, a different non-blocking stream: the copy
+    // is ordered after both streams' work by issuing it on dst->stream once src->stream has drained
+    cudaError_t e = cudaStreamSynchronize(src->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dst->state, src->state, sizeof(c64) << src->n_local, cudaMemcpyDeviceToDevice, dst->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(dst->stream);
     if (e != cudaSuccess) { free_reg(dst); *out = nullptr; return fail_cuda(e, "clone copy", __FILE__, __LINE__); }
     return QB_OK;
 } QB_CATCH_ALL

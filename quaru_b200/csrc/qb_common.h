@@ -148,4 +148,8 @@ int run_local(Reg* r, std::vector<Gate>& gates);  // fused or unfused according 
 int64_t plan_debug(uint32_t n, std::vector<Gate>& gates, uint32_t tile_bits, int32_t* pass_of_gate,
                    int32_t* order_in_pass);
 
+// ---- specialised tile kernels (qb_jit.cu): process-wide compiler state ------------------------------
+int jit_drain();           // wait until no compile is pending
+void jit_global_stats(int64_t* compiled, int64_t* failed, int64_t* pending, int64_t* compile_ms);
+
 }  // namespace qb

@@ -36,7 +36,5 @@ std::string jit_generate(const ProgView& p, const JitOpts& o);
 // Launch path (qb_tile2.cu).  *launched = true if a specialised kernel ran the pass; false: the caller runs the interpreter
 // kernel (compile pending, JIT off, or unavailable).  With r->jit == 2 the call waits for the compiler and a failure is an error.
 int jit_try_launch(Reg* r, const ProgView& p, const RemoteArgs* remote, bool* launched);
-int jit_drain();           // wait until no compile is pending
-void jit_global_stats(int64_t* compiled, int64_t* failed, int64_t* pending, int64_t* compile_ms);
 
 }  // namespace qb

@@ -170,8 +170,10 @@ bool tile_supported(const Gate& g) {
 static void plan_passes(const std::vector<Gate>& gates, uint32_t n_local, uint32_t T_opt, int max_ops, int max_mats,
                         const std::function<void(PlannedPass&&)>& sink) {
     const uint32_t T = std::min(T_opt, n_local);
-    const uint32_t lc_min = std::min(MIN_LC, T);
-    const uint32_t h_max = std::min<uint32_t>(T - lc_min, 7);
+    // QB_PLAN_MIN_LC=4 (experiment): 256-byte contiguous segments, one more arbitrary high bit per tile
+    const char* lc_env = getenv("QB_PLAN_MIN_LC");
+    const uint32_t lc_min = std::min((lc_env && lc_env[0] == '4' && T == 12) ? 4u : MIN_LC, T);
+    const uint32_t h_max = std::min<uint32_t>(T - lc_min, 8);
     std::vector<char> done(gates.size(), 0);
     size_t remaining = gates.size();
     // One pass = one scan of the remaining gates in program order.  A gate WRITES its dense target bits and READS its

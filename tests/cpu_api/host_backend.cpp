@@ -145,6 +145,8 @@ int run_fused(Reg* r, std::vector<Gate>& gates, std::vector<Gate>* hold) {   // 
 
 int64_t plan_debug(uint32_t, std::vector<Gate>&, uint32_t, int32_t*, int32_t*) { return set_error(QB_ERR_UNSUPPORTED, -1, "host stand-in"); }
 int64_t rounds_debug(uint32_t, std::vector<Gate>&, unsigned char*, uint64_t) { return set_error(QB_ERR_UNSUPPORTED, -1, "host stand-in"); }
+int jit_drain() { return QB_OK; }
+void jit_global_stats(int64_t* c, int64_t* f, int64_t* p, int64_t* ms) { *c = *f = *p = *ms = 0; }
 
 int shard_unique_id(void*) { return set_error(QB_ERR_UNSUPPORTED, -1, "host stand-in: single rank only"); }
 int shard_init(Reg*, const void*) { return set_error(QB_ERR_UNSUPPORTED, -1, "host stand-in: single rank only"); }
@@ -158,3 +160,8 @@ int shard_reduce_diff(Reg*, double*, double*) { return QB_OK; }
 int64_t shard_plan_debug(uint32_t, int, int, std::vector<Gate>&, int32_t*, uint64_t, uint32_t*) { return set_error(QB_ERR_UNSUPPORTED, -1, "host stand-in"); }
 
 }  // namespace qb
+
+// the specialised-kernel entry points live in qb_jit.cu (not part of the host build)
+extern "C" int64_t qb_jit_source_debug(const void*, uint64_t, int32_t, int32_t, int32_t, int32_t, char*, uint64_t) { return qb::set_error(QB_ERR_UNSUPPORTED, -1, "host stand-in"); }
+extern "C" int64_t qb_jit_compile_debug(const char*, double*, void*, uint64_t) { return qb::set_error(QB_ERR_UNSUPPORTED, -1, "host stand-in"); }
+extern "C" int qb_jit_drain(void) { return QB_OK; }

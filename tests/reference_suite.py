@@ -56,6 +56,9 @@ class _OracleReg:
     def measure(self, t, u):
         return self.r.measure(t, u)
 
+    def apply_circuit(self, ops, measurement_targets, conditional_ops, us):      # register.rs:345-377
+        return self.r.apply_circuit(ops, measurement_targets, conditional_ops, us)
+
     def state(self):
         return self.r.state.copy()
 
@@ -117,6 +120,16 @@ class _EngineReg:
 
     def measure(self, t, u):
         return self.r.measure(t, u=u)
+
+    def apply_circuit(self, ops, measurement_targets, conditional_ops, us):      # register.rs:345-377
+        circ = self.b.e.QuantumCircuit()                                         # the builder of operation.rs:276-321
+        for g in ops:
+            circ.add_operation(self.b.op(g))
+        for t in measurement_targets:
+            circ.add_measurement(t)
+        for g, conds in conditional_ops:
+            circ.add_conditional_operation(self.b.op(g), conds)
+        return self.r.apply_circuit(circ, us)
 
     def state(self):
         return self.r.state
@@ -444,22 +457,33 @@ def _state_of_qubit(state, n):                                        # get_stat
     return np.array([alpha, beta]) / math.sqrt(prob)
 
 
-def t_quantum_teleportation(B, rng, trials=20):                       # :142-160
+def t_quantum_teleportation(B, rng, trials=20):                       # :142-149, protocol :83-99
     for _ in range(trials):
         v = rng.normal(size=2) + 1j * rng.normal(size=2)
         q0 = v / np.linalg.norm(v)
         reg = B.new([False] * 3)
         reg.set_state(np.kron(np.kron([1, 0], [1, 0]), q0))            # kron(kron(|0>,|0>), q0)
-        reg.apply(og.hadamard(1))
-        reg.apply(og.cnot(1, 2))
+        reg.apply(og.hadamard(2))
+        reg.apply(og.cnot(2, 1))
         reg.apply(og.cnot(0, 1))
         reg.apply(og.hadamard(0))
-        m0 = reg.measure(0, rng.random())
-        m1 = reg.measure(1, rng.random())
-        if m1:
+        if reg.measure(1, rng.random()):
             reg.apply(og.not_(2))
-        if m0:
+        if reg.measure(0, rng.random()):
             reg.apply(og.pauli_z(2))
+        assert equal_qubits(_state_of_qubit(reg.state(), 2), q0)
+
+
+def t_qantum_teleportation_circuit(B, rng, trials=20):                # :150-157 (sic), circuit :100-118, driver :60-74
+    for _ in range(trials):
+        v = rng.normal(size=2) + 1j * rng.normal(size=2)
+        q0 = v / np.linalg.norm(v)
+        reg = B.new([False] * 3)
+        reg.set_state(np.kron(np.kron([1, 0], [1, 0]), q0))
+        ops = [og.hadamard(2), og.cnot(2, 1), og.cnot(0, 1), og.hadamard(0)]
+        conditional = [(og.not_(2), [(1, True)]), (og.pauli_z(2), [(0, True)])]
+        measures = reg.apply_circuit(ops, [1, 0], conditional, [rng.random(), rng.random()])
+        assert [t for t, _ in measures] == [1, 0]                      # insertion order (register.rs:369-375)
         assert equal_qubits(_state_of_qubit(reg.state(), 2), q0)
 
 
@@ -483,4 +507,5 @@ ALL = [t_measure_on_zero_state_gives_false, t_from_qubits_test, t_not_on_arbitra
        t_any_entangled_bit_measure_same, t_first_bell_state_measure_equal, t_arbitrary_unary_applied_twice_gives_equal,
        t_arbitrary_binary_applied_twice_gives_equal, t_swap_single_true_qubit, t_toffoli_test, t_apply_all_test,
        t_apply_all_panics_if_not_unary, t_invalid_target_returns_error, t_grover_oracle_operation,
-       t_grover_diffuser_operation, t_grover_finds_target, t_qft_add, t_quantum_teleportation, t_superdense_coding]
+       t_grover_diffuser_operation, t_grover_finds_target, t_qft_add, t_quantum_teleportation, t_qantum_teleportation_circuit,
+       t_superdense_coding]

@@ -102,8 +102,10 @@ def test_error_payloads_and_options(engine):
         reg.try_measure(7, u=0.5)
     with pytest.raises(Exception):
         reg.set_option(_ffi.QB_OPT_FORCE_PATH, 12)
-    reg.set_option(_ffi.QB_OPT_FORCE_PATH, 11)
     reg.set_option(_ffi.QB_OPT_FORCE_PATH, 0)
+    with pytest.raises(Exception):
+        reg.set_option(_ffi.QB_OPT_JIT, 3)
+    reg.set_option(_ffi.QB_OPT_JIT, 1)
     assert reg.stat(_ffi.QB_STAT_REMOTE_PASSES) == 0
     reg.close()
 
@@ -116,10 +118,10 @@ def test_bench_diagnostics_row_on_the_host_build(engine, capsys):
     spec = importlib.util.spec_from_file_location("bench_diagnostics", os.path.join(ROOT, "tools", "bench_diagnostics.py"))
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
-    mod.one(12, 0)
+    mod.one(12, 0, 2)
     out = [ln for ln in capsys.readouterr().out.splitlines() if ln.startswith("DIAG ")]
     row = json.loads(out[-1][5:])
-    assert row["max_abs_diff_vs_default_n24"] == 0.0 and abs(row["norm2_end"] - 1.0) < 1e-9
+    assert row["max_abs_diff_vs_interpreter_n24"] == 0.0 and abs(row["norm2_end"] - 1.0) < 1e-9
     for kind in ("layers", "qft", "h4", "h12"):
         assert row[kind]["passes"] >= 1 and row[kind]["gates"] >= 4
 

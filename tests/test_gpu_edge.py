@@ -103,3 +103,18 @@ def test_many_controls_through_every_path(engine, n):
         st = ora.state
         st[[-2, -1]] = st[[-1, -2]]
         assert_close(reg.state, st, f"n={n} fusion={fusion}")
+
+
+def test_clone_of_a_large_register_is_ordered_after_its_initialisation(engine):
+    """qb_clone (#[derive(Clone)], /root/reference/src/register.rs:23) at a size where the new handle's memset takes far longer
+    than a launch: the copy must not race with it (the two handles own different streams)."""
+    n = 27
+    reg = engine.Register.new([False] * n)
+    for q in (0, 5, 13, 20, 26):
+        reg.apply(engine.operation.hadamard(q))
+    for _ in range(3):
+        c = reg.clone()
+        assert reg.max_abs_diff(c) == 0.0
+        assert abs(c.norm2() - 1.0) < 1e-12
+        assert abs(c.read(0, 1)[0] - reg.read(0, 1)[0]) == 0.0
+        c.close()

@@ -59,8 +59,9 @@ def test_cache_hits_on_the_second_application(engine):
     n = 14
     ops = circuits.random_circuit(n, 4, seed=9)
     reg, ora = _run(engine, n, ops, 21)
-    c0, l0 = reg.stat(STAT_JIT_COMPILES), reg.stat(STAT_JIT_LAUNCHES)
     reg.sync()
+    c0, l0 = reg.stat(STAT_JIT_COMPILES), reg.stat(STAT_JIT_LAUNCHES)
+    assert l0 >= 1
     reg.apply_batch([engine.Operation(m, t) for m, t in ops])
     for o in ops:
         ora.apply(o)
