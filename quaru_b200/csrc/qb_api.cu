@@ -172,13 +172,17 @@ static void reset_labels(Reg* r) {
 // relabelling, then the sharded placement is restored).
 static int canonical(Reg* r) {
     if (r->relabel) {
-        std::vector<uint32_t> pairs;
-        canonical_swaps(&r->label, &pairs);
+        // the swaps are derived on a COPY of the label map; the map itself becomes the identity only once the SWAP passes have
+        // been launched -- if the flush fails the labels still describe the resident layout (the gates stay dropped)
+        std::vector<uint32_t> pairs, label = r->label;
+        canonical_swaps(&label, &pairs);
         for (size_t i = 0; i + 1 < pairs.size(); i += 2) {
             Gate g;
             make_swap_gate(pairs[i], pairs[i + 1], &g);
             r->queue.push_back(std::move(g));
         }
+        QB_TRY(flush(r));
+        r->label = label;
     }
     QB_TRY(flush(r));
     if (r->world > 1) QB_TRY(shard_canonicalize(r));
@@ -420,6 +424,7 @@ int qb_load_state(qb_reg* reg, const char* path) try {
     CHECK_REG(reg);
     Reg* r = REG(reg);
     if (!path) return set_error(QB_ERR_INVALID_ARGUMENT, -1, "path is NULL");
+    QB_TRY(state_load_check(r, path));   // missing file / wrong register: nothing below happens, the handle is untouched
     r->queue.clear();  // the loaded image replaces whatever the pending gates would have produced
     r->held = 0;
     shard_reset_placement(r);  // files hold the identity placement
@@ -524,7 +529,7 @@ int qb_set_option(qb_reg* reg, int32_t option, int64_t value) try {
             r->jit_min_blocks = (int)(value & 15); r->jit_persistent = (int)((value >> 4) & 1); r->jit_prefetch = (int)((value >> 5) & 1);
             return QB_OK;
         case QB_OPT_FORCE_PATH:
-            if (value < 0 || value > 11) return set_error(QB_ERR_INVALID_ARGUMENT, value, "force path must be in [0, 11]");
+            if (value < 0 || value > 4) return set_error(QB_ERR_INVALID_ARGUMENT, value, "force path must be in [0, 4]");
             r->force_path = (int)value;
             return QB_OK;
     }

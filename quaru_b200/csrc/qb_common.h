@@ -137,6 +137,7 @@ int ensure_dmat(Reg* r, size_t bytes);
 // ---- raw state files (qb_stateio.cu); the caller has flushed the queue and restored the identity placement ------
 int state_save(Reg* r, const char* path);
 int state_load(Reg* r, const char* path);
+int state_load_check(Reg* r, const char* path);  // header validation only; the register is not touched
 
 // ---- fused tile passes (qb_tile.cu) ----------------------------------------------------------------
 int drain_tile_events(Reg* r);  // fold finished profiling events into st_tile_ns

@@ -326,15 +326,12 @@ struct Gen {
                 close();
                 break;
             case RC_TAB:
-            case RC_TAB_ACC:
-            case RC_TABW:
-            case RC_TABW_ACC: {
-                const bool wide = code == RC_TABW || code == RC_TABW_ACC;
-                const uint32_t sel[7] = {op.src[0], op.src[1], op.src[2], op.b, op.tmask & 0xffu, (uint32_t)op.tmask >> 8, op.rmask & 0xffu};
-                const std::string oc = cond_of(0, op.omask);   // tmask / rmask carry selectors here, not controls
+            case RC_TAB_ACC: {
+                const uint32_t sel[4] = {op.src[0], op.src[1], op.src[2], op.b};
+                const std::string oc = cond_of(0, op.omask);
                 if (op.k == 0) { tph_mul_lit(M[0], oc); break; }
                 std::string idx = std::to_string(op.mat) + "u";
-                for (int i = 0; i < (int)op.k && i < (wide ? 7 : 4); ++i) idx += " + " + sel_bit(sel[i], i);
+                for (int i = 0; i < (int)op.k && i < 4; ++i) idx += " + " + sel_bit(sel[i], i);
                 tph_mul_table(idx, oc);
             } break;
             case RC_LAYER: {
@@ -353,11 +350,6 @@ struct Gen {
                 const uint32_t s0 = op.src[0];
                 tph_mul_table(std::to_string(op.mat) + "u + " + sel_bit(s0, 0), c);
             } break;
-            case RC_RTAB:
-                open(cond_of(0, op.omask));
-                for (int j = 0; j < 16; ++j) cmul_reg_lit(j, M[j]);
-                close();
-                break;
             default: {   // RC_DG
                 uint32_t regmask[3] = {0, 0, 0};
                 std::string dyn;

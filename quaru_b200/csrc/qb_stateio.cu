@@ -155,19 +155,33 @@ int state_save(Reg* r, const char* path) {
     return QB_OK;
 }
 
+// Opens `path` and validates its header against the handle; nothing of the register is touched.
+static int open_and_check(Reg* r, const char* path, File* in, StateFileHeader* h) {
+    in->f = fopen(path, "rb");
+    if (!in->f) return io_error("cannot open", path);
+    if (fread(h, sizeof *h, 1, in->f) != 1) return set_error(QB_ERR_IO, 0, "%s: shorter than a state-file header", path);
+    if (memcmp(h->magic, kMagic, 8) != 0 || h->version != 1 || h->dtype != 0)
+        return set_error(QB_ERR_IO, 0, "%s: not a version-1 complex-f64 state file", path);
+    if (h->n != r->n || h->world != (uint32_t)r->world || h->rank != (uint32_t)r->rank || h->n_local != r->n_local ||
+        h->count != (1ull << r->n_local))
+        return set_error(QB_ERR_INVALID_ARGUMENT, h->n,
+                         "%s holds shard %u/%u of a %u-qubit register; this handle is shard %d/%d of %u qubits", path, h->rank,
+                         h->world, h->n, r->rank, r->world, r->n);
+    return QB_OK;
+}
+
+// qb_load_state calls this BEFORE it drops the gate queue and resets the qubit labels / placement: a missing file or a file
+// of another register leaves the handle exactly as it was.
+int state_load_check(Reg* r, const char* path) {
+    File in;
+    StateFileHeader h;
+    return open_and_check(r, path, &in, &h);
+}
+
 int state_load(Reg* r, const char* path) {
     File in;
-    in.f = fopen(path, "rb");
-    if (!in.f) return io_error("cannot open", path);
     StateFileHeader h;
-    if (fread(&h, sizeof h, 1, in.f) != 1) return set_error(QB_ERR_IO, 0, "%s: shorter than a state-file header", path);
-    if (memcmp(h.magic, kMagic, 8) != 0 || h.version != 1 || h.dtype != 0)
-        return set_error(QB_ERR_IO, 0, "%s: not a version-1 complex-f64 state file", path);
-    if (h.n != r->n || h.world != (uint32_t)r->world || h.rank != (uint32_t)r->rank || h.n_local != r->n_local ||
-        h.count != (1ull << r->n_local))
-        return set_error(QB_ERR_INVALID_ARGUMENT, h.n,
-                         "%s holds shard %u/%u of a %u-qubit register; this handle is shard %d/%d of %u qubits", path, h.rank,
-                         h.world, h.n, r->rank, r->world, r->n);
+    QB_TRY(open_and_check(r, path, &in, &h));
 
     const size_t total = (size_t)h.count * sizeof(c64);
     const size_t chunk = std::min(kChunkBytes, total);

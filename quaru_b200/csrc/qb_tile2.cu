@@ -57,11 +57,8 @@ static bool is_x(const Gate& g) {
 // tries all three and keeps the shortest program.
 template <class Prog>
 static bool encode_rounds_with(const std::vector<Gate>& gates, const std::vector<size_t>& gate_idx, const std::vector<uint32_t>& tile_pos,
-                               uint32_t lc, Prog* prog, int mode, int extras) {
-    // extras: 0 = the ops of the default kernel only; 4..7 = the experimental ops of the persistent kernels as well: RC_RTAB, and
-    // merged phase tables over up to `extras` selector bits (RC_TABW above 4)
-    const bool allow_rtab = extras != 0;
-    const size_t max_sel = extras > 4 ? (size_t)extras : 4;
+                               uint32_t lc, Prog* prog, int mode) {
+    const size_t max_sel = 4;   // selector bits of a merged per-thread phase table
     const uint32_t T = (uint32_t)tile_pos.size();
     if (T != RT) return false;
     int8_t local_of[64];
@@ -298,65 +295,6 @@ static bool encode_rounds_with(const std::vector<Gate>& gates, const std::vector
                 out.push_back(in[i]);
             }
             for (int b = 0; b < 4; ++b) emit_group(b);
-            // Experimental (kernels with RC_RTAB only): the unconditional phases on register bits that are left (relative
-            // phases of RZ gates, CZ between register bits, the same under one outer control) are merged into register-indexed
-            // tables.  A later phase may join an earlier one if nothing in between writes one of its bits; merging pays when
-            // the ops saved outweigh the 16 complex multiplies of the table (~40 FP64 instructions of overhead per op).
-            if (allow_rtab) {
-                struct Group { uint64_t omask; uint32_t written; std::vector<size_t> members; };
-                std::vector<Group> groups;
-                auto dense_writes = [](const ROp& o) -> uint32_t {
-                    const int c = o.code;
-                    if (c == RC_D2) return (1u << o.a) | (1u << o.b);
-                    if (c >= RC_H && c < RC_H + 4) return 1u << (c - RC_H);
-                    const bool diag1 = (c >= RC_DG1R && c < RC_DG1R + 4) || (c >= RC_DG1R_P && c < RC_DG1R_P + 4);
-                    if (c < RC_D2 && !diag1) return 1u << (c & 3);
-                    return 0;
-                };
-                for (size_t i = 0; i < out.size(); ++i) {
-                    const ROp& o = out[i];
-                    if ((o.code == RC_PH_R || o.code == RC_PH_NEG) && o.tmask == 0 && o.rmask != 0) {
-                        bool placed = false;
-                        for (Group& g : groups)
-                            if (g.omask == o.omask && !(g.written & o.rmask)) { g.members.push_back(i); placed = true; break; }
-                        if (!placed) groups.push_back(Group{o.omask, 0u, {i}});
-                        continue;
-                    }
-                    const uint32_t w = dense_writes(o);
-                    for (Group& g : groups) g.written |= w;
-                }
-                std::vector<char> drop(out.size(), 0);
-                for (const Group& g : groups) {
-                    if (g.members.size() < 2 || n_mats + 16 > max_mats) continue;
-                    int fp = 0;
-                    for (size_t i : g.members) {
-                        const int regs = 16 >> __builtin_popcount(out[i].rmask);
-                        fp += (out[i].code == RC_PH_R ? 4 : 2) * regs;
-                    }
-                    if ((int)(g.members.size() - 1) * 40 <= 64 - fp) continue;
-                    c64 T[16];
-                    for (int j = 0; j < 16; ++j) T[j] = make_double2(1.0, 0.0);
-                    for (size_t i : g.members) {
-                        const c64 f = prog->mats[out[i].mat];
-                        for (uint32_t j = 0; j < 16; ++j)
-                            if ((j & out[i].rmask) == out[i].rmask) T[j] = make_double2(T[j].x * f.x - T[j].y * f.y, T[j].x * f.y + T[j].y * f.x);
-                    }
-                    ROp t;
-                    memset(&t, 0, sizeof(t));
-                    t.code = RC_RTAB;
-                    t.omask = g.omask;
-                    for (size_t i : g.members) t.a |= (uint8_t)out[i].rmask;   // register bits the table depends on (host bookkeeping only)
-                    t.mat = (uint32_t)n_mats;
-                    memcpy(prog->mats + n_mats, T, sizeof(T));
-                    n_mats += 16;
-                    out[g.members[0]] = t;
-                    for (size_t m = 1; m < g.members.size(); ++m) drop[g.members[m]] = 1;
-                }
-                std::vector<ROp> kept;
-                for (size_t i = 0; i < out.size(); ++i)
-                    if (!drop[i]) kept.push_back(out[i]);
-                out.swap(kept);
-            }
             // Second pass: every thread-uniform phase (RC_PH_T, RC_DG1T, RC_PH_ACC) is a function of a few thread / outer
             // bits.  They all commute, so they are multiplied together on the host into tables over <= 4 selector bits:
             // one table op replaces several ops (each op costs ~25 instructions of decode for 4 FP64 instructions of work).
@@ -412,15 +350,11 @@ static bool encode_rounds_with(const std::vector<Gate>& gates, const std::vector
                     if (n_mats + t.tab.size() > max_mats) { overflow = true; return; }
                     ROp o;
                     memset(&o, 0, sizeof(o));
-                    const bool wide = t.sel.size() > 4;
-                    o.code = wide ? (code == RC_TAB ? RC_TABW : RC_TABW_ACC) : code;
+                    o.code = code;
                     o.k = (uint8_t)t.sel.size();
                     for (size_t i = 0; i < t.sel.size(); ++i) {
                         if (i < 3) o.src[i] = t.sel[i];
-                        else if (i == 3) o.b = t.sel[i];
-                        else if (i == 4) o.tmask |= t.sel[i];
-                        else if (i == 5) o.tmask |= (uint16_t)(t.sel[i] << 8);
-                        else o.rmask = t.sel[i];
+                        else o.b = t.sel[i];
                     }
                     o.mat = (uint32_t)n_mats;
                     memcpy(prog->mats + n_mats, t.tab.data(), t.tab.size() * sizeof(c64));
@@ -461,7 +395,6 @@ static bool encode_rounds_with(const std::vector<Gate>& gates, const std::vector
                     if (c < RC_D2) return (1u << (c & 3)) | o.rmask;                  // D1C / D1R / DG1R and predicated forms
                     if (c == RC_D2) return (1u << o.a) | (1u << o.b) | o.rmask;
                     if (c == RC_PH_NEG || c == RC_PH_R) return o.rmask;
-                    if (c == RC_RTAB) return o.a;
                     if (c >= RC_PH_FLUSH && c < RC_PH_FLUSH + 4) return 1u << (c - RC_PH_FLUSH);
                     if (c >= RC_H && c < RC_H + 4) return 1u << (c - RC_H);
                     if (c == RC_DG) {
@@ -685,7 +618,7 @@ static bool encode_rounds_with(const std::vector<Gate>& gates, const std::vector
         bool absorbed = false;   // ... by a per-thread table that round already has (its entries are scaled), ...
         for (uint32_t oi = last.op_begin; oi < last.op_end && !absorbed; ++oi) {
             const ROp& t = prog->ops[oi];
-            if (t.code != RC_TAB && t.code != RC_TABW) continue;
+            if (t.code != RC_TAB) continue;
             for (uint32_t e = 0; e < (1u << t.k); ++e) {
                 c64& v = prog->mats[t.mat + e];
                 v = make_double2(v.x * pass_scalar.x - v.y * pass_scalar.y, v.x * pass_scalar.y + v.y * pass_scalar.x);
@@ -730,25 +663,18 @@ static bool thorough_encoding(uint32_t n_local) {
 
 template <class Prog>
 static bool encode_rounds(const std::vector<Gate>& gates, const std::vector<size_t>& gate_idx, const std::vector<uint32_t>& tile_pos,
-                          uint32_t lc, Prog* prog, bool thorough, bool allow_rtab) {
+                          uint32_t lc, Prog* prog, bool thorough) {
     static thread_local Prog other;
     auto n_ops = [](const Prog& p) { return p.rounds[p.n_rounds - 1].op_end; };
-    // The experimental ops trade coefficient space for op count (a table over 7 selector bits has 128 entries): take the widest
-    // tables that still fit the pass, down to the default kernel's op set.
-    static const int kLevels[5] = {7, 6, 5, 4, 0};
-    for (int li = allow_rtab ? 0 : 4; li < 5; ++li) {
-        const int extras = kLevels[li];
-        bool have = encode_rounds_with(gates, gate_idx, tile_pos, lc, prog, 0, extras);
-        for (int mode = 1; thorough && mode <= 2; ++mode) {
-            if (!encode_rounds_with(gates, gate_idx, tile_pos, lc, &other, mode, extras)) continue;
-            if (!have || other.n_rounds < prog->n_rounds || (other.n_rounds == prog->n_rounds && n_ops(other) < n_ops(*prog))) {
-                *prog = other;
-                have = true;
-            }
+    bool have = encode_rounds_with(gates, gate_idx, tile_pos, lc, prog, 0);
+    for (int mode = 1; thorough && mode <= 2; ++mode) {
+        if (!encode_rounds_with(gates, gate_idx, tile_pos, lc, &other, mode)) continue;
+        if (!have || other.n_rounds < prog->n_rounds || (other.n_rounds == prog->n_rounds && n_ops(other) < n_ops(*prog))) {
+            *prog = other;
+            have = true;
         }
-        if (have) return true;
     }
-    return false;
+    return have;
 }
 
 template <class Prog>
@@ -794,10 +720,14 @@ static int launch_rpass_remote(Reg* r, const Prog& prog, uint32_t n_virtual, c64
     for (uint32_t j = 0; j < prog.h; ++j) in_tile += prog.hp[j] >= r->n_local;
     const uint64_t tiles = 1ull << (r->n_local - RT);
     if (tiles > 0x7fffffffull) return set_error(QB_ERR_UNSUPPORTED, (int64_t)tiles, "too many tiles for one grid");
-    if (r->profile) QB_TRY(tile_profile_begin(r));
-    k2r_tile_pass_remote<Prog><<<(unsigned)tiles, RTHREADS, sizeof(c64) << RT, r->stream>>>(ra, prog);
-    QB_CUDA(cudaGetLastError());
-    if (r->profile) QB_TRY(tile_profile_end(r));
+    bool jitted = false;   // the specialised kernel of this pass (same generator, amplitudes addressed through `ra.base`)
+    QB_TRY(jit_try_launch(r, make_view(prog), &ra, &jitted));
+    if (!jitted) {
+        if (r->profile) QB_TRY(tile_profile_begin(r));
+        k2r_tile_pass_remote<Prog><<<(unsigned)tiles, RTHREADS, sizeof(c64) << RT, r->stream>>>(ra, prog);
+        QB_CUDA(cudaGetLastError());
+        if (r->profile) QB_TRY(tile_profile_end(r));
+    }
     r->st_launches++;
     r->st_passes++;
     r->st_rounds += prog.n_rounds;
@@ -805,37 +735,6 @@ static int launch_rpass_remote(Reg* r, const Prog& prog, uint32_t n_virtual, c64
     // NVLink accounting: what this rank stores into peers' shards (it loads as much from them)
     r->st_swap_bytes += (int64_t)((16ull << r->n_local) - ((16ull << r->n_local) >> in_tile));
     r->st_remote_passes += in_tile > 0;
-    return QB_OK;
-}
-
-// Experimental (QB_OPT_FORCE_PATH = 5..11): persistent CTAs with the coefficient tables staged in shared memory;
-// 6, 8, 10 also stage the op records, 7 and 8 prefetch the next tile into L2, 9 and 10 fetch op records one op ahead, 11 does all three.
-template <class Prog, bool STAGE_OPS, bool PREFETCH, bool AHEAD>
-static int launch_rpass_persist(Reg* r, const Prog& prog) {
-    const uint32_t n_ops = prog.rounds[prog.n_rounds - 1].op_end;
-    const size_t smem = (sizeof(c64) << RT) + (size_t)prog.n_mats * sizeof(c64) + (STAGE_OPS ? (size_t)n_ops * sizeof(SOp) : 0);
-    static std::atomic<uint64_t> attr_devs{0};
-    if (!((attr_devs.load() >> (r->device & 63)) & 1)) {
-        QB_CUDA(cudaFuncSetAttribute(k2r_tile_pass_persist<Prog, STAGE_OPS, PREFETCH, AHEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)((sizeof(c64) << RT) + sizeof(prog.mats) + sizeof(prog.ops))));
-        attr_devs.fetch_or(1ull << (r->device & 63));
-    }
-    const uint64_t tiles = 1ull << (r->n_local - RT);
-    if (tiles > 0x7fffffffull) return set_error(QB_ERR_UNSUPPORTED, (int64_t)tiles, "too many tiles for one grid");
-    int sms = 148;
-    QB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, r->device));
-    int per_sm = 0;
-    QB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2r_tile_pass_persist<Prog, STAGE_OPS, PREFETCH, AHEAD>, RTHREADS, smem));
-    if (per_sm < 1) return set_error(QB_ERR_UNSUPPORTED, -1, "persistent tile kernel does not fit an SM");
-    const unsigned grid = (unsigned)std::min<uint64_t>(tiles, (uint64_t)sms * (uint64_t)per_sm);
-    if (r->profile) QB_TRY(tile_profile_begin(r));
-    k2r_tile_pass_persist<Prog, STAGE_OPS, PREFETCH, AHEAD><<<grid, RTHREADS, smem, r->stream>>>(r->state, prog, (uint32_t)tiles, prog.n_mats, n_ops);
-    QB_CUDA(cudaGetLastError());
-    if (r->profile) QB_TRY(tile_profile_end(r));
-    r->st_launches++;
-    r->st_passes++;
-    r->st_rounds += prog.n_rounds;
-    r->st_bytes += (int64_t)(32ull << r->n_local);
     return QB_OK;
 }
 
@@ -847,7 +746,7 @@ int64_t encode_rounds_debug(uint32_t n_local, const std::vector<Gate>& gates, co
     if (tile_pos.size() != RT) return 0;
     static thread_local RProgLarge prog;
     memset(&prog, 0, sizeof(prog));
-    if (!encode_rounds(gates, gate_idx, tile_pos, lc, &prog, thorough_encoding(n_local), getenv("QB_TILE_RTAB") != nullptr)) return 0;
+    if (!encode_rounds(gates, gate_idx, tile_pos, lc, &prog, thorough_encoding(n_local))) return 0;
     const uint32_t n_rounds = prog.n_rounds, n_ops = prog.rounds[n_rounds - 1].op_end;
     uint32_t n_mats = 4;
     for (uint32_t i = 0; i < n_ops; ++i) {   // the encoder does not keep the table count: recover an upper bound per op
@@ -855,9 +754,8 @@ int64_t encode_rounds_debug(uint32_t n_local, const std::vector<Gate>& gates, co
         uint32_t len = 4;
         if (o.code == RC_D2) len = 16;
         else if (o.code == RC_DG) len = 1u << o.k;
-        else if (o.code == RC_TAB || o.code == RC_TAB_ACC || o.code == RC_TABW || o.code == RC_TABW_ACC) len = 1u << o.k;
+        else if (o.code == RC_TAB || o.code == RC_TAB_ACC) len = 1u << o.k;
         else if (o.code == RC_LAYER) len = 8;
-        else if (o.code == RC_RTAB) len = 16;
         n_mats = std::max(n_mats, o.mat + len);
     }
     n_mats = std::min<uint32_t>(n_mats, sizeof(prog.mats) / sizeof(c64));
@@ -876,20 +774,6 @@ int64_t encode_rounds_debug(uint32_t n_local, const std::vector<Gate>& gates, co
     return (int64_t)(w - out);
 }
 
-template <class Prog>
-static int launch_variant(Reg* r, const Prog& prog) {
-    switch (r->force_path) {
-        case 5: return launch_rpass_persist<Prog, false, false, false>(r, prog);
-        case 6: return launch_rpass_persist<Prog, true, false, false>(r, prog);
-        case 7: return launch_rpass_persist<Prog, false, true, false>(r, prog);
-        case 8: return launch_rpass_persist<Prog, true, true, false>(r, prog);
-        case 9: return launch_rpass_persist<Prog, false, false, true>(r, prog);
-        case 10: return launch_rpass_persist<Prog, true, false, true>(r, prog);
-        case 11: return launch_rpass_persist<Prog, true, true, true>(r, prog);
-        default: return launch_rpass(r, prog);
-    }
-}
-
 // returns QB_OK and *handled = true if the pass went through the register-blocked kernel
 int run_pass_v2(Reg* r, const std::vector<Gate>& gates, const std::vector<size_t>& gate_idx, const std::vector<uint32_t>& tile_pos,
                 uint32_t lc, bool* handled) {
@@ -899,17 +783,15 @@ int run_pass_v2(Reg* r, const std::vector<Gate>& gates, const std::vector<size_t
     for (size_t gi : gate_idx) mats += gates[gi].matrix.size();
     if (gate_idx.size() <= 20 && mats <= 150) {
         RProgSmall small;
-        const bool rtab = r->force_path >= 5 && getenv("QB_TILE_RTAB") != nullptr;   // only the persistent kernels implement RC_RTAB
-        if (encode_rounds(gates, gate_idx, tile_pos, lc, &small, thorough_encoding(r->n_local), rtab)) {
+        if (encode_rounds(gates, gate_idx, tile_pos, lc, &small, thorough_encoding(r->n_local))) {
             *handled = true;
-            return launch_variant(r, small);
+            return launch_rpass(r, small);
         }
     }
     static thread_local RProgLarge large;
-    if (!encode_rounds(gates, gate_idx, tile_pos, lc, &large, thorough_encoding(r->n_local), r->force_path >= 5 && getenv("QB_TILE_RTAB") != nullptr))
-        return QB_OK;
+    if (!encode_rounds(gates, gate_idx, tile_pos, lc, &large, thorough_encoding(r->n_local))) return QB_OK;
     *handled = true;
-    return launch_variant(r, large);
+    return launch_rpass(r, large);
 }
 
 // Sharded registers (qb_shard.cu, QB_SHARD_REMOTE=1): one pass over the virtual register of n_virtual = n_local + g bits.
@@ -923,13 +805,13 @@ int run_pass_remote(Reg* r, uint32_t n_virtual, const std::vector<Gate>& gates, 
     for (size_t gi : gate_idx) mats += gates[gi].matrix.size();
     if (gate_idx.size() <= 20 && mats <= 150) {
         RProgSmall small;
-        if (encode_rounds(gates, gate_idx, tile_pos, lc, &small, thorough_encoding(n_virtual), false)) {
+        if (encode_rounds(gates, gate_idx, tile_pos, lc, &small, thorough_encoding(n_virtual))) {
             *handled = true;
             return launch_rpass_remote(r, small, n_virtual, bases);
         }
     }
     static thread_local RProgLarge large;
-    if (!encode_rounds(gates, gate_idx, tile_pos, lc, &large, thorough_encoding(n_virtual), false)) return QB_OK;
+    if (!encode_rounds(gates, gate_idx, tile_pos, lc, &large, thorough_encoding(n_virtual))) return QB_OK;
     *handled = true;
     return launch_rpass_remote(r, large, n_virtual, bases);
 }

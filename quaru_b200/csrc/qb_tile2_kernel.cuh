@@ -18,11 +18,7 @@ enum RCode : uint8_t {
     RC_PH_ACC = 44,                                // phase whose only register-bit control is one bit: accumulate per thread ...
     RC_PH_FLUSH = 48,                              // + register bit: ... and apply the product to the 8 registers with that bit set
     RC_TAB = 52, RC_TAB_ACC = 53,                  // merged thread-uniform phases: table over <= 4 thread / outer bits -> tph
-    RC_LAYER = 54,                                 // up to four real 2x2 gates, one per register bit, decoded once
-    RC_RTAB = 55,                                  // experimental (persistent kernels only): unconditional diagonal over the register
-                                                   // bits, register j is multiplied by the j-th of 16 coefficients
-    RC_TABW = 56, RC_TABW_ACC = 57                 // experimental (persistent kernels only): RC_TAB / RC_TAB_ACC with 5..7 selector bits
-                                                   // (selectors 4, 5 in tmask's bytes, selector 6 in rmask): one op where two were needed
+    RC_LAYER = 54                                  // up to four real 2x2 gates, one per register bit, decoded once
 };
 
 struct ROp {
@@ -49,7 +45,7 @@ struct RoundDesc {
 
 template <int NOPS, int NMAT, int NROUNDS>
 struct RProgram {
-    uint32_t lc, h, n_rounds, n_mats;   // n_mats: coefficients in use (what the persistent kernel stages in shared memory)
+    uint32_t lc, h, n_rounds, n_mats;   // n_mats: coefficients in use
     uint8_t hp[8];
     uint64_t gro_first[16], gro_last[16];  // offset from the tile base of register j in the first / last round
     RoundDesc rounds[NROUNDS];
@@ -275,46 +271,14 @@ __device__ __forceinline__ void r_d2_dispatch(c64 (&v)[16], const c64* M, uint32
     }
 }
 
-// Compact op record of the persistent kernels: the 24-byte ROp packed into one 128-bit word (one LDS.128 / four registers to
-// carry a record one op ahead), decoded with shifts and masks at the point of use.  Byte fields copied as a struct made ptxas
-// spill them one by one (ten STL.S16 / LDL.S16 / PRMT triples per op in the first version of the one-op-ahead kernels).
-struct __align__(16) SOp {
-    uint32_t x0;   // code | k << 8 | mat << 16 (12 bits) | a << 28
-    uint32_t x1;   // tmask | rmask << 16
-    uint32_t x2;   // src[0] | src[1] << 8 | src[2] << 16 | b << 24
-    uint32_t x3;   // omask (tile indices have fewer than 32 bits)
-};
-__device__ __forceinline__ SOp sop_pack(const ROp& o) {
-    SOp s;
-    s.x0 = (uint32_t)o.code | ((uint32_t)o.k << 8) | ((o.mat & 0xfffu) << 16) | (((uint32_t)o.a & 0xfu) << 28);
-    s.x1 = (uint32_t)o.tmask | ((uint32_t)o.rmask << 16);
-    s.x2 = (uint32_t)o.src[0] | ((uint32_t)o.src[1] << 8) | ((uint32_t)o.src[2] << 16) | ((uint32_t)o.b << 24);
-    s.x3 = (uint32_t)o.omask;
-    return s;
-}
-// an opaque copy: what is derived from it cannot be merged with (and hoisted next to) what is derived from the original
-__device__ __forceinline__ SOp sop_launder(SOp s) {
-#ifndef QB_HOST_EMU
-    asm volatile("" : "+r"(s.x0), "+r"(s.x1), "+r"(s.x2), "+r"(s.x3));
-#endif
-    return s;
-}
-struct SOpView {   // the field names of ROp, as values
-    uint32_t code, k, mat, a, b, tmask, rmask, src[3];
-    uint64_t omask;
-    __device__ __forceinline__ explicit SOpView(const SOp& s)
-        : code(s.x0 & 0xffu), k((s.x0 >> 8) & 0xffu), mat((s.x0 >> 16) & 0xfffu), a(s.x0 >> 28), b(s.x2 >> 24), tmask(s.x1 & 0xffffu),
-          rmask(s.x1 >> 16), src{s.x2 & 0xffu, (s.x2 >> 8) & 0xffu, (s.x2 >> 16) & 0xffu}, omask(s.x3) {}
-};
-
 #ifdef QB_HOST_EMU
 #define QB_DYNAMIC_SMEM(name) unsigned char* name = qb_emu_shared()
 #else
 #define QB_DYNAMIC_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
 #endif
 
-// One CTA per tile; coefficients are read from the kernel-parameter (constant) bank.  Every measurement so far was taken
-// with this kernel.
+// The interpreter kernel: one CTA per tile, the pass program in the kernel-parameter (constant) bank.  It runs a pass until
+// (or unless) the pass's specialised kernel is available (qb_jit.cu), and every pass of registers too small to be worth a compile.
 template <class Prog>
 __global__ void __launch_bounds__(RTHREADS, 2) k2r_tile_pass(c64* __restrict__ st, const __grid_constant__ Prog prog) {
     QB_DYNAMIC_SMEM(smem_raw);
@@ -322,94 +286,10 @@ __global__ void __launch_bounds__(RTHREADS, 2) k2r_tile_pass(c64* __restrict__ s
 #define QB_TILE_IX blockIdx.x
 #define QB_AMP(off) (st + (off))
 #define QB_MATS prog.mats
-#define QB_BEFORE_OPS
-#define QB_FETCH_OP const ROp& op = prog.ops[oi];
-#define QB_AFTER_FIRST_LOADS
-#define QB_EXTRA_CASES
-#define QB_CASE_OP
-#include "qb_tile2_body.inc"
-#undef QB_CASE_OP
-#undef QB_TILE_IX
-#undef QB_AMP
-#undef QB_MATS
-#undef QB_BEFORE_OPS
-#undef QB_FETCH_OP
-#undef QB_AFTER_FIRST_LOADS
-#undef QB_EXTRA_CASES
-}
-
-// Experimental persistent variants (QB_OPT_FORCE_PATH = 5..8, not yet measured on hardware): grid = resident CTAs; each CTA
-// stages the coefficient tables of the pass in shared memory once (behind the 64 KB transpose buffer), where
-// per-thread-indexed reads are not serialised like divergent constant-bank reads, and then walks tiles blockIdx.x,
-// blockIdx.x + gridDim.x, ...   STAGE_OPS also stages the op records; PREFETCH asks L2 for the next tile's lines as soon as
-// the current tile's loads have been issued, so that the next round-0 loads find them there; AHEAD fetches each op record
-// one op before its use.
-// Within a tile the transpose buffer is last read before a __syncthreads() (second barrier of a transpose), so the next
-// tile's first transpose store needs no extra barrier.
-// Op records reach the op loop as compact 128-bit words (SOp): from shared memory (STAGE_OPS) or packed on the fly from the
-// kernel-parameter bank.
-template <class Prog, bool STAGE_OPS, bool PREFETCH, bool AHEAD>
-__global__ void __launch_bounds__(RTHREADS, 2) k2r_tile_pass_persist(c64* __restrict__ st, const __grid_constant__ Prog prog, uint32_t n_tiles,
-                                                                     uint32_t n_mats, uint32_t n_ops) {
-    QB_DYNAMIC_SMEM(smem_raw);
-    c64* tile = reinterpret_cast<c64*>(smem_raw);
-    c64* s_mats = tile + (1u << RT);
-    SOp* s_ops = reinterpret_cast<SOp*>(s_mats + n_mats);   // 16-byte aligned
-    for (uint32_t i = threadIdx.x; i < n_mats; i += RTHREADS) s_mats[i] = prog.mats[i];
-    if (STAGE_OPS)
-        for (uint32_t i = threadIdx.x; i < n_ops; i += RTHREADS) s_ops[i] = sop_pack(prog.ops[i]);
-    __syncthreads();
-    for (uint32_t tile_ix = blockIdx.x; tile_ix < n_tiles; tile_ix += gridDim.x) {
-#define QB_TILE_IX tile_ix
-#define QB_AMP(off) (st + (off))
-#define QB_MATS s_mats
-#define QB_OPS(i) (STAGE_OPS ? s_ops[i] : sop_pack(prog.ops[i]))
-    /* AHEAD: the record of op oi+1 is requested before op oi is executed, so the decode chain of the next op (record ->   \
-       compare / branch -> coefficients) starts from registers instead of from a load */                                    \
-#define QB_BEFORE_OPS SOp w_next = {0u, 0u, 0u, 0u}; if (AHEAD && rd.op_begin < rd.op_end) w_next = QB_OPS(rd.op_begin);
-#define QB_FETCH_OP                                                        \
-    SOp w_cur;                                                             \
-    if (AHEAD) { w_cur = w_next; if (oi + 1 < rd.op_end) w_next = QB_OPS(oi + 1); } else { w_cur = QB_OPS(oi); } \
-    const SOpView op(w_cur);
-#define QB_CASE_OP const SOpView op(sop_launder(w_cur));
-#define QB_AFTER_FIRST_LOADS                                                                         \
-    if (PREFETCH) {                                                                                  \
-        const uint32_t next_ix = tile_ix + gridDim.x;                                                \
-        if (next_ix < n_tiles && (tid & 7u) == 0u) { /* lanes are tile bits 0..4: one thread per 128-byte line */ \
-            uint64_t nb = (uint64_t)next_ix << lc;                                                   \
-            for (uint32_t j = 0; j < h; ++j) nb = insert_zero_bit(nb, prog.hp[j]);                   \
-            const uint64_t ngt = nb + goff(tl);                                                      \
-            _Pragma("unroll") for (int j = 0; j < 16; ++j) prefetch_l2(st + (ngt + prog.gro_first[j])); \
-        }                                                                                            \
-    }
-#define QB_EXTRA_CASES                                                                    \
-    case RC_RTAB: {                                                                       \
-        const c64* T = QB_MATS + op.mat;                                                  \
-        _Pragma("unroll") for (int j = 0; j < 16; ++j) ip_cmul(v[j], T[j]);               \
-    } break;                                                                              \
-    case RC_TABW:                                                                         \
-    case RC_TABW_ACC: {                                                                   \
-        QB_CASE_OP                                                                        \
-        const uint32_t wsel[7] = {op.src[0], op.src[1], op.src[2], op.b, op.tmask & 0xffu, (uint32_t)op.tmask >> 8, op.rmask & 0xffu}; \
-        uint32_t widx = 0;                                                                \
-        _Pragma("unroll") for (int i = 0; i < 7; ++i) {                                   \
-            if (i >= op.k) break;                                                         \
-            const uint32_t sc = wsel[i];                                                  \
-            widx |= (((sc & 0x80) ? (QB_TILE_IX >> (sc & 0x3f)) : (tl >> (sc & 0x3f))) & 1u) << i; \
-        }                                                                                 \
-        ip_cmul(tph, QB_MATS[op.mat + widx]);                                             \
-    } break;
 #include "qb_tile2_body.inc"
 #undef QB_TILE_IX
 #undef QB_AMP
 #undef QB_MATS
-#undef QB_OPS
-#undef QB_CASE_OP
-#undef QB_BEFORE_OPS
-#undef QB_FETCH_OP
-#undef QB_AFTER_FIRST_LOADS
-#undef QB_EXTRA_CASES
-    }
 }
 
 // ---- sharded registers: a tile pass whose tile may contain RANK bits (experimental, QB_SHARD_REMOTE=1) --------------------
@@ -458,20 +338,10 @@ __global__ void __launch_bounds__(RTHREADS, 2) k2r_tile_pass_remote(const __grid
 #define QB_TILE_IX tile_ix
 #define QB_AMP(off) remote_amp(ra, lmask, (off))
 #define QB_MATS prog.mats
-#define QB_BEFORE_OPS
-#define QB_FETCH_OP const ROp& op = prog.ops[oi];
-#define QB_AFTER_FIRST_LOADS
-#define QB_EXTRA_CASES
-#define QB_CASE_OP
 #include "qb_tile2_body.inc"
-#undef QB_CASE_OP
 #undef QB_TILE_IX
 #undef QB_AMP
 #undef QB_MATS
-#undef QB_BEFORE_OPS
-#undef QB_FETCH_OP
-#undef QB_AFTER_FIRST_LOADS
-#undef QB_EXTRA_CASES
 }
 
 }  // namespace qb

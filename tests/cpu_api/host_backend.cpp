@@ -165,3 +165,12 @@ int64_t shard_plan_debug(uint32_t, int, int, std::vector<Gate>&, int32_t*, uint6
 extern "C" int64_t qb_jit_source_debug(const void*, uint64_t, int32_t, int32_t, int32_t, int32_t, char*, uint64_t) { return qb::set_error(QB_ERR_UNSUPPORTED, -1, "host stand-in"); }
 extern "C" int64_t qb_jit_compile_debug(const char*, double*, void*, uint64_t) { return qb::set_error(QB_ERR_UNSUPPORTED, -1, "host stand-in"); }
 extern "C" int qb_jit_drain(void) { return QB_OK; }
+
+namespace qb {
+int state_load_check(Reg*, const char* path) {   // the host stand-in's files have no header: existence is all there is to check
+    FILE* f = fopen(path, "rb");
+    if (!f) return set_error(QB_ERR_IO, -1, "cannot open %s", path);
+    fclose(f);
+    return QB_OK;
+}
+}  // namespace qb

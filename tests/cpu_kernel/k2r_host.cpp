@@ -63,56 +63,6 @@ static void run_grid(double* state, uint32_t n_tiles, const Prog& prog) {
     pthread_barrier_destroy(&qb_emu_barrier);
 }
 
-template <class Prog, bool STAGE_OPS, bool PREFETCH, bool AHEAD>
-static void run_grid_persist(double* state, uint32_t n_tiles, uint32_t grid, const Prog& prog) {
-    blockDim = {RTHREADS, 1, 1};
-    gridDim = {grid, 1, 1};
-    pthread_barrier_init(&qb_emu_barrier, nullptr, RTHREADS);
-    std::vector<std::thread> threads;
-    for (unsigned t = 0; t < RTHREADS; ++t)
-        threads.emplace_back([=, &prog]() {
-            for (unsigned b = 0; b < grid; ++b) {   // the resident CTAs, one after the other
-                threadIdx = {t, 0, 0};
-                blockIdx = {b, 0, 0};
-                k2r_tile_pass_persist<Prog, STAGE_OPS, PREFETCH, AHEAD>(reinterpret_cast<c64*>(state), prog, n_tiles, prog.n_mats,
-                                                                 prog.rounds[prog.n_rounds - 1].op_end);
-                pthread_barrier_wait(&qb_emu_barrier);
-            }
-        });
-    for (std::thread& th : threads) th.join();
-    pthread_barrier_destroy(&qb_emu_barrier);
-}
-
-template <class Prog>
-static void run_variant(double* state, uint32_t n_tiles, uint32_t grid, const Prog& prog, int variant) {
-    switch (variant) {   // numbering of QB_OPT_FORCE_PATH
-        case 5: run_grid_persist<Prog, false, false, false>(state, n_tiles, grid, prog); break;
-        case 6: run_grid_persist<Prog, true, false, false>(state, n_tiles, grid, prog); break;
-        case 7: run_grid_persist<Prog, false, true, false>(state, n_tiles, grid, prog); break;
-        case 8: run_grid_persist<Prog, true, true, false>(state, n_tiles, grid, prog); break;
-        case 9: run_grid_persist<Prog, false, false, true>(state, n_tiles, grid, prog); break;
-        case 10: run_grid_persist<Prog, true, false, true>(state, n_tiles, grid, prog); break;
-        default: run_grid_persist<Prog, true, true, true>(state, n_tiles, grid, prog); break;
-    }
-}
-
-// the experimental persistent kernels (variant = the QB_OPT_FORCE_PATH value, 5..11) with `grid` CTAs walking the tiles
-extern "C" int k2r_host_run_persist(double* state, uint32_t n, const unsigned char* program, uint64_t len, int use_small, uint32_t grid,
-                                    int variant) {
-    if (n < RT || grid < 1 || variant < 5 || variant > 11) return -1;
-    const uint32_t n_tiles = 1u << (n - RT);
-    if (use_small) {
-        static RProgSmall small;
-        if (!deserialise(program, len, &small)) return -2;
-        run_variant(state, n_tiles, grid, small, variant);
-    } else {
-        static RProgLarge large;
-        if (!deserialise(program, len, &large)) return -2;
-        run_variant(state, n_tiles, grid, large, variant);
-    }
-    return 0;
-}
-
 extern "C" int k2r_host_run(double* state, uint32_t n, const unsigned char* program, uint64_t len, int use_small) {
     if (n < RT) return -1;
     const uint32_t n_tiles = 1u << (n - RT);

@@ -17,7 +17,7 @@ import numpy as np
 RC_D1C, RC_D1R, RC_DG1R = 0, 4, 8
 RC_D1C_P, RC_D1R_P, RC_DG1R_P = 16, 20, 24
 RC_D2, RC_PH_T, RC_PH_NEG, RC_PH_R, RC_DG, RC_DG1T = 32, 33, 34, 35, 36, 37
-RC_H, RC_PH_ACC, RC_PH_FLUSH, RC_TAB, RC_TAB_ACC, RC_LAYER, RC_RTAB, RC_TABW, RC_TABW_ACC = 40, 44, 48, 52, 53, 54, 55, 56, 57
+RC_H, RC_PH_ACC, RC_PH_FLUSH, RC_TAB, RC_TAB_ACC, RC_LAYER = 40, 44, 48, 52, 53, 54
 
 ROP_FMT = "<BBBBHHI3sBQ"          # code a b flags rmask tmask mat src[3] k omask   (24 bytes)
 ROUND_FMT = "<4s8sHHB3s16H"       # R tb op_begin op_end has_tph pad sro[16]          (52 bytes)
@@ -188,16 +188,6 @@ def emulate_program(state, n, tile_pos, prog):
                 for i in range(op["k"]):
                     idx |= sel_bit(sels[i]) << i
                 tph = mats[mat + idx] * tph
-            elif code in (RC_TABW, RC_TABW_ACC):                       # experimental: tables over 5..7 selector bits
-                assert op["omask"] == 0 and 4 < op["k"] <= 7
-                sels = op["src"] + [op["b"], tmask & 0xff, tmask >> 8, rmask & 0xff]
-                idx = np.zeros(N, dtype=np.int64)
-                for i in range(op["k"]):
-                    idx |= sel_bit(sels[i]) << i
-                tph = mats[mat + idx] * tph
-            elif code == RC_RTAB:                                      # experimental: register-indexed phase table
-                assert tmask == 0 and rmask == 0
-                s = np.where(live, mats[mat + j] * s, s)
             elif code == RC_LAYER:
                 assert op["omask"] == 0
                 present, hmask = op["k"] & 15, op["k"] >> 4

@@ -101,7 +101,7 @@ def test_error_payloads_and_options(engine):
     with pytest.raises(OperationError):
         reg.try_measure(7, u=0.5)
     with pytest.raises(Exception):
-        reg.set_option(_ffi.QB_OPT_FORCE_PATH, 12)
+        reg.set_option(_ffi.QB_OPT_FORCE_PATH, 5)
     reg.set_option(_ffi.QB_OPT_FORCE_PATH, 0)
     with pytest.raises(Exception):
         reg.set_option(_ffi.QB_OPT_JIT, 3)
@@ -167,3 +167,23 @@ def test_cpp_mirror_through_the_api_layer(host_lib, relabel_env, tmp_path):
                            "-lquaru_hostapi", f"-Wl,-rpath,{os.path.dirname(host_lib)}"])
     out = subprocess.run([exe], capture_output=True, text=True, timeout=120, env=dict(os.environ, QB_SWAP_RELABEL=relabel_env))
     assert out.returncode == 0 and "CPP_OK" in out.stdout, out.stdout + out.stderr
+
+
+def test_failed_load_leaves_queue_and_labels_untouched(engine, relabel, tmp_path):
+    """qb_load_state validates the file BEFORE it drops the gate queue and resets the SWAP relabelling / placement: after a
+    failed load (missing file) the pending gates are still applied and the caller's qubit names still match the layout."""
+    from oracle import gates as og
+    from oracle.oracle import OracleRegister
+    n = 5
+    ops = [og.hadamard(0), og.swap(0, 2), og.not_(1), og.cnot(2, 4)]
+    reg = engine.Register.new([False] * n)
+    ora = OracleRegister.new([False] * n)
+    for g in ops[:3]:
+        reg.apply(engine.Operation(g[0], g[1]))
+        ora.apply(g)
+    reg.sync()                                      # H, SWAP (a relabelling), X executed; the labels are permuted now
+    reg.apply(engine.Operation(ops[3][0], ops[3][1]))   # still queued
+    ora.apply(ops[3])
+    with pytest.raises(Exception):
+        reg.load_state(tmp_path / "missing.qbstate")
+    assert np.abs(reg.state - ora.state).max() < 1e-12

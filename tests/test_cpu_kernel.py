@@ -33,15 +33,13 @@ def host_kernel():
     lib = ctypes.CDLL(OUT)
     lib.k2r_host_run.restype = ctypes.c_int
     lib.k2r_host_run.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_char_p, ctypes.c_uint64, ctypes.c_int]
-    lib.k2r_host_run_persist.restype = ctypes.c_int
-    lib.k2r_host_run_persist.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_char_p, ctypes.c_uint64, ctypes.c_int, ctypes.c_uint32, ctypes.c_int]
     lib.k2r_host_run_remote.restype = ctypes.c_int
     lib.k2r_host_run_remote.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_char_p,
                                         ctypes.c_uint64, ctypes.c_int]
     return lib
 
 
-def _run(lib, n, ops, seed, small=False, persist_grid=0, variant=5):
+def _run(lib, n, ops, seed, small=False):
     s0 = random_state(n, seed)
     ora = OracleRegister(s0.copy(), n)
     for o in ops:
@@ -58,10 +56,7 @@ def _run(lib, n, ops, seed, small=False, persist_grid=0, variant=5):
             continue
         n_prog += 1
         assert p[2][:p[3]["lc"]] == list(range(p[3]["lc"]))
-        if persist_grid:
-            rc = lib.k2r_host_run_persist(dev.ctypes.data, n, p[3]["bytes"], len(p[3]["bytes"]), int(small), persist_grid, variant)
-        else:
-            rc = lib.k2r_host_run(dev.ctypes.data, n, p[3]["bytes"], len(p[3]["bytes"]), int(small))
+        rc = lib.k2r_host_run(dev.ctypes.data, n, p[3]["bytes"], len(p[3]["bytes"]), int(small))
         assert rc == 0, rc
         emu = em.emulate_program(emu, n, p[2], p[3])
     return dev, emu, ora.state, n_prog
@@ -100,24 +95,6 @@ def test_small_program_instantiation(host_kernel):
     assert_close(dev, want)
 
 
-@pytest.mark.parametrize("n,grid,kind,variant", [(14, 3, "layers", 5), (14, 1, "mixed", 6), (15, 5, "qft", 7), (13, 2, "mixed", 8),
-                                                 (12, 1, "layers", 6), (14, 3, "qft", 8), (14, 2, "mixed", 9), (13, 3, "layers", 10), (14, 3, "mixed", 11),
-                                                 (13, 2, "qft", 11)])
-def test_persistent_variants_on_the_host_compiled_kernel(host_kernel, n, grid, kind, variant):
-    """The experimental persistent kernels (QB_OPT_FORCE_PATH = 5..10): `grid` CTAs walk 2^(n-12) tiles with the coefficient
-    tables (and, for 6 / 8, the op records) staged in shared memory; grids that do not divide the tile count and a single
-    CTA doing everything included."""
-    ops = {"layers": circuits.random_circuit(n, 4, seed=n), "qft": circuits.qft_circuit(n), "mixed": circuits.mixed_circuit(n, 100, n)}[kind]
-    dev, emu, want, n_prog = _run(host_kernel, n, ops, 80 + n, persist_grid=grid, variant=variant)
-    assert n_prog >= 1
-    assert_close(dev, want, f"persistent kernel {variant} vs oracle, {kind} n={n} grid={grid}")
-    ref, _, _, _ = _run(host_kernel, n, ops, 80 + n)
-    assert np.array_equal(dev, ref), "same arithmetic as the default kernel: bit-identical results"
-    short = [og.hadamard(3), og.cnot(3, 9), og.rz(0.7, 9), og.hadamard(12)]
-    dev_s, _, want_s, _ = _run(host_kernel, 13, short, 3, small=True, persist_grid=2, variant=variant)
-    assert_close(dev_s, want_s)
-
-
 @pytest.mark.parametrize("kind,n", [("layers", 14), ("mixed", 13), ("qft", 14)])
 def test_programs_of_the_thorough_encoder_on_the_host_compiled_kernel(host_kernel, kind, n, monkeypatch):
     """The round programs big registers get (look-ahead planner, roll-out round selection; forced on here with
@@ -127,23 +104,6 @@ def test_programs_of_the_thorough_encoder_on_the_host_compiled_kernel(host_kerne
     dev, emu, want, n_prog = _run(host_kernel, n, ops, 90 + n)
     assert n_prog >= 1
     assert_close(dev, want, f"thorough encoder, kernel vs oracle, {kind} n={n}")
-    assert_close(dev, emu, "kernel vs program emulator")
-
-
-@pytest.mark.parametrize("kind,n,variant", [("layers", 14, 5), ("mixed", 13, 6), ("qft", 14, 9), ("layers", 13, 10)])
-def test_register_table_op_on_the_persistent_kernels(host_kernel, kind, n, variant, monkeypatch):
-    """Experimental RC_RTAB (QB_TILE_RTAB=1, persistent kernels only): unconditional phases on register bits merged into a
-    16-entry table indexed by the register number.  Programs through the emulator and through the kernel source."""
-    monkeypatch.setenv("QB_TILE_RTAB", "1")
-    ops = {"layers": circuits.random_circuit(n, 8, seed=n), "qft": circuits.qft_circuit(n), "mixed": circuits.mixed_circuit(n, 150, n)}[kind]
-    codes = [o["code"] for p in em.dump_programs(n, ops) if p[0] == "prog" for o in p[3]["ops"]]
-    if kind == "layers":
-        assert em.RC_RTAB in codes, "random layers have mergeable phases"
-    if kind == "qft":
-        assert em.RC_TABW in codes or em.RC_TABW_ACC in codes, "the QFT's cascades have tables over more than 4 selector bits"
-    dev, emu, want, n_prog = _run(host_kernel, n, ops, 95 + n, persist_grid=2, variant=variant)
-    assert n_prog >= 1
-    assert_close(dev, want, f"RTAB, kernel {variant} vs oracle, {kind} n={n}")
     assert_close(dev, emu, "kernel vs program emulator")
 
 

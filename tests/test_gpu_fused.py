@@ -138,21 +138,6 @@ def test_register_blocked_qft_and_diagonals(engine, n):
     assert_close(reg.state, ora.state, f"v2 qft+diag n={n}")
 
 
-@pytest.mark.skipif(os.environ.get("QB_TEST_EXPERIMENTAL") != "1", reason="experimental kernel variants: set QB_TEST_EXPERIMENTAL=1")
-@pytest.mark.parametrize("variant", [5, 6, 7, 8, 9, 10, 11])
-@pytest.mark.parametrize("n,kind", [(12, "layers"), (14, "mixed"), (16, "qft"), (18, "layers"), (20, "mixed")])
-def test_persistent_tile_kernels(engine, n, kind, variant):
-    """QB_OPT_FORCE_PATH = 5..10: persistent CTAs, coefficient tables (6, 8: op records too) staged in shared memory, 7 / 8 with
-    an L2 prefetch of the next tile, 9 / 10 with op records fetched one op ahead.  Their logic is covered on CPU by tests/test_cpu_kernel.py; this is the hardware check,
-    opt-in until the variants have been measured."""
-    ops = {"layers": circuits.random_circuit(n, 5, seed=n), "qft": circuits.qft_circuit(n), "mixed": circuits.mixed_circuit(n, 120, n)}[kind]
-    reg, ora = _run(engine, n, ops, 3000 + n, force=variant)
-    assert_close(reg.state, ora.state, f"persistent kernel {variant} n={n} {kind}")
-    ref, _ = _run(engine, n, ops, 3000 + n)
-    if not os.environ.get("QB_TILE_RTAB"):        # the register-table op multiplies phases on the host: equal within tolerance only
-        assert reg.max_abs_diff(ref) == 0.0, "same arithmetic as the default kernel: bit-identical"
-
-
 @pytest.mark.parametrize("n,kind", [(14, "layers"), (16, "mixed"), (17, "qft"), (20, "layers")])
 def test_thorough_planning_forced_on_small_registers(engine, n, kind, monkeypatch):
     """Registers of >= 26 / 28 local qubits (the bench) plan with a look-ahead over the tile bits and search the rounds;

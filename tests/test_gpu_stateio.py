@@ -100,3 +100,29 @@ def test_rejects_missing_wrong_size_truncated_and_corrupt_files(tmp_path):
     with pytest.raises(EngineError, match="cannot create"):
         a.save_state(tmp_path / "no_such_dir" / "x.qbstate")
     Register.from_int(n, 0).load_state(path)        # the intact file still loads
+
+
+def test_failed_load_leaves_the_register_as_it_was(tmp_path, monkeypatch):
+    """A missing file or a file of another register is detected before the gate queue is dropped and the SWAP relabelling /
+    placement is reset (qb_load_state): pending gates still run and the caller's qubit names still match the resident layout."""
+    from oracle import gates as og
+    from oracle.oracle import OracleRegister
+    monkeypatch.setenv("QB_SWAP_RELABEL", "1")
+    n = 13
+    ops = [og.hadamard(0), og.swap(0, 2), og.not_(1), og.cnot(2, 12), og.hadamard(7)]
+    reg = Register.new([False] * n)
+    ora = OracleRegister.new([False] * n)
+    for g in ops[:3]:
+        reg.apply(Operation(g[0], g[1]))
+        ora.apply(g)
+    reg.sync()
+    for g in ops[3:]:
+        reg.apply(Operation(g[0], g[1]))            # still queued when the load fails
+        ora.apply(g)
+    other = tmp_path / "other.qbstate"
+    Register.from_int(n + 1, 3).save_state(other)
+    with pytest.raises(EngineError):
+        reg.load_state(tmp_path / "missing.qbstate")
+    with pytest.raises(IndexError):
+        reg.load_state(other)
+    assert np.abs(reg.state - ora.state).max() < 1e-12

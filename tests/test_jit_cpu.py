@@ -130,3 +130,56 @@ def test_nvrtc_compiles_the_generated_source():
         ms = ctypes.c_double(0)
         got = L.qb_jit_compile_debug(src.encode(), ctypes.byref(ms), None, 0)
         assert got > 0, _ffi.last_error()
+
+
+def _remote_fixed_bits(hp, n_local, g, rank):
+    """qb_tile2_kernel.cuh remote_fixed_bits: the g fixed top bits of rank `rank`'s tile indices."""
+    in_tile = 0
+    for b in hp:
+        if b >= n_local:
+            in_tile |= 1 << (b - n_local)
+    fixed = pos = 0
+    for J in range(g):
+        if (in_tile >> J) & 1:
+            fixed |= ((rank >> J) & 1) << pos
+            pos += 1
+    for J in range(g):
+        if not (in_tile >> J) & 1:
+            fixed |= ((rank >> J) & 1) << pos
+            pos += 1
+    return fixed
+
+
+@pytest.mark.parametrize("world,n,kind", [(2, 14, "layers"), (4, 15, "qft"), (4, 14, "mixed"), (8, 16, "mixed")])
+def test_remote_variant_over_separately_allocated_shards(world, n, kind):
+    """Sharded registers (QB_SHARD_REMOTE=1): the specialised kernel of a pass whose tile contains RANK bits addresses amplitudes
+    through the table of peer-mapped shards.  The register is split into `world` separate host buffers; every rank runs its
+    share of the tiles; together they must reproduce the oracle."""
+    g = world.bit_length() - 1
+    nl = n - g
+    ops = {"layers": circuits.random_circuit(n, 5, seed=7 * n), "qft": circuits.qft_circuit(n),
+           "mixed": [o for o in circuits.mixed_circuit(n, 120, 3 * n) if len(o[1]) <= 2]}[kind]
+    s0 = random_state(n, 40 + n)
+    ora = OracleRegister(s0.copy(), n)
+    for o in ops:
+        ora.apply(o)
+    shards = [np.ascontiguousarray(s0[r << nl:(r + 1) << nl]) for r in range(world)]
+    bases = (ctypes.c_void_p * world)(*[sh.ctypes.data for sh in shards])
+    n_remote = 0
+    for p in em.dump_programs(n, ops):
+        if p[0] == "gates":
+            whole = np.concatenate(shards)
+            tmp = OracleRegister(whole, n)
+            for tag in p[1]:
+                tmp.apply(ops[tag])
+            for r in range(world):
+                shards[r][:] = tmp.state[r << nl:(r + 1) << nl]
+            continue
+        hp = p[3]["hp"][:p[3]["h"]]
+        n_remote += any(b >= nl for b in hp)
+        lib = build_host(jit_source(p[3]["bytes"], remote=1), remote=True)
+        for r in range(world):
+            tile_or = _remote_fixed_bits(hp, nl, g, r) << (n - 12 - g)
+            assert lib.jit_host_run(None, 1 << (nl - 12), 0, tile_or, bases, world, nl) == 0
+    assert n_remote >= 1, "at least one pass has a rank bit among its tile bits"
+    assert_close(np.concatenate(shards), ora.state, f"remote generated kernel vs oracle, world={world} n={n} {kind}")

@@ -166,26 +166,3 @@ def test_unconditional_phases_on_one_bit_are_multiplied_on_the_host():
     assert em.RC_PH_R not in codes and em.RC_PH_NEG not in codes
     got, want, seen, st = _replay(n, ops, 32)
     assert_close(got, want)
-
-
-@pytest.mark.parametrize("n,kind", [(18, "qft"), (19, "bench"), (20, "qft")])
-def test_experimental_op_set_with_big_register_planning(n, kind, monkeypatch):
-    """The programs the persistent kernels would get on a big register: look-ahead planner and round search forced on
-    (QB_PLAN_LOOKAHEAD=1) together with the experimental ops (QB_TILE_RTAB=1: register-indexed tables, per-thread tables over
-    5..7 selector bits, several of them OUTER bits at these sizes), replayed by the emulator against the oracle."""
-    monkeypatch.setenv("QB_PLAN_LOOKAHEAD", "1")
-    monkeypatch.setenv("QB_TILE_RTAB", "1")
-    ops = circuits.qft_circuit(n) if kind == "qft" else circuits.qft_circuit(n) + circuits.random_circuit(n, 6, seed=n)
-    got, want, seen, st = _replay(n, ops, 300 + n)
-    assert sorted(seen) == list(range(len(ops)))
-    assert_close(got, want, f"experimental ops, big-register planning, {kind} n={n}")
-    assert {em.RC_TABW, em.RC_TABW_ACC} & st["codes"], "cascades against 6+ thread / outer bits need wide tables"
-    wide_outer = False
-    for p in em.dump_programs(n, ops):
-        if p[0] != "prog":
-            continue
-        for o in p[3]["ops"]:
-            if o["code"] in (em.RC_TABW, em.RC_TABW_ACC):
-                sels = o["src"] + [o["b"], o["tmask"] & 0xff, o["tmask"] >> 8, o["rmask"] & 0xff]
-                wide_outer = wide_outer or any(s & 0x80 for s in sels[:o["k"]])
-    assert wide_outer, "at least one wide table is indexed by an outer (tile-index) bit"

@@ -1,6 +1,5 @@
 """Fused vs unfused timing of the C3-style random layered circuit.
-Usage: bench_fused.py [n] [depth] [tile_bits] [fused|both] [layers|qft] [force_path]
-force_path 5..10 select the experimental persistent tile kernels (QB_OPT_FORCE_PATH, include/quaru_b200.h)."""
+Usage: bench_fused.py [n] [depth] [tile_bits] [fused|both] [layers|qft] [force_path]   (see QB_OPT_FORCE_PATH)"""
 import os
 import sys
 import time
