@@ -172,8 +172,9 @@ static void plan_passes(const std::vector<Gate>& gates, uint32_t n_local, uint32
     const uint32_t T = std::min(T_opt, n_local);
     // QB_PLAN_MIN_LC=4 (experiment): 256-byte contiguous segments, one more arbitrary high bit per tile
     const char* lc_env = getenv("QB_PLAN_MIN_LC");
-    const uint32_t lc_min = std::min((lc_env && lc_env[0] == '4' && T == 12) ? 4u : MIN_LC, T);
-    const uint32_t h_max = std::min<uint32_t>(T - lc_min, 8);
+    const bool lc4 = lc_env && lc_env[0] == '4' && T == 12;
+    const uint32_t lc_min = std::min(lc4 ? 4u : MIN_LC, T);
+    const uint32_t h_max = std::min<uint32_t>(T - lc_min, lc4 ? 8 : 7);
     std::vector<char> done(gates.size(), 0);
     size_t remaining = gates.size();
     // One pass = one scan of the remaining gates in program order.  A gate WRITES its dense target bits and READS its
