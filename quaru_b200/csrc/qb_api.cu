@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <new>
+#include <string>
 
 #include "qb_common.h"
 #include "qb_shard.h"
@@ -82,7 +83,8 @@ static void free_reg(Reg* r) {
     delete r;
 }
 
-static int create_impl(uint32_t n, uint64_t basis_index, int rank, int world, const void* uid, int device, qb_reg** out) {
+static int create_impl(uint32_t n, uint64_t basis_index, int rank, int world, const void* uid, int device, qb_reg** out,
+                       Group* group = nullptr) {
     if (!out) return set_error(QB_ERR_INVALID_ARGUMENT, -1, "out is NULL");
     *out = nullptr;
     if (n > 40) return set_error(QB_ERR_UNSUPPORTED, n, "%u qubits: at most 40 are supported", n);
@@ -102,14 +104,56 @@ static int create_impl(uint32_t n, uint64_t basis_index, int rank, int world, co
     r->n_local = n - g;
     r->rank = rank;
     r->world = world;
+    r->group = group;
     int rc = alloc_common(r);
+    if (group) {
+        // in-process register: every rank publishes its shard, and all of them learn whether every allocation succeeded
+        // BEFORE anybody enters a collective (a rank that failed would leave the others waiting in ncclCommInitRank)
+        group_set_member(group, rank, r);
+        group_barrier(group);
+        for (int p = 0; p < world && rc == QB_OK; ++p)
+            if (!group_member(group, p) || !group_member(group, p)->state) rc = set_error(QB_ERR_OOM, p, "shard %d of the in-process register could not be allocated", p);
+        group_barrier(group);
+    }
     if (rc == QB_OK && world > 1) rc = shard_init(r, uid);
     if (rc == QB_OK) {
         const uint64_t owner = basis_index >> r->n_local;
         rc = k_init_basis(r, basis_index & ((1ull << r->n_local) - 1), owner == (uint64_t)rank);
     }
-    if (rc != QB_OK) { free_reg(r); return rc; }
+    if (rc != QB_OK) {
+        if (group) group_set_member(group, rank, nullptr);
+        free_reg(r);
+        return rc;
+    }
     *out = reinterpret_cast<qb_reg*>(r);
+    return QB_OK;
+}
+
+// Register::new with QB_NUM_GPUS = P in the environment: the same sharded register as qb_create_sharded, its P shards driven
+// by P worker threads of this process (qb_group.cu).  The handle is rank 0's shard.
+static int create_group(uint32_t n, uint64_t basis_index, int world, qb_reg** out) {
+    if (!out) return set_error(QB_ERR_INVALID_ARGUMENT, -1, "out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    QB_CUDA(cudaGetDeviceCount(&ndev));
+    if (ndev < world) return set_error(QB_ERR_NO_DEVICE, ndev, "QB_NUM_GPUS=%d but only %d CUDA device(s) are visible", world, ndev);
+    unsigned char uid[128];
+    QB_TRY(shard_unique_id(uid));
+    Group* G = group_create(world);
+    const int rc = group_run(G, [&](Reg*, int rank) -> int {
+        qb_reg* m = nullptr;
+        return create_impl(n, basis_index, rank, world, uid, rank, &m, G);
+    });
+    if (rc != QB_OK) {
+        // ranks that did succeed are released by their own workers (shard_destroy is collective over the survivors only when
+        // all of them survived; after a failed creation the communicator is abandoned, not torn down collectively)
+        for (int p = 0; p < world; ++p)
+            if (Reg* m = group_member(G, p)) { m->shard = nullptr; }
+        group_run(G, [&](Reg* m, int) -> int { if (m) free_reg(m); return QB_OK; });
+        group_destroy(G);
+        return rc;
+    }
+    *out = reinterpret_cast<qb_reg*>(group_member(G, 0));
     return QB_OK;
 }
 
@@ -200,6 +244,16 @@ using namespace qb;
     if (!(p)) return qb::set_error(QB_ERR_INVALID_ARGUMENT, -1, "register handle is NULL");    \
     QB_CUDA(cudaSetDevice(REG(p)->device))
 
+// In-process multi-GPU registers: a call made from outside the register's worker threads is executed by every worker on its
+// own shard (`m`), collectively; the workers' own (nested) calls take the ordinary path below.
+#define GROUP_CALL(reg, expr)                                                                        \
+    if (qb::Group* G_ = qb::group_of(REG(reg)))                                                      \
+        return qb::group_run(G_, [&](qb::Reg* m_, int rank_) -> int {                                \
+            qb_reg* m = reinterpret_cast<qb_reg*>(m_);                                               \
+            (void)rank_;                                                                             \
+            return (expr);                                                                           \
+        })
+
 extern "C" {
 
 const char* qb_last_error(void) { return qb::last_error_str(); }
@@ -237,7 +291,13 @@ int64_t qb_rounds_debug(uint32_t n, const qb_gate* gates, uint64_t count, void* 
 
 const char* qb_version(void) { return "quaru_b200 0.1 (sm_100a)"; }
 
-int qb_create(uint32_t n, uint64_t basis_index, qb_reg** out) try { return create_impl(n, basis_index, 0, 1, nullptr, -1, out); } QB_CATCH_ALL
+int qb_create(uint32_t n, uint64_t basis_index, qb_reg** out) try {
+    const int world = group_requested_world();   // QB_NUM_GPUS: Register::new keeps its signature (register.rs:41)
+    uint32_t g = 0;
+    while ((1 << g) < world) ++g;
+    if (world > 1 && n >= 2 * g + 1 && n <= 40 && (n >= 64 || basis_index < (1ull << n))) return create_group(n, basis_index, world, out);
+    return create_impl(n, basis_index, 0, 1, nullptr, -1, out);
+} QB_CATCH_ALL
 
 int qb_create_sharded(uint32_t n, uint64_t basis_index, int32_t rank, int32_t world, const void* uid, int32_t device,
                       qb_reg** out) try {
@@ -290,9 +350,17 @@ int qb_clone(qb_reg* src_, qb_reg** out) try {
     return QB_OK;
 } QB_CATCH_ALL
 
-void qb_destroy(qb_reg* reg) { free_reg(REG(reg)); }
+void qb_destroy(qb_reg* reg) {
+    if (Group* G = group_of(REG(reg))) {
+        group_run(G, [&](Reg* m, int) -> int { free_reg(m); return QB_OK; });   // shard_destroy is collective
+        group_destroy(G);
+        return;
+    }
+    free_reg(REG(reg));
+}
 
 int qb_reset(qb_reg* reg, uint64_t basis_index) try {
+    if (reg) GROUP_CALL(reg, qb_reset(m, basis_index));
     CHECK_REG(reg);
     Reg* r = REG(reg);
     if (basis_index >= (1ull << r->n)) return set_error(QB_ERR_INVALID_ARGUMENT, (int64_t)basis_index, "basis index out of range");
@@ -308,6 +376,7 @@ uint32_t qb_num_qubits(const qb_reg* reg) { return reg ? reinterpret_cast<const 
 
 // Register::apply -> try_apply_fast (register.rs:134-191)
 int qb_apply(qb_reg* reg, const double* matrix, const uint32_t* targets, uint32_t k) try {
+    if (reg) GROUP_CALL(reg, qb_apply(m, matrix, targets, k));
     CHECK_REG(reg);
     Reg* r = REG(reg);
     if (!matrix) return set_error(QB_ERR_INVALID_ARGUMENT, -1, "matrix is NULL");
@@ -317,6 +386,7 @@ int qb_apply(qb_reg* reg, const double* matrix, const uint32_t* targets, uint32_
 
 int qb_apply_controlled(qb_reg* reg, const double* matrix, const uint32_t* targets, uint32_t k, const uint32_t* controls,
                         uint32_t n_controls) try {
+    if (reg) GROUP_CALL(reg, qb_apply_controlled(m, matrix, targets, k, controls, n_controls));
     CHECK_REG(reg);
     Reg* r = REG(reg);
     if (!matrix) return set_error(QB_ERR_INVALID_ARGUMENT, -1, "matrix is NULL");
@@ -335,6 +405,7 @@ int qb_apply_controlled(qb_reg* reg, const double* matrix, const uint32_t* targe
 
 // Register::try_apply_all (register.rs:267-281) == the 2x2 gate on every qubit
 int qb_apply_all(qb_reg* reg, const double* m2x2) try {
+    if (reg) GROUP_CALL(reg, qb_apply_all(m, m2x2));
     CHECK_REG(reg);
     Reg* r = REG(reg);
     if (!m2x2) return set_error(QB_ERR_INVALID_ARGUMENT, -1, "matrix is NULL");
@@ -344,6 +415,7 @@ int qb_apply_all(qb_reg* reg, const double* m2x2) try {
 
 // gate loop of Register::apply_circuit (register.rs:346-350)
 int qb_apply_batch(qb_reg* reg, const qb_gate* gates, uint64_t count) try {
+    if (reg) GROUP_CALL(reg, qb_apply_batch(m, gates, count));
     CHECK_REG(reg);
     Reg* r = REG(reg);
     if (count && !gates) return set_error(QB_ERR_INVALID_ARGUMENT, -1, "gates is NULL");
@@ -357,6 +429,12 @@ int qb_apply_batch(qb_reg* reg, const qb_gate* gates, uint64_t count) try {
 
 // first loop of try_measure (register.rs:303-315)
 int qb_probabilities(qb_reg* reg, uint32_t target, double* p0, double* p1) try {
+    if (reg && p0 && p1)
+        if (Group* G_ = group_of(REG(reg)))
+            return group_run(G_, [&](Reg* m_, int rank_) -> int {
+                double a, b;
+                return qb_probabilities(reinterpret_cast<qb_reg*>(m_), target, rank_ ? &a : p0, rank_ ? &b : p1);
+            });
     CHECK_REG(reg);
     Reg* r = REG(reg);
     if (!p0 || !p1) return set_error(QB_ERR_INVALID_ARGUMENT, -1, "output pointer is NULL");
@@ -369,6 +447,12 @@ int qb_probabilities(qb_reg* reg, uint32_t target, double* p0, double* p1) try {
 
 // Register::try_measure (register.rs:297-342)
 int qb_measure(qb_reg* reg, uint32_t target, double u, int32_t* outcome) try {
+    if (reg && outcome)
+        if (Group* G_ = group_of(REG(reg)))
+            return group_run(G_, [&](Reg* m_, int rank_) -> int {
+                int32_t o;   // every rank derives the same outcome from the same probabilities and the same u
+                return qb_measure(reinterpret_cast<qb_reg*>(m_), target, u, rank_ ? &o : outcome);
+            });
     CHECK_REG(reg);
     Reg* r = REG(reg);
     if (!outcome) return set_error(QB_ERR_INVALID_ARGUMENT, -1, "outcome is NULL");
@@ -383,6 +467,7 @@ int qb_measure(qb_reg* reg, uint32_t target, double u, int32_t* outcome) try {
 } QB_CATCH_ALL
 
 int qb_read_state(qb_reg* reg, uint64_t offset, uint64_t count, double* out) try {
+    if (reg) GROUP_CALL(reg, qb_read_state(m, offset, count, out));
     CHECK_REG(reg);
     Reg* r = REG(reg);
     const uint64_t N = 1ull << r->n;
@@ -398,6 +483,7 @@ int qb_read_state(qb_reg* reg, uint64_t offset, uint64_t count, double* out) try
 } QB_CATCH_ALL
 
 int qb_write_state(qb_reg* reg, uint64_t offset, uint64_t count, const double* in) try {
+    if (reg) GROUP_CALL(reg, qb_write_state(m, offset, count, in));
     CHECK_REG(reg);
     Reg* r = REG(reg);
     const uint64_t N = 1ull << r->n;
@@ -413,6 +499,12 @@ int qb_write_state(qb_reg* reg, uint64_t offset, uint64_t count, const double* i
 } QB_CATCH_ALL
 
 int qb_save_state(qb_reg* reg, const char* path) try {
+    if (reg && path)
+        if (Group* G_ = group_of(REG(reg)))   // one file per shard: <path>.r<rank>
+            return group_run(G_, [&](Reg* m_, int rank_) -> int {
+                const std::string p = std::string(path) + ".r" + std::to_string(rank_);
+                return qb_save_state(reinterpret_cast<qb_reg*>(m_), p.c_str());
+            });
     CHECK_REG(reg);
     Reg* r = REG(reg);
     if (!path) return set_error(QB_ERR_INVALID_ARGUMENT, -1, "path is NULL");
@@ -421,6 +513,12 @@ int qb_save_state(qb_reg* reg, const char* path) try {
 } QB_CATCH_ALL
 
 int qb_load_state(qb_reg* reg, const char* path) try {
+    if (reg && path)
+        if (Group* G_ = group_of(REG(reg)))   // one file per shard: <path>.r<rank>
+            return group_run(G_, [&](Reg* m_, int rank_) -> int {
+                const std::string p = std::string(path) + ".r" + std::to_string(rank_);
+                return qb_load_state(reinterpret_cast<qb_reg*>(m_), p.c_str());
+            });
     CHECK_REG(reg);
     Reg* r = REG(reg);
     if (!path) return set_error(QB_ERR_INVALID_ARGUMENT, -1, "path is NULL");
@@ -433,6 +531,12 @@ int qb_load_state(qb_reg* reg, const char* path) try {
 } QB_CATCH_ALL
 
 int qb_norm2(qb_reg* reg, double* out) try {
+    if (reg && out)
+        if (Group* G_ = group_of(REG(reg)))
+            return group_run(G_, [&](Reg* m_, int rank_) -> int {
+                double o;
+                return qb_norm2(reinterpret_cast<qb_reg*>(m_), rank_ ? &o : out);
+            });
     CHECK_REG(reg);
     Reg* r = REG(reg);
     if (!out) return set_error(QB_ERR_INVALID_ARGUMENT, -1, "out is NULL");
@@ -445,6 +549,15 @@ int qb_norm2(qb_reg* reg, double* out) try {
 } QB_CATCH_ALL
 
 static int diff_impl(qb_reg* a_, qb_reg* b_, double* mx, double* l2) {
+    if (a_ && b_)
+        if (Group* Ga = group_of(REG(a_))) {
+            Group* Gb = REG(b_)->group;
+            if (!Gb || group_world(Gb) != group_world(Ga)) return set_error(QB_ERR_INVALID_ARGUMENT, -1, "registers differ in size, sharding or device");
+            return group_run(Ga, [&](Reg* m_, int rank_) -> int {
+                double x, y;
+                return diff_impl(reinterpret_cast<qb_reg*>(m_), reinterpret_cast<qb_reg*>(group_member(Gb, rank_)), rank_ ? &x : mx, rank_ ? &y : l2);
+            });
+        }
     CHECK_REG(a_);
     CHECK_REG(b_);
     Reg *a = REG(a_), *b = REG(b_);
@@ -473,11 +586,13 @@ int qb_l2_diff2(qb_reg* a, qb_reg* b, double* out) try {
 } QB_CATCH_ALL
 
 int qb_flush(qb_reg* reg) try {
+    if (reg) GROUP_CALL(reg, qb_flush(m));
     CHECK_REG(reg);
     return flush(REG(reg));
 } QB_CATCH_ALL
 
 int qb_sync(qb_reg* reg) try {
+    if (reg) GROUP_CALL(reg, qb_sync(m));
     CHECK_REG(reg);
     Reg* r = REG(reg);
     QB_TRY(flush(r));
@@ -486,6 +601,7 @@ int qb_sync(qb_reg* reg) try {
 } QB_CATCH_ALL
 
 int qb_timer_start(qb_reg* reg) try {
+    if (reg) GROUP_CALL(reg, qb_timer_start(m));
     CHECK_REG(reg);
     Reg* r = REG(reg);
     QB_TRY(flush(r));
@@ -494,6 +610,14 @@ int qb_timer_start(qb_reg* reg) try {
 } QB_CATCH_ALL
 
 int qb_timer_stop(qb_reg* reg, float* ms) try {
+    if (reg && ms)
+        if (Group* G_ = group_of(REG(reg))) {
+            float per_rank[8] = {0};
+            QB_TRY(group_run(G_, [&](Reg* m_, int rank_) -> int { return qb_timer_stop(reinterpret_cast<qb_reg*>(m_), &per_rank[rank_]); }));
+            *ms = 0.f;
+            for (int p = 0; p < group_world(G_); ++p) *ms = std::max(*ms, per_rank[p]);   // max over the shards
+            return QB_OK;
+        }
     CHECK_REG(reg);
     Reg* r = REG(reg);
     if (!ms) return set_error(QB_ERR_INVALID_ARGUMENT, -1, "ms is NULL");
@@ -505,6 +629,7 @@ int qb_timer_stop(qb_reg* reg, float* ms) try {
 } QB_CATCH_ALL
 
 int qb_set_option(qb_reg* reg, int32_t option, int64_t value) try {
+    if (reg) GROUP_CALL(reg, qb_set_option(m, option, value));
     CHECK_REG(reg);
     Reg* r = REG(reg);
     QB_TRY(flush(r));
@@ -537,6 +662,12 @@ int qb_set_option(qb_reg* reg, int32_t option, int64_t value) try {
 } QB_CATCH_ALL
 
 int qb_get_stat(qb_reg* reg, int32_t stat, int64_t* value) try {
+    if (reg && value)
+        if (Group* G_ = group_of(REG(reg)))
+            return group_run(G_, [&](Reg* m_, int rank_) -> int {
+                int64_t v;   // rank 0's counters (every rank launches the same passes and exchanges)
+                return qb_get_stat(reinterpret_cast<qb_reg*>(m_), stat, rank_ ? &v : value);
+            });
     CHECK_REG(reg);
     Reg* r = REG(reg);
     if (!value) return set_error(QB_ERR_INVALID_ARGUMENT, -1, "value is NULL");

@@ -79,6 +79,7 @@ void make_swap_gate(uint32_t a, uint32_t b, Gate* out);
 
 // ---- the handle ----------------------------------------------------------------------------------
 struct Shard;  // multi-GPU state (qb_shard.cu)
+struct Group;  // P shards driven from one process (qb_group.cu)
 
 struct Reg {
     int device = 0;
@@ -118,6 +119,7 @@ struct Reg {
     // sharding
     int rank = 0, world = 1;
     Shard* shard = nullptr;
+    Group* group = nullptr;  // set on every shard of an in-process (QB_NUM_GPUS) register
     std::vector<uint32_t> phys_of;  // logical qubit -> physical bit position
     // SWAP relabelling (above the placement): caller's qubit q is engine ("logical") qubit label[q]
     bool relabel = false;
@@ -148,6 +150,20 @@ int run_fused(Reg* r, std::vector<Gate>& gates, std::vector<Gate>* hold = nullpt
 int run_local(Reg* r, std::vector<Gate>& gates);  // fused or unfused according to r->fusion (qb_api.cu)
 int64_t plan_debug(uint32_t n, std::vector<Gate>& gates, uint32_t tile_bits, int32_t* pass_of_gate,
                    int32_t* order_in_pass);
+
+// ---- in-process multi-GPU registers (qb_group.cu) ---------------------------------------------------
+Group* group_create(int world);             // spawns one worker thread per rank (device = rank)
+void group_destroy(Group* g);               // joins the workers
+Group* group_of(Reg* r);                    // the register's group when called from OUTSIDE its workers, else nullptr
+int group_world(const Group* g);
+Reg* group_member(Group* g, int rank);
+void group_set_member(Group* g, int rank, Reg* r);
+void group_barrier(Group* g);               // workers only
+int group_requested_world();                // QB_NUM_GPUS (2, 4, 8), else 1
+}  // namespace qb
+#include <functional>
+namespace qb {
+int group_run(Group* g, const std::function<int(Reg*, int)>& fn);   // fn(shard, rank) on every worker; first failure in rank order
 
 // ---- specialised tile kernels (qb_jit.cu): process-wide compiler state ------------------------------
 int jit_drain();           // wait until no compile is pending

@@ -135,6 +135,21 @@ int shard_init(Reg* r, const void* unique_id) {
     // peer-memory transport: exchange CUDA IPC handles of the shards through NCCL and map every peer's shard
     const char* tr = getenv("QB_SHARD_TRANSPORT");
     if (!(tr && !strcmp(tr, "nccl")) && r->world <= 8) {
+        int opened = 0;
+        if (r->group) {
+            // in-process register (qb_group.cu): the peers' shards are ordinary device pointers of this process
+            group_barrier(r->group);   // every rank has allocated its shard
+            bool ok = true;
+            for (int p = 0; p < r->world; ++p) {
+                Reg* m = group_member(r->group, p);
+                s->peer[p] = m->state;
+                if (p == r->rank) continue;
+                const cudaError_t e = cudaDeviceEnablePeerAccess(m->device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) ok = false;
+                cudaGetLastError();
+            }
+            opened = ok ? r->world : 0;
+        } else {
         cudaIpcMemHandle_t mine, all[8];
         static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
         // Every rank takes part in both all-gathers whatever happened locally (a rank that skipped one would hang
@@ -152,7 +167,6 @@ int shard_init(Reg* r, const void* unique_id) {
             cudaFree(dbuf);
             if (!moved) return set_error(QB_ERR_NCCL, -1, "exchange of the shards' IPC handles failed");
         }
-        int opened = 0;
         if (ok) {
             for (int p = 0; p < r->world; ++p) {
                 if (p == r->rank) { s->peer[p] = r->state; ++opened; continue; }
@@ -161,6 +175,7 @@ int shard_init(Reg* r, const void* unique_id) {
                 s->peer[p] = (c64*)ptr;
                 ++opened;
             }
+        }
         }
         cudaGetLastError();   // a failed IPC call must not poison later launches
         // all ranks must agree on the transport: gather the success flags
@@ -176,7 +191,7 @@ int shard_init(Reg* r, const void* unique_id) {
         if (!s->p2p) {   // agreed fallback to NCCL send/recv: unmap whatever was mapped, then let nobody run ahead and
                          // free a shard that a slower peer still has mapped
             for (int p = 0; p < 8; ++p) {
-                if (s->peer[p] && p != r->rank) cudaIpcCloseMemHandle(s->peer[p]);
+                if (s->peer[p] && p != r->rank && !r->group) cudaIpcCloseMemHandle(s->peer[p]);
                 s->peer[p] = nullptr;
             }
             cudaGetLastError();
@@ -198,7 +213,7 @@ void shard_destroy(Reg* r) {
     Shard* s = r->shard;
     if (!s) return;
     for (int p = 0; p < 8; ++p)
-        if (s->peer[p] && p != r->rank) cudaIpcCloseMemHandle(s->peer[p]);
+        if (s->peer[p] && p != r->rank && !r->group) cudaIpcCloseMemHandle(s->peer[p]);
     // nobody frees its shard before every peer has unmapped it; keyed on the transport all ranks agreed on, so
     // that every rank makes the same collective calls
     if (s->p2p && s->comm && s->d_gather && g_nccl.AllGather) {

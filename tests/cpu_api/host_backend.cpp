@@ -174,3 +174,16 @@ int state_load_check(Reg*, const char* path) {   // the host stand-in's files ha
     return QB_OK;
 }
 }  // namespace qb
+
+// in-process multi-GPU registers (qb_group.cu) do not exist in the host build: QB_NUM_GPUS is ignored
+namespace qb {
+Group* group_create(int) { return nullptr; }
+void group_destroy(Group*) {}
+Group* group_of(Reg*) { return nullptr; }
+int group_world(const Group*) { return 1; }
+Reg* group_member(Group*, int) { return nullptr; }
+void group_set_member(Group*, int, Reg*) {}
+void group_barrier(Group*) {}
+int group_requested_world() { return 1; }
+int group_run(Group*, const std::function<int(Reg*, int)>&) { return set_error(QB_ERR_UNSUPPORTED, -1, "host stand-in"); }
+}  // namespace qb
