@@ -613,6 +613,54 @@ static bool encode_rounds_with(const std::vector<Gate>& gates, const std::vector
     if (n_rounds == 0 || (last_R & ~io_allowed)) {  // the storing round must have its register bits within 5..11
         if (!emit_round(0xf00, {})) return false;
     }
+    // Per-thread phase tables travel forward: a merged table (RC_TAB) of round r is a function of thread / tile-index bits
+    // only, so it commutes with every dense gate of round r + 1 unless one of its selector bits becomes a register bit there.
+    // Moving it to the end of round r + 1 (and on, as long as that holds) leaves many rounds with nothing in their per-thread
+    // phase: the 16 complex multiplies that apply it (64 FP64 instructions per thread and round) are not issued at all, and the
+    // table costs one multiply per thread where it lands.  QB_TILE_DEFER_TPH=0 keeps every table in its round.
+    {
+        const char* dt = getenv("QB_TILE_DEFER_TPH");
+        if (!(dt && dt[0] == '0') && n_rounds > 1) {
+            std::vector<std::vector<ROp>> per(n_rounds);
+            for (size_t r = 0; r < n_rounds; ++r)
+                per[r].assign(prog->ops + prog->rounds[r].op_begin, prog->ops + prog->rounds[r].op_end);
+            auto writes_tph_at_end = [](const std::vector<ROp>& v) {
+                size_t from = 0;   // the chains' flushes reset the accumulator: only what follows the last one is applied at the round's end
+                for (size_t i = 0; i < v.size(); ++i)
+                    if (v[i].code >= RC_PH_FLUSH && v[i].code < RC_PH_FLUSH + 4) from = i + 1;
+                for (size_t i = from; i < v.size(); ++i) {
+                    const ROp& o = v[i];
+                    if (o.code == RC_TAB || o.code == RC_PH_T || o.code == RC_DG1T) return true;
+                    if (o.code == RC_DG && o.rmask == 0) {
+                        bool reg = false;
+                        for (int k = 0; k < o.k && k < 3; ++k) reg = reg || o.src[k] < 4;
+                        if (!reg) return true;
+                    }
+                }
+                return false;
+            };
+            for (size_t r = 0; r + 1 < n_rounds; ++r) {
+                uint32_t Rn = 0;
+                for (int i = 0; i < 4; ++i) Rn |= 1u << prog->rounds[r + 1].R[i];
+                std::vector<ROp> keep;
+                for (const ROp& o : per[r]) {
+                    bool movable = o.code == RC_TAB && o.omask == 0;
+                    const uint8_t sel[4] = {o.src[0], o.src[1], o.src[2], o.b};
+                    for (int i = 0; movable && i < o.k && i < 4; ++i)
+                        if (!(sel[i] & 0x80) && ((Rn >> (sel[i] & 0x3f)) & 1u)) movable = false;
+                    if (movable) per[r + 1].push_back(o); else keep.push_back(o);
+                }
+                per[r].swap(keep);
+            }
+            n_ops = 0;
+            for (size_t r = 0; r < n_rounds; ++r) {
+                prog->rounds[r].op_begin = (uint16_t)n_ops;
+                for (const ROp& o : per[r]) prog->ops[n_ops++] = o;
+                prog->rounds[r].op_end = (uint16_t)n_ops;
+                prog->rounds[r].has_tph = writes_tph_at_end(per[r]) ? 1 : 0;
+            }
+        }
+    }
     if (pass_scalar.x != 1.0 || pass_scalar.y != 0.0) {   // the pass's constant factor, applied in the last round:
         RoundDesc& last = prog->rounds[n_rounds - 1];
         bool absorbed = false;   // ... by a per-thread table that round already has (its entries are scaled), ...

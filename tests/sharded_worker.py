@@ -35,11 +35,14 @@ def main():
 
     failures = []
     remote_passes = [0]
+    jit_launches = [0]
     g = int(np.log2(world))
 
     def check(name, n, ops, fusion, measure=()):
         reg = Register.sharded(n, 0, rank, world, new_uid(), device=local)
         reg.set_option(_ffi.QB_OPT_FUSION, fusion)
+        reg.set_option(_ffi.QB_OPT_JIT, 2)               # fused passes of shards with >= 12 local qubits run through their
+        reg.set_option(_ffi.QB_OPT_JIT_MIN_QUBITS, 12)   # specialised kernels (local and remote variants), compiled synchronously
         ora = OracleRegister.new([False] * n)
         rng = np.random.default_rng(1234)
         for m, t in ops:
@@ -63,6 +66,7 @@ def main():
             failures.append(f"{name}: norm2 {nrm}")
         swaps = reg.stat(_ffi.QB_STAT_SWAPS)
         remote_passes[0] += reg.stat(_ffi.QB_STAT_REMOTE_PASSES)
+        jit_launches[0] += reg.stat(_ffi.QB_STAT_JIT_LAUNCHES)
         reg.close()
         return swaps
 
@@ -81,7 +85,7 @@ def main():
     # a bigger one: 20 qubits, fused, 3 layers
     swaps = check("layers n=20", 20, circuits.random_circuit(20, 3, seed=20), 1, measure=(19,))
     if rank == 0:
-        print(f"exchanges in the n=20 run: {swaps}", flush=True)
+        print(f"exchanges in the n=20 run: {swaps}; specialised-kernel launches so far: {jit_launches[0]}", flush=True)
     if os.environ.get("QB_SHARD_REMOTE") == "1":
         # experimental exchange-free scheduler: shards of >= 2^12 amplitudes, so that rank bits can be tile bits
         n = 13 + g
