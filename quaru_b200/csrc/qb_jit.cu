@@ -109,11 +109,14 @@ struct Entry {
     std::mutex load_mu;
 };
 
-std::mutex g_mu;
-std::condition_variable g_cv, g_idle_cv;
-std::unordered_map<Key, std::shared_ptr<Entry>, KeyHash> g_cache;
-std::deque<std::shared_ptr<Entry>> g_jobs;
-std::vector<std::thread> g_workers;
+// The pool's workers are detached and spend their idle time waiting on g_cv: none of this state may be destroyed at process
+// exit (destroying a condition variable with waiters blocks forever in glibc), so it lives on the heap and is never freed.
+std::mutex& g_mu = *new std::mutex;
+std::condition_variable& g_cv = *new std::condition_variable;
+std::condition_variable& g_idle_cv = *new std::condition_variable;
+std::unordered_map<Key, std::shared_ptr<Entry>, KeyHash>& g_cache = *new std::unordered_map<Key, std::shared_ptr<Entry>, KeyHash>;
+std::deque<std::shared_ptr<Entry>>& g_jobs = *new std::deque<std::shared_ptr<Entry>>;
+std::vector<std::thread>& g_workers = *new std::vector<std::thread>;
 std::atomic<int64_t> g_compiled{0}, g_failed{0}, g_pending{0}, g_compile_us{0};
 
 void fnv(const void* data, size_t len, uint64_t* a, uint64_t* b) {
@@ -128,7 +131,7 @@ Key key_of(const ProgView& p, const JitOpts& o) {
     uint64_t a = 0xcbf29ce484222325ull, b = 0x84222325cbf29ce4ull;
     const uint32_t hdr[9] = {p.lc, p.h, p.n_rounds, p.n_mats, p.n_ops, (uint32_t)o.min_blocks, (uint32_t)o.persistent, (uint32_t)o.prefetch, (uint32_t)o.remote};
     fnv(hdr, sizeof(hdr), &a, &b);
-    fnv(p.hp, 8, &a, &b);
+    fnv(p.hp, p.h, &a, &b);   // only the entries in use are initialised
     fnv(p.gro_first, 128, &a, &b);
     fnv(p.gro_last, 128, &a, &b);
     fnv(p.rounds, p.n_rounds * sizeof(RoundDesc), &a, &b);
