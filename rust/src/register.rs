@@ -105,6 +105,11 @@ impl Register {
     pub fn try_apply_fast(&mut self, op: &Operation) -> Result<&mut Self, OperationError> {
         let matrix = op.matrix(); // Array2<c64>, standard (row-major) layout; c64 is #[repr(C)] {re, im}
         let matrix = matrix.as_standard_layout();
+        // a target that does not fit the ABI's u32 can never be a qubit of this register: report it as the reference would
+        // (InvalidTarget(t), register.rs:149-153) instead of truncating it in the cast below
+        if let Some(&t) = op.targets().iter().find(|&&t| t > u32::MAX as usize) {
+            return Err(OperationError::InvalidTarget(t));
+        }
         let targets: Vec<u32> = op.targets().iter().map(|&t| t as u32).collect();
         check(unsafe {
             qb_apply(self.handle, matrix.as_ptr() as *const f64, targets.as_ptr(), targets.len() as u32)
@@ -146,6 +151,9 @@ impl Register {
 
     /// Seeded-parity hook: measurement with a caller-supplied uniform draw.
     pub fn try_measure_with(&mut self, target: usize, u: f64) -> Result<bool, OperationError> {
+        if target > u32::MAX as usize {
+            return Err(OperationError::InvalidTarget(target)); // register.rs:298-300; never truncated by the cast below
+        }
         let mut outcome: i32 = 0;
         check(unsafe { qb_measure(self.handle, target as u32, u, &mut outcome) })?;
         Ok(outcome != 0)
@@ -155,6 +163,9 @@ impl Register {
     pub fn apply_circuit(&mut self, circuit: &mut QuantumCircuit) -> Vec<(usize, bool)> {
         // one C-ABI call for the whole gate list, so the library can fuse it into tile passes
         let mats: Vec<_> = circuit.get_operations().iter().map(|op| op.matrix().as_standard_layout().to_owned()).collect();
+        if circuit.get_operations().iter().any(|op| op.targets().iter().any(|&t| t > u32::MAX as usize)) {
+            panic!("Could not apply operation"); // what Register::apply does for an InvalidTarget (register.rs:136)
+        }
         let tgts: Vec<Vec<u32>> =
             circuit.get_operations().iter().map(|op| op.targets().iter().map(|&t| t as u32).collect()).collect();
         let gates: Vec<qb_gate> = mats
@@ -214,30 +225,43 @@ impl Register {
         }
     }
 
+    /// Streams the amplitudes to the host in chunks of 2^20 (a 33-qubit state is 137 GB: `state()` would need that much
+    /// host memory) and hands each one, with its index, to `f`.
+    fn for_each_amplitude(&self, mut f: impl FnMut(usize, c64)) {
+        const CHUNK: u64 = 1 << 20;
+        let total: u64 = 1u64 << self.size;
+        let mut buf = vec![c64::new(0.0, 0.0); CHUNK.min(total) as usize];
+        let mut offset = 0u64;
+        while offset < total {
+            let count = CHUNK.min(total - offset);
+            check(unsafe { qb_read_state(self.handle, offset, count, buf.as_mut_ptr() as *mut f64) }).expect("Could not read state");
+            for (k, s) in buf[..count as usize].iter().enumerate() {
+                f(offset as usize + k, *s);
+            }
+            offset += count;
+        }
+    }
+
     /// register.rs:379
     pub fn print_probabilities(&self) {
         let n = self.size;
-        for (i, s) in self.state().iter().enumerate() {
-            println!("{:0n$b}: {}%", i, s.norm_sqr() * 100.0);
-        }
+        self.for_each_amplitude(|i, s| println!("{:0n$b}: {}%", i, s.norm_sqr() * 100.0));
     }
 
     /// register.rs:386
     pub fn print_nonzero_probabilities(&self) {
         let n = self.size;
-        for (i, s) in self.state().iter().enumerate() {
+        self.for_each_amplitude(|i, s| {
             if s.norm_sqr() > 0.0 {
                 println!("{:0n$b}: {}%", i, s.norm_sqr() * 100.0);
             }
-        }
+        });
     }
 
     /// register.rs:396
     pub fn print_state(&self) {
         let n = self.size;
-        for (i, s) in self.state().iter().enumerate() {
-            println!("{i:0n$b}: {s}");
-        }
+        self.for_each_amplitude(|i, s| println!("{i:0n$b}: {s}"));
     }
 
     /// register.rs:404
