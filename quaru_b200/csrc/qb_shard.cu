@@ -92,6 +92,9 @@ struct Shard {
     std::vector<int32_t> events;       // dry run: [gate index, g', V..., J...] per exchange
     int64_t cur_gate = -1;
     int64_t dry_passes = 0;            // dry run: state sweeps the local planner would need for the epochs so far
+    // placement memory (see shard_run): gate-list hash -> the placement the list was first run from
+    struct Seen { uint64_t hash; std::vector<uint32_t> phys_of; };
+    std::vector<Seen> seen;
 };
 
 // dry run only: how many sweeps the fused local path would need for this batch of mapped gates
@@ -680,9 +683,105 @@ static int shard_run_remote(Reg* r, std::vector<Gate>& gates) {
     return QB_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Placement memory.  The exchange schedulers leave the qubits wherever the last exchange put them, so a circuit that is
+// applied again (every step of an iterative algorithm, every shot, every step of the bench) would start from another
+// placement each time: other physical gate positions, hence other pass programs -- none of the specialised kernels
+// compiled for the first application (qb_jit.cu) would ever be reused.  shard_run therefore remembers, per gate-list hash,
+// the placement the list was first run from, and when the same list comes back it first moves the qubits to that placement:
+// ONE exchange that brings the displaced global qubits home (only the rank bits that differ) and one fused pass of local
+// SWAPs.  From there every scheduling decision repeats (they depend on the placement and the gate list only), and so does
+// every pass program.  All ranks hold the same maps, so all take the same decisions.  QB_SHARD_PLACEMENT_MEMORY=0 disables it.
+// ------------------------------------------------------------------------------------------------
+static uint64_t gate_list_hash(const std::vector<Gate>& gates) {
+    uint64_t h = 0xcbf29ce484222325ull;
+    auto mix = [&](const void* p, size_t n) {
+        const unsigned char* b = (const unsigned char*)p;
+        for (size_t i = 0; i < n; ++i) h = (h ^ b[i]) * 0x100000001b3ull;
+    };
+    for (const Gate& g : gates) {
+        mix(&g.k, sizeof g.k);
+        mix(&g.kind, sizeof g.kind);
+        mix(&g.ctrl_mask, sizeof g.ctrl_mask);
+        mix(g.targets.data(), g.targets.size() * sizeof(uint32_t));
+        mix(g.matrix.data(), g.matrix.size() * sizeof(c64));
+    }
+    return h;
+}
+
+static void push_local_swap(std::vector<Gate>* batch, uint32_t pa, uint32_t pb);
+static int shard_move_to(Reg* r, const std::vector<uint32_t>& target) {   // target: logical qubit -> physical position
+    Shard* s = r->shard;
+    const uint32_t nl = r->n_local, n = r->n;
+    if (r->phys_of == target) return QB_OK;
+    std::vector<uint32_t> want_at(n);   // physical position -> the logical qubit that belongs there
+    for (uint32_t q = 0; q < n; ++q) want_at[target[q]] = q;
+    // (1) rank bits: every displaced home qubit that is local now goes back in ONE exchange
+    std::vector<uint32_t> V, J;
+    for (uint32_t j = 0; j < s->g; ++j) {
+        const uint32_t q = want_at[nl + j];
+        if (s->logical_at[nl + j] == q) continue;
+        if (r->phys_of[q] >= nl) { V.clear(); J.clear(); break; }   // it sits on another rank bit: general path below
+        V.push_back(r->phys_of[q]);
+        J.push_back(j);
+    }
+    bool rank_bits_ok = true;
+    if (!V.empty()) QB_TRY(exchange(r, V, J));
+    for (uint32_t j = 0; j < s->g; ++j) rank_bits_ok = rank_bits_ok && s->logical_at[nl + j] == want_at[nl + j];
+    if (!rank_bits_ok) {
+        // rank bits permuted among themselves: go through the identity placement (shard_canonicalize) expressed in the target's
+        // qubit names -- rename q -> target[q], restore the identity there, rename back
+        std::vector<uint32_t> inv(n);
+        for (uint32_t q = 0; q < n; ++q) inv[target[q]] = q;
+        std::vector<uint32_t> phys_v(n), at_v(n);
+        for (uint32_t q = 0; q < n; ++q) phys_v[target[q]] = r->phys_of[q];
+        for (uint32_t p = 0; p < n; ++p) at_v[p] = target[s->logical_at[p]];
+        r->phys_of = phys_v;
+        s->logical_at = at_v;
+        const int rc = shard_canonicalize(r);
+        for (uint32_t q = 0; q < n; ++q) phys_v[q] = r->phys_of[target[q]];
+        for (uint32_t p = 0; p < n; ++p) at_v[p] = inv[s->logical_at[p]];
+        r->phys_of = phys_v;
+        s->logical_at = at_v;
+        return rc;
+    }
+    // (2) local positions: SWAP gates on physical positions, fused by the planner into (usually) one pass
+    std::vector<Gate> batch;
+    for (uint32_t p = 0; p < nl; ++p) {
+        const uint32_t q = want_at[p];
+        if (s->logical_at[p] == q) continue;
+        const uint32_t cur = r->phys_of[q];
+        push_local_swap(&batch, p, cur);
+        const uint32_t other = s->logical_at[p];
+        s->logical_at[p] = q; s->logical_at[cur] = other;
+        r->phys_of[q] = p; r->phys_of[other] = cur;
+    }
+    if (!batch.empty()) QB_TRY(run_local(r, batch));
+    if (r->phys_of != target) return set_error(QB_ERR_UNSUPPORTED, -1, "internal: placement restore failed");
+    return QB_OK;
+}
+
 int shard_run(Reg* r, std::vector<Gate>& gates) {
     const char* remote = getenv("QB_SHARD_REMOTE");
-    if (remote && !strcmp(remote, "1")) return shard_run_remote(r, gates);
+    if (remote && !strcmp(remote, "1")) return shard_run_remote(r, gates);   // never changes the placement
+    Shard* s = r->shard;
+    const char* pm = getenv("QB_SHARD_PLACEMENT_MEMORY");
+    if (!s->dry && r->jit != 0 && r->n_local >= r->jit_min_qubits && gates.size() >= 16 && !(pm && pm[0] == '0') && r->n_local >= 2 * s->g) {
+        const uint64_t h = gate_list_hash(gates);
+        bool found = false;
+        for (size_t i = 0; i < s->seen.size() && !found; ++i)
+            if (s->seen[i].hash == h) {
+                found = true;
+                const Shard::Seen hit = s->seen[i];
+                s->seen.erase(s->seen.begin() + (long)i);
+                s->seen.push_back(hit);                      // most recently used last
+                QB_TRY(shard_move_to(r, hit.phys_of));
+            }
+        if (!found) {
+            if (s->seen.size() >= 16) s->seen.erase(s->seen.begin());
+            s->seen.push_back(Shard::Seen{h, r->phys_of});
+        }
+    }
     const char* reorder = getenv("QB_SHARD_REORDER");   // "0": the first scheduler (cuts the gate list at every exchange)
     if (reorder && !strcmp(reorder, "0")) return shard_run_default(r, gates);
     return shard_run_reordered(r, gates);

@@ -86,6 +86,34 @@ def main():
     swaps = check("layers n=20", 20, circuits.random_circuit(20, 3, seed=20), 1, measure=(19,))
     if rank == 0:
         print(f"exchanges in the n=20 run: {swaps}; specialised-kernel launches so far: {jit_launches[0]}", flush=True)
+    # Placement memory (qb_shard.cu shard_run): the same circuit applied again first moves the qubits back to the placement it
+    # was first run from, so every pass program -- and its specialised kernel -- repeats.  Three applications against the oracle;
+    # the third must not hand a single new program to the compiler.
+    if os.environ.get("QB_SHARD_REMOTE") != "1":
+        n = 14 + g
+        ops = circuits.random_circuit(n, 4, seed=31) + circuits.qft_circuit(n)[:60]
+        reg = Register.sharded(n, 0, rank, world, new_uid(), device=local)
+        reg.set_option(_ffi.QB_OPT_JIT, 2)
+        reg.set_option(_ffi.QB_OPT_JIT_MIN_QUBITS, 12)
+        ora = OracleRegister.new([False] * n)
+        eops = [Operation(m, t) for m, t in ops]
+        compiles = []
+        for rep in range(3):
+            reg.apply_batch(eops)
+            reg.sync()
+            compiles.append(reg.stat(_ffi.QB_STAT_JIT_COMPILES))
+            for o in ops:
+                ora.apply(o)
+        nl, lo = n - g, rank << (n - g)
+        d = np.abs(reg.read(0, 1 << n)[lo:lo + (1 << nl)] - ora.state[lo:lo + (1 << nl)])
+        if d.max() > ABS_TOL:
+            failures.append(f"repeated circuit: rank {rank} max|diff| {d.max():.3e}")
+        if compiles[2] != compiles[1]:
+            failures.append(f"repeated circuit: rank {rank} compiled new programs on the third application {compiles}")
+        if rank == 0:
+            print(f"repeated circuit n={n}: programs compiled after each application {compiles}, exchanges {reg.stat(_ffi.QB_STAT_SWAPS)}", flush=True)
+        reg.close()
+
     if os.environ.get("QB_SHARD_REMOTE") == "1":
         # experimental exchange-free scheduler: shards of >= 2^12 amplitudes, so that rank bits can be tile bits
         n = 13 + g
