@@ -320,7 +320,7 @@ def timed_steps(job, reg, ops, steps, clock_index=None):
     keys = {"launches": S.QB_STAT_KERNEL_LAUNCHES, "passes": S.QB_STAT_PASSES, "bytes": S.QB_STAT_BYTES_MOVED,
             "tile_launches": S.QB_STAT_TILE_LAUNCHES, "tile_ns": S.QB_STAT_TILE_NS, "swap_bytes": S.QB_STAT_SWAP_BYTES,
             "swaps": S.QB_STAT_SWAPS, "jit_launches": S.QB_STAT_JIT_LAUNCHES, "jit_misses": S.QB_STAT_JIT_MISSES,
-            "remote_passes": S.QB_STAT_REMOTE_PASSES, "rounds": S.QB_STAT_ROUNDS}
+            "remote_passes": S.QB_STAT_REMOTE_PASSES, "rounds": S.QB_STAT_ROUNDS, "fused_exchanges": S.QB_STAT_FUSED_EXCHANGES}
     before = {k: reg.stat(v) for k, v in keys.items()}
     sampler = ClockSampler(clock_index) if clock_index is not None else None
     if sampler:
@@ -383,6 +383,7 @@ def nvlink_roofline(m, steps, per_gpu_bytes, hbm_peak):
     hbm_s = (m["passes"] / steps) * per_gpu_bytes / (hbm_peak * 1e9)
     sb = m["swap_bytes"] / steps
     out = {"swap_bytes_sent_per_gpu_per_step": sb, "exchanges_per_step": m["swaps"] / steps,
+           "exchanges_carried_by_a_pass_per_step": m["fused_exchanges"] / steps,
            "remote_passes_per_step": m["remote_passes"] / steps, "passes_per_step": m["passes"] / steps,
            "roofline_hbm_s": hbm_s, "step_s": step_s}
     for peak in (900.0, 770.0):

@@ -193,6 +193,7 @@ int qb_set_option(qb_reg* reg, int32_t option, int64_t value);
 #define QB_STAT_JIT_COMPILE_MS 15 /* process-wide: summed NVRTC time, ms */
 #define QB_STAT_JIT_PENDING 16    /* process-wide: compiles queued or running */
 #define QB_STAT_JIT_FAILED 17     /* process-wide: compiles that failed */
+#define QB_STAT_FUSED_EXCHANGES 18 /* sharded registers: exchanges carried by the stores of a tile pass (counted in QB_STAT_SWAPS too) */
 int qb_get_stat(qb_reg* reg, int32_t stat, int64_t* value);
 
 /* Blocks until no specialised kernel is being compiled (process-wide).  A driver that is about to time a circuit it has
@@ -257,7 +258,8 @@ int64_t qb_shard_plan_debug(uint32_t n, int32_t world, int32_t rank, const qb_ga
  * an NVRTC compile of such a source for sm_100a; neither needs a GPU.  tests/test_jit_cpu.py builds the source as host C++
  * (-DQB_HOST_EMU) and replays it against the oracle. */
 int64_t qb_jit_source_debug(const void* program, uint64_t len, int32_t min_blocks, int32_t persistent, int32_t prefetch,
-                            int32_t remote, char* out, uint64_t capacity);
+                            int32_t remote, int32_t xchg_bits, const uint8_t* xchg_vj /* V[3] then J[3] */, char* out,
+                            uint64_t capacity);
 int64_t qb_jit_compile_debug(const char* source, double* ms, void* cubin_out, uint64_t capacity);
 
 const char* qb_version(void);

@@ -21,6 +21,7 @@ QB_OPT_FUSION, QB_OPT_TILE_BITS, QB_OPT_MAX_QUEUE, QB_OPT_FORCE_PATH, QB_OPT_PRO
 QB_OPT_JIT, QB_OPT_JIT_MIN_QUBITS, QB_OPT_JIT_VARIANT = 6, 7, 8
 (QB_STAT_JIT_LAUNCHES, QB_STAT_JIT_COMPILES, QB_STAT_JIT_MISSES, QB_STAT_JIT_COMPILE_MS, QB_STAT_JIT_PENDING,
  QB_STAT_JIT_FAILED) = 12, 13, 14, 15, 16, 17
+QB_STAT_FUSED_EXCHANGES = 18
 (QB_STAT_KERNEL_LAUNCHES, QB_STAT_PASSES, QB_STAT_GATES, QB_STAT_BYTES_MOVED, QB_STAT_SWAP_BYTES,
  QB_STAT_SWAPS, QB_STAT_TILE_LAUNCHES, QB_STAT_TILE_NS, QB_STAT_ROUNDS, QB_STAT_P2P_EXCHANGES,
  QB_STAT_REMOTE_PASSES) = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11
@@ -102,7 +103,7 @@ SIGNATURES = {
     "qb_plan_debug": (ctypes.c_int64, [ctypes.c_uint32, ctypes.POINTER(QbGate), ctypes.c_uint64, ctypes.c_uint32,
                                        _i32p, _i32p]),
     "qb_jit_source_debug": (ctypes.c_int64, [ctypes.c_char_p, ctypes.c_uint64, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
-                                             ctypes.c_int32, ctypes.c_char_p, ctypes.c_uint64]),
+                                             ctypes.c_int32, ctypes.c_int32, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_uint64]),
     "qb_jit_compile_debug": (ctypes.c_int64, [ctypes.c_char_p, ctypes.POINTER(ctypes.c_double), ctypes.c_void_p, ctypes.c_uint64]),
     "qb_jit_drain": (ctypes.c_int, []),
 }

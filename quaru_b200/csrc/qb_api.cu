@@ -686,6 +686,7 @@ int qb_get_stat(qb_reg* reg, int32_t stat, int64_t* value) try {
         case QB_STAT_JIT_LAUNCHES: *value = r->st_jit_launches; return QB_OK;
         case QB_STAT_JIT_COMPILES: *value = r->st_jit_compiles; return QB_OK;
         case QB_STAT_JIT_MISSES: *value = r->st_jit_misses; return QB_OK;
+        case QB_STAT_FUSED_EXCHANGES: *value = r->st_fused_exchanges; return QB_OK;
         case QB_STAT_JIT_COMPILE_MS:
         case QB_STAT_JIT_PENDING:
         case QB_STAT_JIT_FAILED: {

@@ -79,6 +79,7 @@ void make_swap_gate(uint32_t a, uint32_t b, Gate* out);
 
 // ---- the handle ----------------------------------------------------------------------------------
 struct Shard;  // multi-GPU state (qb_shard.cu)
+struct XchgArgs;  // an exchange carried by the stores of a tile pass (qb_jit.h)
 struct Group;  // P shards driven from one process (qb_group.cu)
 
 struct Reg {
@@ -120,6 +121,11 @@ struct Reg {
     int rank = 0, world = 1;
     Shard* shard = nullptr;
     Group* group = nullptr;  // set on every shard of an in-process (QB_NUM_GPUS) register
+    // The shard scheduler asks the LAST pass of the next run_fused to carry a global<->local exchange in its stores
+    // (xchg_request); run_fused raises xchg_last_pass around that launch; the launcher reports xchg_done.
+    const XchgArgs* xchg_request = nullptr;
+    bool xchg_last_pass = false, xchg_done = false;
+    int64_t st_fused_exchanges = 0;
     std::vector<uint32_t> phys_of;  // logical qubit -> physical bit position
     // SWAP relabelling (above the placement): caller's qubit q is engine ("logical") qubit label[q]
     bool relabel = false;

@@ -129,7 +129,10 @@ void fnv(const void* data, size_t len, uint64_t* a, uint64_t* b) {
 }
 Key key_of(const ProgView& p, const JitOpts& o) {
     uint64_t a = 0xcbf29ce484222325ull, b = 0x84222325cbf29ce4ull;
-    const uint32_t hdr[9] = {p.lc, p.h, p.n_rounds, p.n_mats, p.n_ops, (uint32_t)o.min_blocks, (uint32_t)o.persistent, (uint32_t)o.prefetch, (uint32_t)o.remote};
+    const uint32_t hdr[12] = {p.lc, p.h, p.n_rounds, p.n_mats, p.n_ops, (uint32_t)o.min_blocks, (uint32_t)o.persistent, (uint32_t)o.prefetch,
+                              (uint32_t)o.remote, (uint32_t)o.xchg_bits,
+                              (uint32_t)o.xchg_V[0] | ((uint32_t)o.xchg_V[1] << 8) | ((uint32_t)o.xchg_V[2] << 16),
+                              (uint32_t)o.xchg_J[0] | ((uint32_t)o.xchg_J[1] << 8) | ((uint32_t)o.xchg_J[2] << 16)};
     fnv(hdr, sizeof(hdr), &a, &b);
     fnv(p.hp, p.h, &a, &b);   // only the entries in use are initialised
     fnv(p.gro_first, 128, &a, &b);
@@ -258,7 +261,7 @@ int jit_drain() {
     return QB_OK;
 }
 
-int jit_try_launch(Reg* r, const ProgView& p, const RemoteArgs* remote, bool* launched) {
+int jit_try_launch(Reg* r, const ProgView& p, const RemoteArgs* remote, bool* launched, const XchgArgs* xchg) {
     *launched = false;
     if (r->jit == 0 || r->n_local < r->jit_min_qubits || r->device < 0 || r->device >= 16) return QB_OK;
     JitOpts o;
@@ -266,22 +269,30 @@ int jit_try_launch(Reg* r, const ProgView& p, const RemoteArgs* remote, bool* la
     o.persistent = r->jit_persistent;
     o.prefetch = r->jit_persistent ? r->jit_prefetch : 0;
     o.remote = remote != nullptr;
+    if (xchg) {
+        o.xchg_bits = xchg->gp;
+        for (int i = 0; i < xchg->gp; ++i) { o.xchg_V[i] = xchg->V[i]; o.xchg_J[i] = xchg->J[i]; }
+        o.persistent = o.prefetch = 0;
+    }
+    // An exchanging pass is a collective decision: whether it runs must not depend on how far this rank's compiler got, so its
+    // kernel is always waited for, and a failure is an error on every rank alike.
+    const bool must_wait = r->jit == 2 || xchg != nullptr;
     bool fresh = false;
     std::shared_ptr<Entry> e = lookup_or_submit(p, o, &fresh);
     if (fresh) r->st_jit_compiles++;
     if (e->state.load() == 0) {
-        if (r->jit != 2) { r->st_jit_misses++; return QB_OK; }   // asynchronous mode: the interpreter runs this pass
+        if (!must_wait) { r->st_jit_misses++; return QB_OK; }   // asynchronous mode: the interpreter runs this pass
         std::unique_lock<std::mutex> lk(g_mu);
         g_idle_cv.wait(lk, [&] { return e->state.load() != 0; });
     }
     if (e->state.load() < 0) {
-        if (r->jit == 2) return set_error(QB_ERR_UNSUPPORTED, -1, "JIT compilation failed: %.600s", e->log.c_str());
+        if (must_wait) return set_error(QB_ERR_UNSUPPORTED, -1, "JIT compilation failed: %.600s", e->log.c_str());
         r->st_jit_misses++;
         return QB_OK;
     }
     int rc = load_on_device(e.get(), r->device);
     if (rc != QB_OK) {
-        if (r->jit == 2) return rc;
+        if (must_wait) return rc;
         r->st_jit_misses++;
         return QB_OK;
     }
@@ -295,17 +306,30 @@ int jit_try_launch(Reg* r, const ProgView& p, const RemoteArgs* remote, bool* la
         grid = (unsigned)std::min<uint64_t>(tiles, (uint64_t)sms * (uint64_t)e->per_sm[r->device]);
     }
     RemoteArgs ra;
-    void* args[3];
+    void* args[5];
     c64* st = r->state;
-    if (remote) {
-        ra = *remote;
-        tile_or = ra.tile_or;
-        args[0] = &ra;
-    } else {
+    uint32_t rank = 0;
+    if (xchg) {   // (st, out table, rank, tile_or, n_tiles)
+        memset(&ra, 0, sizeof(ra));
+        for (int q = 0; q < 8; ++q) ra.base[q] = xchg->out[q];
+        ra.n_local = r->n_local;
+        rank = xchg->rank;
         args[0] = &st;
+        args[1] = &ra;
+        args[2] = &rank;
+        args[3] = &tile_or;
+        args[4] = &n_tiles;
+    } else {
+        if (remote) {
+            ra = *remote;
+            tile_or = ra.tile_or;
+            args[0] = &ra;
+        } else {
+            args[0] = &st;
+        }
+        args[1] = &tile_or;
+        args[2] = &n_tiles;
     }
-    args[1] = &tile_or;
-    args[2] = &n_tiles;
     if (r->profile) QB_TRY(tile_profile_begin(r));
     rc = driver()->LaunchKernel(e->fn[r->device], grid, 1, 1, RTHREADS, 1, 1, (unsigned)(sizeof(c64) << RT), (void*)r->stream, args, nullptr);
     if (rc) return fail_cu(rc, "cuLaunchKernel(qb_jit_pass)");
@@ -350,7 +374,7 @@ using namespace qb;
 extern "C" {
 
 int64_t qb_jit_source_debug(const void* program, uint64_t len, int32_t min_blocks, int32_t persistent, int32_t prefetch, int32_t remote,
-                            char* out, uint64_t capacity) try {
+                            int32_t xchg_bits, const uint8_t* xchg_vj, char* out, uint64_t capacity) try {
     if (!program || (capacity && !out)) return set_error(QB_ERR_INVALID_ARGUMENT, -1, "NULL argument");
     static thread_local RProgLarge prog;
     uint32_t n_ops = 0;
@@ -360,6 +384,9 @@ int64_t qb_jit_source_debug(const void* program, uint64_t len, int32_t min_block
     o.persistent = persistent;
     o.prefetch = prefetch;
     o.remote = remote;
+    if (xchg_bits < 0 || xchg_bits > 3 || (xchg_bits && !xchg_vj)) return set_error(QB_ERR_INVALID_ARGUMENT, xchg_bits, "0..3 exchanged bits");
+    o.xchg_bits = xchg_bits;
+    for (int i = 0; i < xchg_bits; ++i) { o.xchg_V[i] = xchg_vj[i]; o.xchg_J[i] = xchg_vj[3 + i]; }
     const std::string src = jit_generate(make_view(prog), o);
     if (src.size() + 1 > capacity) return set_error(QB_ERR_INVALID_ARGUMENT, (int64_t)src.size() + 1, "buffer too small");
     memcpy(out, src.c_str(), src.size() + 1);

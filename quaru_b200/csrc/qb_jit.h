@@ -29,12 +29,24 @@ struct JitOpts {
     int persistent = 0;   // CTAs walk the tiles (grid = resident CTAs) instead of one CTA per tile
     int prefetch = 0;     // persistent only: prefetch.global.L2 of the next tile after the current tile's loads were issued
     int remote = 0;       // sharded registers: amplitudes addressed through the table of peer-mapped shards
+    // sharded registers, the exchanging epilogue: the pass stores every amplitude where it lives after the exchange of local
+    // bits xchg_V[i] with rank bits xchg_J[i], into the destination rank's other state buffer (0 = an ordinary pass)
+    int xchg_bits = 0;
+    uint8_t xchg_V[3] = {0, 0, 0}, xchg_J[3] = {0, 0, 0};
+};
+
+// what the launch of an exchanging pass needs beside the program
+struct XchgArgs {
+    int gp = 0;
+    uint8_t V[3] = {0, 0, 0}, J[3] = {0, 0, 0};   // ascending V
+    c64* out[8] = {nullptr};                      // every rank's other buffer (out[own rank] = own other buffer)
+    uint32_t rank = 0;
 };
 
 std::string jit_generate(const ProgView& p, const JitOpts& o);
 
 // Launch path (qb_tile2.cu).  *launched = true if a specialised kernel ran the pass; false: the caller runs the interpreter
 // kernel (compile pending, JIT off, or unavailable).  With r->jit == 2 the call waits for the compiler and a failure is an error.
-int jit_try_launch(Reg* r, const ProgView& p, const RemoteArgs* remote, bool* launched);
+int jit_try_launch(Reg* r, const ProgView& p, const RemoteArgs* remote, bool* launched, const XchgArgs* xchg = nullptr);
 
 }  // namespace qb

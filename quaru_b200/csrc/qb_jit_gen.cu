@@ -39,6 +39,7 @@ typedef unsigned long long u64;
 struct QbRemote { double2* base[8]; u32 n_local; u32 pad; };
 #define QB_KERNEL(name, minb) extern "C" __global__ void __launch_bounds__(256, minb) name(double2* __restrict__ st, u32 tile_or, u32 n_tiles)
 #define QB_KERNEL_REMOTE(name, minb) extern "C" __global__ void __launch_bounds__(256, minb) name(const __grid_constant__ QbRemote ra, u32 tile_or, u32 n_tiles)
+#define QB_KERNEL_XCHG(name, minb) extern "C" __global__ void __launch_bounds__(256, minb) name(const double2* __restrict__ st, const __grid_constant__ QbRemote out, u32 rank, u32 tile_or, u32 n_tiles)
 )QB";
 
 struct Gen {
@@ -383,7 +384,7 @@ struct Gen {
 
     std::string run() {
         // ---- kernel body ----
-        f("%s(qb_jit_pass, %d)\n{\n", o.remote ? "QB_KERNEL_REMOTE" : "QB_KERNEL", o.min_blocks);
+        f("%s(qb_jit_pass, %d)\n{\n", o.xchg_bits > 0 ? "QB_KERNEL_XCHG" : o.remote ? "QB_KERNEL_REMOTE" : "QB_KERNEL", o.min_blocks);
         s += "    QB_SMEM(tile);\n    const u32 tid = QB_TID;\n";
         if (o.remote) s += "    const u64 lmask = (1ull << ra.n_local) - 1ull;\n";
         if (o.persistent) s += "    for (u32 t0 = QB_BID; t0 < n_tiles; t0 += QB_GRID) {\n    const u32 tix = t0 | tile_or;\n";
@@ -440,10 +441,28 @@ struct Gen {
         }
         // last round: registers -> HBM
         f("    {\n      const u64 gt = base + (%s);\n", goff_expr().c_str());
-        for (int j = 0; j < 16; ++j) {
-            char off[64];
-            snprintf(off, sizeof(off), "gt + 0x%llxull", (unsigned long long)p.gro_last[j]);
-            f("      QB_ST(%s, %s, %s);\n", amp_ptr(off).c_str(), X(j).c_str(), Y(j).c_str());
+        if (o.xchg_bits > 0) {
+            // The exchanging epilogue (sharded registers): the amplitude at local index l of this rank is stored where it lives
+            // AFTER the global<->local exchange of local bits V[i] with rank bits J[i] -- rank bit J[i] of the destination is bit
+            // V[i] of l, bit V[i] of the destination index is this rank's bit J[i] -- into the destination rank's OTHER state
+            // buffer (out.base[]), which nobody reads during this pass.  The transfer rides on the pass's stores (posted writes
+            // over NVLink), tile by tile, while other CTAs compute.
+            uint32_t jmask = 0;
+            for (int i = 0; i < o.xchg_bits; ++i) jmask |= 1u << o.xchg_J[i];
+            f("      const u32 rk0 = rank & ~0x%xu;\n", jmask);
+            for (int i = 0; i < o.xchg_bits; ++i) f("      const u64 rb%d = (u64)((rank >> %u) & 1u) << %u;\n", i, o.xchg_J[i], o.xchg_V[i]);
+            for (int j = 0; j < 16; ++j) {
+                f("      { const u64 l_ = gt + 0x%llxull; u32 dr_ = rk0; u64 dl_ = l_;\n", (unsigned long long)p.gro_last[j]);
+                for (int i = 0; i < o.xchg_bits; ++i)
+                    f("        dr_ |= ((u32)(l_ >> %u) & 1u) << %u; dl_ = (dl_ & ~(1ull << %u)) | rb%d;\n", o.xchg_V[i], o.xchg_J[i], o.xchg_V[i], i);
+                f("        QB_ST(out.base[dr_] + dl_, %s, %s); }\n", X(j).c_str(), Y(j).c_str());
+            }
+        } else {
+            for (int j = 0; j < 16; ++j) {
+                char off[64];
+                snprintf(off, sizeof(off), "gt + 0x%llxull", (unsigned long long)p.gro_last[j]);
+                f("      QB_ST(%s, %s, %s);\n", amp_ptr(off).c_str(), X(j).c_str(), Y(j).c_str());
+            }
         }
         s += "    }\n";
         if (o.persistent) s += "    }\n";

@@ -25,6 +25,7 @@
 #include <algorithm>
 #include <mutex>
 
+#include "qb_jit.h"
 #include "qb_shard.h"
 #include "qb_tile.h"
 #include "qb_device.cuh"
@@ -92,6 +93,10 @@ struct Shard {
     std::vector<int32_t> events;       // dry run: [gate index, g', V..., J...] per exchange
     int64_t cur_gate = -1;
     int64_t dry_passes = 0;            // dry run: state sweeps the local planner would need for the epochs so far
+    // second state buffer for exchanges carried by a tile pass's stores (see shard_run_reordered); nullptr if it does not fit
+    c64* alt = nullptr;
+    c64* peer_alt[8] = {nullptr};      // every rank's second buffer as mapped here; peer_alt[rank] = alt
+    bool fused_ok = false;             // all ranks have it, mapped everywhere
     // placement memory (see shard_run): gate-list hash -> the placement the list was first run from
     struct Seen { uint64_t hash; std::vector<uint32_t> phys_of; };
     std::vector<Seen> seen;
@@ -112,6 +117,73 @@ int shard_unique_id(void* out128) {
     QB_NCCL(g_nccl.GetUniqueId(&id));
     memcpy(out128, &id, 128);
     return QB_OK;
+}
+
+// Maps buffer `mine` of every rank into this process: CUDA IPC handles all-gathered through NCCL (SPMD), or the peers' plain
+// device pointers after cudaDeviceEnablePeerAccess (in-process registers).  COLLECTIVE: every rank calls it, also one whose
+// `mine` is nullptr (it publishes a handle nobody can open).  *opened = number of ranks whose buffer is reachable from here.
+static int map_peer_buffers(Reg* r, c64* mine, c64* const* group_ptrs, c64** table, int* opened) {
+    Shard* s = r->shard;
+    *opened = 0;
+    if (r->group) {
+        bool ok = mine != nullptr;
+        for (int p = 0; p < r->world; ++p) {
+            table[p] = group_ptrs[p];
+            ok = ok && group_ptrs[p] != nullptr;
+            if (p == r->rank) continue;
+            const cudaError_t e = cudaDeviceEnablePeerAccess(group_member(r->group, p)->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) ok = false;
+            cudaGetLastError();
+        }
+        *opened = ok ? r->world : 0;
+        return QB_OK;
+    }
+    cudaIpcMemHandle_t h, all[8];
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    bool ok = mine != nullptr && cudaIpcGetMemHandle(&h, mine) == cudaSuccess;
+    if (!ok) memset(&h, 0, sizeof(h));
+    cudaGetLastError();
+    char* dbuf = nullptr;
+    QB_CUDA(cudaMalloc((void**)&dbuf, 64 * (r->world + 1)));
+    const bool moved = cudaMemcpyAsync(dbuf, &h, 64, cudaMemcpyHostToDevice, r->stream) == cudaSuccess &&
+                       g_nccl.AllGather(dbuf, dbuf + 64, 64, ncclChar, s->comm, r->stream) == ncclSuccess &&
+                       cudaMemcpyAsync(all, dbuf + 64, 64 * r->world, cudaMemcpyDeviceToHost, r->stream) == cudaSuccess &&
+                       cudaStreamSynchronize(r->stream) == cudaSuccess;
+    cudaFree(dbuf);
+    if (!moved) return set_error(QB_ERR_NCCL, -1, "exchange of the shards' IPC handles failed");
+    if (ok) {
+        for (int p = 0; p < r->world; ++p) {
+            if (p == r->rank) { table[p] = mine; ++*opened; continue; }
+            void* ptr = nullptr;
+            if (cudaIpcOpenMemHandle(&ptr, all[p], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) break;
+            table[p] = (c64*)ptr;
+            ++*opened;
+        }
+    }
+    cudaGetLastError();   // a failed IPC call must not poison later launches
+    return QB_OK;
+}
+
+// all ranks agree on a yes / no (a two-double all-gather)
+static int agree_all(Reg* r, bool mine, bool* all) {
+    Shard* s = r->shard;
+    double h[2] = {mine ? 1.0 : 0.0, 0.0};
+    std::vector<double> flags(2 * r->world);
+    QB_CUDA(cudaMemcpyAsync(s->d_gather, h, sizeof(h), cudaMemcpyHostToDevice, r->stream));
+    QB_NCCL(g_nccl.AllGather(s->d_gather, s->d_gather + 2, 2, ncclDouble, s->comm, r->stream));
+    QB_CUDA(cudaMemcpyAsync(flags.data(), s->d_gather + 2, 2 * r->world * sizeof(double), cudaMemcpyDeviceToHost, r->stream));
+    QB_CUDA(cudaStreamSynchronize(r->stream));
+    *all = true;
+    for (int p = 0; p < r->world; ++p) *all = *all && flags[2 * p] == 1.0;
+    return QB_OK;
+}
+
+static void unmap_peer_buffers(Reg* r, c64** table) {
+    for (int p = 0; p < 8; ++p) {
+        if (table[p] && p != r->rank && !r->group) cudaIpcCloseMemHandle(table[p]);
+        table[p] = nullptr;
+    }
+    cudaGetLastError();
 }
 
 int shard_init(Reg* r, const void* unique_id) {
@@ -135,71 +207,47 @@ int shard_init(Reg* r, const void* unique_id) {
     QB_CUDA(cudaMalloc((void**)&s->d_gather, (2 + 2 * r->world) * sizeof(double)));
     s->logical_at.resize(r->n);
     for (uint32_t q = 0; q < r->n; ++q) s->logical_at[q] = q;
-    // peer-memory transport: exchange CUDA IPC handles of the shards through NCCL and map every peer's shard
+    // peer-memory transport: every rank maps every peer's shard
     const char* tr = getenv("QB_SHARD_TRANSPORT");
     if (!(tr && !strcmp(tr, "nccl")) && r->world <= 8) {
-        int opened = 0;
+        c64* gp[8] = {nullptr};
         if (r->group) {
-            // in-process register (qb_group.cu): the peers' shards are ordinary device pointers of this process
             group_barrier(r->group);   // every rank has allocated its shard
-            bool ok = true;
-            for (int p = 0; p < r->world; ++p) {
-                Reg* m = group_member(r->group, p);
-                s->peer[p] = m->state;
-                if (p == r->rank) continue;
-                const cudaError_t e = cudaDeviceEnablePeerAccess(m->device, 0);
-                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) ok = false;
-                cudaGetLastError();
-            }
-            opened = ok ? r->world : 0;
-        } else {
-        cudaIpcMemHandle_t mine, all[8];
-        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
-        // Every rank takes part in both all-gathers whatever happened locally (a rank that skipped one would hang
-        // the others); a rank whose export failed publishes a zeroed handle, which no peer can open.
-        char* dbuf = nullptr;
-        bool ok = cudaIpcGetMemHandle(&mine, r->state) == cudaSuccess;
-        if (!ok) memset(&mine, 0, sizeof(mine));
-        cudaGetLastError();
-        QB_CUDA(cudaMalloc((void**)&dbuf, 64 * (r->world + 1)));
-        {
-            const bool moved = cudaMemcpyAsync(dbuf, &mine, 64, cudaMemcpyHostToDevice, r->stream) == cudaSuccess &&
-                               g_nccl.AllGather(dbuf, dbuf + 64, 64, ncclChar, s->comm, r->stream) == ncclSuccess &&
-                               cudaMemcpyAsync(all, dbuf + 64, 64 * r->world, cudaMemcpyDeviceToHost, r->stream) == cudaSuccess &&
-                               cudaStreamSynchronize(r->stream) == cudaSuccess;
-            cudaFree(dbuf);
-            if (!moved) return set_error(QB_ERR_NCCL, -1, "exchange of the shards' IPC handles failed");
+            for (int p = 0; p < r->world; ++p) gp[p] = group_member(r->group, p)->state;
         }
-        if (ok) {
-            for (int p = 0; p < r->world; ++p) {
-                if (p == r->rank) { s->peer[p] = r->state; ++opened; continue; }
-                void* ptr = nullptr;
-                if (cudaIpcOpenMemHandle(&ptr, all[p], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) break;
-                s->peer[p] = (c64*)ptr;
-                ++opened;
-            }
-        }
-        }
-        cudaGetLastError();   // a failed IPC call must not poison later launches
-        // all ranks must agree on the transport: gather the success flags
-        std::vector<double> flags;
-        double h[2] = {opened == r->world ? 1.0 : 0.0, 0.0};
-        QB_CUDA(cudaMemcpyAsync(s->d_gather, h, sizeof(h), cudaMemcpyHostToDevice, r->stream));
-        QB_NCCL(g_nccl.AllGather(s->d_gather, s->d_gather + 2, 2, ncclDouble, s->comm, r->stream));
-        flags.resize(2 * r->world);
-        QB_CUDA(cudaMemcpyAsync(flags.data(), s->d_gather + 2, 2 * r->world * sizeof(double), cudaMemcpyDeviceToHost, r->stream));
-        QB_CUDA(cudaStreamSynchronize(r->stream));
-        s->p2p = true;
-        for (int p = 0; p < r->world; ++p) s->p2p = s->p2p && flags[2 * p] == 1.0;
+        int opened = 0;
+        QB_TRY(map_peer_buffers(r, r->state, gp, s->peer, &opened));
+        QB_TRY(agree_all(r, opened == r->world, &s->p2p));   // all ranks must agree on the transport
         if (!s->p2p) {   // agreed fallback to NCCL send/recv: unmap whatever was mapped, then let nobody run ahead and
                          // free a shard that a slower peer still has mapped
-            for (int p = 0; p < 8; ++p) {
-                if (s->peer[p] && p != r->rank && !r->group) cudaIpcCloseMemHandle(s->peer[p]);
-                s->peer[p] = nullptr;
-            }
-            cudaGetLastError();
+            unmap_peer_buffers(r, s->peer);
             QB_NCCL(g_nccl.AllGather(s->d_gather, s->d_gather + 2, 2, ncclDouble, s->comm, r->stream));
             QB_CUDA(cudaStreamSynchronize(r->stream));
+        }
+    }
+    // Second state buffer (exchanges carried by a pass's stores): only where it fits beside the shard -- 33 qubits on any
+    // number of GPUs, 35 qubits on 8 -- and only if every rank got and mapped one.  QB_SHARD_FUSED_EXCHANGE=0 disables it.
+    const char* fe = getenv("QB_SHARD_FUSED_EXCHANGE");
+    if (s->p2p && !(fe && fe[0] == '0') && r->n_local >= 12) {
+        const size_t shard_bytes = sizeof(c64) << r->n_local;
+        QB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        if (free_b > shard_bytes + (6ull << 30) && cudaMalloc((void**)&s->alt, shard_bytes) != cudaSuccess) s->alt = nullptr;
+        cudaGetLastError();
+        c64* gp[8] = {nullptr};
+        if (r->group) {
+            group_barrier(r->group);   // every rank has tried
+            for (int p = 0; p < r->world; ++p) gp[p] = group_member(r->group, p)->shard->alt;
+            group_barrier(r->group);
+        }
+        int opened = 0;
+        QB_TRY(map_peer_buffers(r, s->alt, gp, s->peer_alt, &opened));
+        QB_TRY(agree_all(r, opened == r->world, &s->fused_ok));
+        if (!s->fused_ok) {
+            unmap_peer_buffers(r, s->peer_alt);
+            QB_NCCL(g_nccl.AllGather(s->d_gather, s->d_gather + 2, 2, ncclDouble, s->comm, r->stream));   // nobody frees a buffer a peer still maps
+            QB_CUDA(cudaStreamSynchronize(r->stream));
+            if (s->alt) cudaFree(s->alt);
+            s->alt = nullptr;
         }
     }
     return QB_OK;
@@ -215,14 +263,15 @@ void shard_reset_placement(Reg* r) {
 void shard_destroy(Reg* r) {
     Shard* s = r->shard;
     if (!s) return;
-    for (int p = 0; p < 8; ++p)
-        if (s->peer[p] && p != r->rank && !r->group) cudaIpcCloseMemHandle(s->peer[p]);
+    unmap_peer_buffers(r, s->peer);
+    unmap_peer_buffers(r, s->peer_alt);
     // nobody frees its shard before every peer has unmapped it; keyed on the transport all ranks agreed on, so
     // that every rank makes the same collective calls
     if (s->p2p && s->comm && s->d_gather && g_nccl.AllGather) {
         g_nccl.AllGather(s->d_gather, s->d_gather + 2, 2, ncclDouble, s->comm, r->stream);
         cudaStreamSynchronize(r->stream);
     }
+    if (s->alt) cudaFree(s->alt);
     if (s->staging) cudaFree(s->staging);
     if (s->d_gather) cudaFree(s->d_gather);
     if (s->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(s->comm);
@@ -463,7 +512,8 @@ static MapResult map_gate(const Reg* r, const Gate& g, Gate* out) {
 }
 
 // Chooses and performs the exchange needed before gates[i] (a dense gate with a global target).
-static int swap_for(Reg* r, const std::vector<Gate>& gates, size_t i, const std::vector<char>* done = nullptr) {
+static int choose_swap(Reg* r, const std::vector<Gate>& gates, size_t i, const std::vector<char>* done, std::vector<uint32_t>* Vout,
+                       std::vector<uint32_t>* Jout) {
     Shard* s = r->shard;
     const uint32_t nl = r->n_local, n = r->n;
     const size_t INF = (size_t)-1;
@@ -509,7 +559,35 @@ static int swap_for(Reg* r, const std::vector<Gate>& gates, size_t i, const std:
         J.push_back(j);
     }
     if (V.empty()) return set_error(QB_ERR_UNSUPPORTED, (int64_t)i, "internal: no exchange candidate");
+    *Vout = V;
+    *Jout = J;
+    return QB_OK;
+}
+
+static int swap_for(Reg* r, const std::vector<Gate>& gates, size_t i, const std::vector<char>* done = nullptr) {
+    std::vector<uint32_t> V, J;
+    QB_TRY(choose_swap(r, gates, i, done, &V, &J));
     return exchange(r, V, J);
+}
+
+// The exchange has been carried by the stores of the epoch's last tile pass (every amplitude already sits in the destination
+// rank's second buffer): wait for every peer's stores, make the second buffers the state, update the placement.
+static int finish_fused_exchange(Reg* r, std::vector<uint32_t> V, std::vector<uint32_t> J) {
+    Shard* s = r->shard;
+    const uint32_t gp = (uint32_t)V.size();
+    QB_TRY(barrier_all(r));
+    std::swap(r->state, s->alt);
+    for (int p = 0; p < 8; ++p) std::swap(s->peer[p], s->peer_alt[p]);
+    r->st_swap_bytes += (int64_t)(((1ull << gp) - 1) * (1ull << (r->n_local - gp)) * sizeof(c64));
+    r->st_swaps++;
+    r->st_fused_exchanges++;
+    for (uint32_t i = 0; i < gp; ++i) {
+        const uint32_t pl = V[i], pg = r->n_local + J[i];
+        const uint32_t ql = s->logical_at[pl], qg = s->logical_at[pg];
+        s->logical_at[pl] = qg; s->logical_at[pg] = ql;
+        r->phys_of[qg] = pl; r->phys_of[ql] = pg;
+    }
+    return QB_OK;
 }
 
 // Commutation-aware scheduler (the default; QB_SHARD_REORDER=0 selects the first scheduler below): instead of cutting the gate
@@ -547,12 +625,39 @@ static int shard_run_reordered(Reg* r, std::vector<Gate>& gates) {
             done[i] = 1;
             --remaining;
         }
-        if (!batch.empty() && !s->dry) QB_TRY(run_local(r, batch));
+        if (remaining && first_deferred == (size_t)-1) return set_error(QB_ERR_UNSUPPORTED, -1, "internal: scheduler made no progress");
+        // The exchange that follows this epoch depends on the placement and the gate list only: it is chosen BEFORE the epoch's
+        // passes are launched, so that the last of them can carry it in its stores (every amplitude goes straight to where it
+        // lives after the exchange, in the destination rank's second buffer: posted writes over NVLink, overlapped with the
+        // pass's compute, instead of a separate pull-and-push sweep of the exchange kernel).
+        std::vector<uint32_t> V, J;
+        if (remaining) {
+            s->cur_gate = gates[first_deferred].tag >= 0 ? gates[first_deferred].tag : (int64_t)first_deferred;
+            QB_TRY(choose_swap(r, gates, first_deferred, &done, &V, &J));
+        }
+        bool fused = false;
+        if (!batch.empty() && !s->dry) {
+            XchgArgs xa;
+            if (remaining && s->fused_ok && V.size() <= 3) {
+                std::vector<size_t> ord(V.size());
+                for (size_t i = 0; i < ord.size(); ++i) ord[i] = i;
+                std::sort(ord.begin(), ord.end(), [&](size_t a, size_t b) { return V[a] < V[b]; });
+                xa.gp = (int)V.size();
+                for (size_t i = 0; i < ord.size(); ++i) { xa.V[i] = (uint8_t)V[ord[i]]; xa.J[i] = (uint8_t)J[ord[i]]; }
+                for (int p = 0; p < r->world; ++p) xa.out[p] = s->peer_alt[p];
+                xa.rank = (uint32_t)r->rank;
+                r->xchg_request = &xa;
+                r->xchg_done = false;
+            }
+            const int rc = run_local(r, batch);
+            r->xchg_request = nullptr;
+            QB_TRY(rc);
+            fused = r->xchg_done;
+            r->xchg_done = false;
+        }
         if (!batch.empty() && s->dry) s->dry_passes += count_passes(r, batch);
         if (!remaining) break;
-        if (first_deferred == (size_t)-1) return set_error(QB_ERR_UNSUPPORTED, -1, "internal: scheduler made no progress");
-        s->cur_gate = gates[first_deferred].tag >= 0 ? gates[first_deferred].tag : (int64_t)first_deferred;
-        QB_TRY(swap_for(r, gates, first_deferred, &done));
+        if (fused) QB_TRY(finish_fused_exchange(r, V, J)); else QB_TRY(exchange(r, V, J));
         Gate probe;
         if (map_gate(r, gates[first_deferred], &probe) == MAP_NEEDS_SWAP)
             return set_error(QB_ERR_UNSUPPORTED, (int64_t)first_deferred, "internal: gate still global after exchange");

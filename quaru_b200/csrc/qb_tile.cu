@@ -458,7 +458,10 @@ int run_fused(Reg* r, std::vector<Gate>& gates, std::vector<Gate>* hold) {
         if (hold && launched_any) {
             for (size_t gi : prev.gate_idx) hold->push_back(gates[gi]);
         } else {
-            QB_TRY(launch(prev));
+            r->xchg_last_pass = r->xchg_request != nullptr;   // sharded registers: this pass may carry the exchange that follows it
+            const int rc_last = launch(prev);
+            r->xchg_last_pass = false;
+            QB_TRY(rc_last);
         }
     }
     return QB_OK;

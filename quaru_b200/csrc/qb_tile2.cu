@@ -735,7 +735,13 @@ static int launch_rpass(Reg* r, const Prog& prog) {
     const uint64_t tiles = 1ull << (r->n_local - RT);
     if (tiles > 0x7fffffffull) return set_error(QB_ERR_UNSUPPORTED, (int64_t)tiles, "too many tiles for one grid");
     bool jitted = false;   // the pass's specialised kernel, if it is ready (qb_jit.cu); else the interpreter kernel below
-    QB_TRY(jit_try_launch(r, make_view(prog), nullptr, &jitted));
+    if (r->xchg_last_pass && r->xchg_request) {
+        // sharded registers: the last pass before a global<->local exchange stores every amplitude where it lives after the
+        // exchange, in the destination rank's other buffer (specialised kernels only; qb_shard.cu flips the buffers afterwards)
+        QB_TRY(jit_try_launch(r, make_view(prog), nullptr, &jitted, r->xchg_request));
+        r->xchg_done = jitted;
+    }
+    if (!jitted) QB_TRY(jit_try_launch(r, make_view(prog), nullptr, &jitted));
     if (!jitted) {
         if (r->profile) QB_TRY(tile_profile_begin(r));
         k2r_tile_pass<Prog><<<(unsigned)tiles, RTHREADS, sizeof(c64) << RT, r->stream>>>(r->state, prog);

@@ -162,7 +162,7 @@ int64_t shard_plan_debug(uint32_t, int, int, std::vector<Gate>&, int32_t*, uint6
 }  // namespace qb
 
 // the specialised-kernel entry points live in qb_jit.cu (not part of the host build)
-extern "C" int64_t qb_jit_source_debug(const void*, uint64_t, int32_t, int32_t, int32_t, int32_t, char*, uint64_t) { return qb::set_error(QB_ERR_UNSUPPORTED, -1, "host stand-in"); }
+extern "C" int64_t qb_jit_source_debug(const void*, uint64_t, int32_t, int32_t, int32_t, int32_t, int32_t, const uint8_t*, char*, uint64_t) { return qb::set_error(QB_ERR_UNSUPPORTED, -1, "host stand-in"); }
 extern "C" int64_t qb_jit_compile_debug(const char*, double*, void*, uint64_t) { return qb::set_error(QB_ERR_UNSUPPORTED, -1, "host stand-in"); }
 extern "C" int qb_jit_drain(void) { return QB_OK; }
 

@@ -16,6 +16,8 @@ double2* qb_emu_shared = g_shared;
 #include QB_JIT_SRC
 
 // grid = 0: one CTA per tile; else `grid` persistent CTAs.  remote: `bases` = world shard pointers, the tiles of rank `rank`.
+// exchanging pass (-DQB_JIT_XCHG): `state` = this rank's shard (read), `bases` = every rank's SECOND buffer (written),
+// `tile_or` carries the rank.
 extern "C" int jit_host_run(double* state, unsigned n_tiles, unsigned grid, unsigned tile_or, void* const* bases, unsigned world,
                             unsigned n_local) {
     const unsigned ctas = grid ? grid : n_tiles;
@@ -27,7 +29,13 @@ extern "C" int jit_host_run(double* state, unsigned n_tiles, unsigned grid, unsi
             for (unsigned b = 0; b < ctas; ++b) {
                 qb_emu_thread = {t, 0, 0};
                 qb_emu_block = {b, 0, 0};
-#ifdef QB_JIT_REMOTE
+#if defined(QB_JIT_XCHG)
+                QbRemote out;
+                for (unsigned p = 0; p < 8; ++p) out.base[p] = p < world ? reinterpret_cast<double2*>(bases[p]) : nullptr;
+                out.n_local = n_local;
+                out.pad = 0;
+                qb_jit_pass(reinterpret_cast<const double2*>(state), out, tile_or, 0u, n_tiles);
+#elif defined(QB_JIT_REMOTE)
                 QbRemote ra;
                 for (unsigned p = 0; p < 8; ++p) ra.base[p] = p < world ? reinterpret_cast<double2*>(bases[p]) : nullptr;
                 ra.n_local = n_local;

@@ -39,3 +39,4 @@ struct QbRemote {
 #define QB_GRID qb_emu_grid.x
 #define QB_KERNEL(name, minb) extern "C" void name(double2* st, u32 tile_or, u32 n_tiles)
 #define QB_KERNEL_REMOTE(name, minb) extern "C" void name(const QbRemote ra, u32 tile_or, u32 n_tiles)
+#define QB_KERNEL_XCHG(name, minb) extern "C" void name(const double2* st, const QbRemote out, u32 rank, u32 tile_or, u32 n_tiles)

@@ -110,8 +110,12 @@ def main():
             failures.append(f"repeated circuit: rank {rank} max|diff| {d.max():.3e}")
         if compiles[2] != compiles[1]:
             failures.append(f"repeated circuit: rank {rank} compiled new programs on the third application {compiles}")
+        fused_x = reg.stat(_ffi.QB_STAT_FUSED_EXCHANGES)
+        if os.environ.get("QB_SHARD_FUSED_EXCHANGE") != "0" and os.environ.get("QB_SHARD_TRANSPORT") != "nccl" and fused_x == 0:
+            failures.append(f"repeated circuit: rank {rank}: no exchange was carried by a tile pass")
         if rank == 0:
-            print(f"repeated circuit n={n}: programs compiled after each application {compiles}, exchanges {reg.stat(_ffi.QB_STAT_SWAPS)}", flush=True)
+            print(f"repeated circuit n={n}: programs compiled after each application {compiles}, exchanges {reg.stat(_ffi.QB_STAT_SWAPS)} "
+                  f"({fused_x} carried by a pass's stores)", flush=True)
         reg.close()
 
     if os.environ.get("QB_SHARD_REMOTE") == "1":

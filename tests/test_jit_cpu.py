@@ -25,19 +25,22 @@ KDIR = os.path.join(ROOT, "tests", "cpu_kernel")
 BUILD = os.path.join(KDIR, "_build", "jit")
 
 
-def jit_source(prog_bytes, min_blocks=2, persistent=0, prefetch=0, remote=0):
+def jit_source(prog_bytes, min_blocks=2, persistent=0, prefetch=0, remote=0, xchg=None):
     from quaru_b200 import _ffi
     L = _ffi.lib()
     cap = 8 << 20
     buf = ctypes.create_string_buffer(cap)
-    got = L.qb_jit_source_debug(prog_bytes, len(prog_bytes), min_blocks, persistent, prefetch, remote, buf, cap)
+    vj = None
+    if xchg:                                           # ([V...], [J...]): local bits V[i] traded against rank bits J[i]
+        vj = bytes(list(xchg[0]) + [0] * (3 - len(xchg[0])) + list(xchg[1]) + [0] * (3 - len(xchg[1])))
+    got = L.qb_jit_source_debug(prog_bytes, len(prog_bytes), min_blocks, persistent, prefetch, remote, len(xchg[0]) if xchg else 0, vj, buf, cap)
     assert got > 0, _ffi.last_error()
     return buf.raw[:got].decode()
 
 
-def build_host(src, remote=False):
+def build_host(src, remote=False, xchg=False):
     os.makedirs(BUILD, exist_ok=True)
-    tag = hashlib.sha1((src + str(remote)).encode()).hexdigest()[:16]
+    tag = hashlib.sha1((src + str(remote) + str(xchg)).encode()).hexdigest()[:16]
     cu, so = os.path.join(BUILD, tag + ".cu"), os.path.join(BUILD, tag + ".so")
     if not os.path.exists(so):
         with open(cu, "w") as f:
@@ -46,6 +49,8 @@ def build_host(src, remote=False):
                "-I", KDIR, os.path.join(KDIR, "jit_host_runner.cpp"), "-o", so]
         if remote:
             cmd.insert(5, "-DQB_JIT_REMOTE")
+        if xchg:
+            cmd.insert(5, "-DQB_JIT_XCHG")
         subprocess.check_call(cmd)
     lib = ctypes.CDLL(so)
     lib.jit_host_run.restype = ctypes.c_int
@@ -183,3 +188,43 @@ def test_remote_variant_over_separately_allocated_shards(world, n, kind):
             assert lib.jit_host_run(None, 1 << (nl - 12), 0, tile_or, bases, world, nl) == 0
     assert n_remote >= 1, "at least one pass has a rank bit among its tile bits"
     assert_close(np.concatenate(shards), ora.state, f"remote generated kernel vs oracle, world={world} n={n} {kind}")
+
+
+@pytest.mark.parametrize("world,n,kind,V,J", [(2, 14, "layers", [12], [0]), (4, 15, "mixed", [9, 12], [1, 0]), (8, 16, "qft", [7, 10, 12], [0, 2, 1]),
+                                             (4, 14, "layers", [5, 11], [0, 1]), (8, 15, "layers", [9, 10, 11], [2, 1, 0])])
+def test_exchanging_pass_stores_into_the_post_exchange_placement(world, n, kind, V, J):
+    """Sharded registers: the last pass before a global<->local exchange carries the exchange in its stores -- every amplitude
+    is written where it lives AFTER local bits V[i] have been traded against rank bits J[i], into the destination rank's
+    second buffer.  Every rank runs the LOCAL programs of its shard (n - g qubits) with that epilogue; the second buffers,
+    read back with the traded bits swapped, must equal what pass-then-exchange gives (the oracle on each shard, permuted)."""
+    g = world.bit_length() - 1
+    nl = n - g
+    ops = {"layers": circuits.random_circuit(nl, 3, seed=3 * n), "qft": circuits.qft_circuit(nl)[:40],
+           "mixed": [o for o in circuits.mixed_circuit(nl, 40, 5 * n) if len(o[1]) <= 2]}[kind]
+    progs = [p for p in em.dump_programs(nl, ops)]
+    assert len(progs) == 1 and progs[0][0] == "prog", "one fused pass per shard"
+    A = [random_state(nl, 700 + r) for r in range(world)]
+    want_local = []
+    for r in range(world):
+        ora = OracleRegister(A[r].copy(), nl)
+        for o in ops:
+            ora.apply(o)
+        want_local.append(ora.state)
+    B = [np.zeros(1 << nl, dtype=np.complex128) for _ in range(world)]
+    bases = (ctypes.c_void_p * world)(*[b.ctypes.data for b in B])
+    lib = build_host(jit_source(progs[0][3]["bytes"], xchg=(V, J)), xchg=True)
+    for r in range(world):
+        assert lib.jit_host_run(A[r].ctypes.data, 1 << (nl - 12), 0, r, bases, world, nl) == 0
+    # expected: amplitude (rank r, local l) -> (rank r', local l') with rank bit J[i] <-> local bit V[i]
+    for r in range(world):
+        l = np.arange(1 << nl, dtype=np.int64)
+        r2 = np.full_like(l, r)
+        l2 = l.copy()
+        for v, j in zip(V, J):
+            lb = (l >> v) & 1
+            rb = (r >> j) & 1
+            r2 = (r2 & ~(1 << j)) | (lb << j)
+            l2 = (l2 & ~(1 << v)) | (rb << v)
+        for rr in range(world):
+            sel = r2 == rr
+            assert_close(B[rr][l2[sel]], want_local[r][l[sel]], f"exchanging pass world={world} rank {r} -> {rr}")
