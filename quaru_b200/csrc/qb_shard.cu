@@ -225,10 +225,13 @@ int shard_init(Reg* r, const void* unique_id) {
             QB_CUDA(cudaStreamSynchronize(r->stream));
         }
     }
-    // Second state buffer (exchanges carried by a pass's stores): only where it fits beside the shard -- 33 qubits on any
-    // number of GPUs, 35 qubits on 8 -- and only if every rank got and mapped one.  QB_SHARD_FUSED_EXCHANGE=0 disables it.
+    // Second state buffer (exchanges carried by a pass's stores): only where it fits beside the shard and only if every rank
+    // got and mapped one.  Measured (33 qubits): 2 GPUs 1799 -> 1893 gates/s, 4 GPUs 2971 -> 2772 -- with more than one peer
+    // the pass's posted stores reach ~480 GB/s per direction against the exchange kernel's ~630 -- so it is the default on 2
+    // GPUs only; QB_SHARD_FUSED_EXCHANGE=1 / 0 forces it on / off.
     const char* fe = getenv("QB_SHARD_FUSED_EXCHANGE");
-    if (s->p2p && !(fe && fe[0] == '0') && r->n_local >= 12) {
+    const bool want_fused = fe ? fe[0] == '1' : r->world == 2;
+    if (s->p2p && want_fused && r->n_local >= 12) {
         const size_t shard_bytes = sizeof(c64) << r->n_local;
         QB_CUDA(cudaMemGetInfo(&free_b, &total_b));
         if (free_b > shard_bytes + (6ull << 30) && cudaMalloc((void**)&s->alt, shard_bytes) != cudaSuccess) s->alt = nullptr;
