@@ -11,6 +11,7 @@
 //   * diagonal gates never constrain the tile either: their non-tile bits select a sub-table.
 // The pass program travels in kernel-parameter (constant-bank) space, so there is no device
 // allocation or copy per pass.
+#include <stdio.h>
 #include <stdlib.h>
 
 #include <functional>
@@ -18,6 +19,8 @@
 
 #include <algorithm>
 #include <atomic>
+#include <mutex>
+#include <unordered_map>
 
 #include "qb_common.h"
 #include "qb_device.cuh"
@@ -321,6 +324,242 @@ static void plan_passes(const std::vector<Gate>& gates, uint32_t n_local, uint32
     plan_passes(gates, n_local, T_opt, max_ops, max_mats, [out](PlannedPass&& p) { out->push_back(std::move(p)); });
 }
 
+// ------------------------------------------------------------------------------------------------
+// Second-tier planner: beam search over the passes' high tile bits.
+//
+// plan_passes above is a one-pass-at-a-time heuristic (it has to be: a pass is launched as soon as the next one is planned).
+// When the SAME gate list comes back (plan cache, run_fused) the search may look at the whole list: `beam` partial plans are
+// kept per depth; each is extended by its best few choices of high bits (greedy set, most frequent dense targets of the
+// next 48..384 gates, hill climbing over one-bit exchanges, every candidate scored by the gates it schedules now plus what
+// the plain pass after it would take) and the `beam` states with the most gates done survive.  On the BASELINE circuit at 33
+// qubits: 21 passes -> 19.  Same commutation rule and capacity limits as plan_passes, so whatever it returns is a valid plan.
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct BeamPlanner {
+    const std::vector<Gate>& gates;
+    uint32_t T, lc_min, h_max;
+    int max_ops, max_mats;
+    std::vector<uint64_t> wm, rm;   // per gate: written bits (dense targets), read bits (controls, diagonal targets)
+    std::vector<char> ok_gate;      // tile_supported
+
+    BeamPlanner(const std::vector<Gate>& g, uint32_t n_local, uint32_t T_opt, int mo, int mm) : gates(g), max_ops(mo), max_mats(mm) {
+        T = std::min(T_opt, n_local);
+        lc_min = std::min(MIN_LC, T);
+        h_max = std::min<uint32_t>(T - lc_min, 7);
+        wm.resize(g.size()); rm.resize(g.size()); ok_gate.resize(g.size());
+        for (size_t i = 0; i < g.size(); ++i) {
+            wm[i] = g[i].kind == GK_DENSE ? g[i].target_mask() : 0;
+            rm[i] = g[i].ctrl_mask | (g[i].kind == GK_DIAG ? g[i].target_mask() : 0);
+            ok_gate[i] = tile_supported(g[i]);
+        }
+    }
+    struct Scan { uint64_t high; uint32_t nh; int count; };
+    Scan scan(const std::vector<char>& done, uint64_t preset, size_t window, std::vector<size_t>* picked) const {
+        uint64_t high = preset, bw = 0, br = 0;
+        uint32_t nh = (uint32_t)__builtin_popcountll(preset);
+        int n_ops = 0, n_mats = 0;
+        size_t seen = 0;
+        const uint64_t low = (1ull << lc_min) - 1ull;
+        for (size_t i = 0; i < gates.size() && seen < window; ++i) {
+            if (done[i]) continue;
+            ++seen;
+            if ((wm[i] & (bw | br)) || (rm[i] & bw)) { bw |= wm[i]; br |= rm[i]; continue; }
+            bool ok = ok_gate[i];
+            const uint64_t need = wm[i] & ~low & ~high;
+            if (ok && nh + (uint32_t)__builtin_popcountll(need) > h_max) ok = false;
+            const int mats = (int)gates[i].matrix.size();
+            if (ok && (n_ops + 1 > max_ops || n_mats + mats > max_mats)) ok = false;
+            if (!ok) { bw |= wm[i]; br |= rm[i]; continue; }
+            high |= need;
+            nh += (uint32_t)__builtin_popcountll(need);
+            n_ops++;
+            n_mats += mats;
+            if (picked) picked->push_back(i);
+        }
+        return Scan{high, nh, n_ops};
+    }
+    // gates this choice schedules now + what the plain pass after it would take
+    int score(const std::vector<char>& done, uint64_t preset, uint64_t* high_out) const {
+        std::vector<size_t> picked;
+        const Scan a = scan(done, preset, (size_t)-1, &picked);
+        if (high_out) *high_out = a.high;
+        std::vector<char> d2 = done;
+        for (size_t i : picked) d2[i] = 1;
+        return a.count + scan(d2, 0, (size_t)-1, nullptr).count;
+    }
+    uint64_t top_bits(const uint32_t* freq, uint32_t k) const {
+        uint64_t m = 0;
+        for (uint32_t c = 0; c < k; ++c) {
+            int arg = -1;
+            for (int b = (int)lc_min; b < 64; ++b)
+                if (!((m >> b) & 1) && freq[b] && (arg < 0 || freq[b] > freq[arg])) arg = b;
+            if (arg < 0) break;
+            m |= 1ull << arg;
+        }
+        return m;
+    }
+    // the best `keep` distinct choices of high bits for this state
+    void options(const std::vector<char>& done, size_t keep, std::vector<std::pair<int, uint64_t>>* out) const {
+        uint32_t freq[64] = {0};
+        std::vector<uint64_t> cands{0ull};
+        size_t seen = 0, mi = 0;
+        const size_t marks[4] = {48, 96, 192, 384};
+        for (size_t i = 0; i < gates.size() && mi < 4; ++i) {
+            if (done[i]) continue;
+            for (uint64_t m = wm[i] >> lc_min << lc_min; m; m &= m - 1) freq[__builtin_ctzll(m)]++;
+            if (++seen == marks[mi]) { cands.push_back(top_bits(freq, h_max)); ++mi; }
+        }
+        if (mi == 0) cands.push_back(top_bits(freq, h_max));
+        std::vector<std::pair<int, uint64_t>> scored;   // (score, preset)
+        auto consider = [&](uint64_t c) -> int {
+            if ((uint32_t)__builtin_popcountll(c) > h_max) return -1;
+            for (const auto& e : scored) if (e.second == c) return e.first;
+            const int sc = score(done, c, nullptr);
+            scored.push_back({sc, c});
+            return sc;
+        };
+        for (uint64_t c : cands) consider(c);
+        // hill climbing from every seed; the options handed back are the LOCAL OPTIMA the climbs end in (distinct ones): the top of
+        // the scored list would be one optimum and its one-bit neighbours, and the beam would lose its diversity
+        const std::vector<std::pair<int, uint64_t>> seeds = scored;
+        std::vector<std::pair<int, uint64_t>> optima;
+        for (const auto& seed : seeds) {
+            uint64_t centre_preset = seed.second, centre_high = 0;
+            int best = score(done, centre_preset, &centre_high);
+            for (int climb = 0; climb < 6; ++climb) {
+                const uint64_t pool = top_bits(freq, 64) & ~centre_high;
+                uint64_t bp = centre_preset;
+                int bs = best;
+                for (uint64_t ib = pool; ib; ib &= ib - 1) {
+                    if ((uint32_t)__builtin_popcountll(centre_high) < h_max) {   // a free slot: add without giving one up
+                        const uint64_t c = centre_high | (ib & -ib);
+                        const int sc = consider(c);
+                        if (sc > bs) { bs = sc; bp = c; }
+                    }
+                    for (uint64_t ob = centre_high; ob; ob &= ob - 1) {
+                        const uint64_t c = (centre_high & ~(ob & -ob)) | (ib & -ib);
+                        const int sc = consider(c);
+                        if (sc > bs) { bs = sc; bp = c; }
+                    }
+                }
+                if (bs == best) break;
+                best = bs;
+                centre_preset = bp;
+                score(done, bp, &centre_high);
+            }
+            bool dup = false;
+            for (const auto& o : optima) dup = dup || o.second == centre_preset;
+            if (!dup) optima.push_back({best, centre_preset});
+        }
+        std::sort(optima.begin(), optima.end(), [](const auto& a, const auto& b) { return a.first > b.first; });
+        for (size_t i = 0; i < optima.size() && out->size() < keep; ++i) out->push_back(optima[i]);
+    }
+    PlannedPass make_pass(uint64_t high, uint32_t nh, std::vector<size_t>&& idx) const {
+        PlannedPass pass;
+        pass.gate_idx = std::move(idx);
+        uint32_t lc = T - nh;
+        for (;;) {
+            uint32_t above = 0;
+            for (uint32_t b = lc; b < 64; ++b) above += (uint32_t)((high >> b) & 1);
+            if (lc + above == T) break;
+            lc = T - above;
+        }
+        pass.lc = lc;
+        for (uint32_t b = 0; b < lc; ++b) pass.tile_pos.push_back(b);
+        for (uint32_t b = lc; b < 64; ++b)
+            if ((high >> b) & 1) pass.tile_pos.push_back(b);
+        return pass;
+    }
+    struct State { std::vector<char> done; size_t n_done; std::vector<PlannedPass> passes; };
+    bool run(size_t beam, size_t per_state, std::vector<PlannedPass>* out) const {
+        std::vector<State> states(1);
+        states[0].done.assign(gates.size(), 0);
+        states[0].n_done = 0;
+        for (size_t depth = 0; depth < 4 * gates.size() + 8; ++depth) {
+            for (const State& st : states)
+                if (st.n_done == gates.size()) { *out = st.passes; return true; }
+            std::vector<State> next;
+            for (const State& st : states) {
+                std::vector<std::pair<int, uint64_t>> opts;
+                options(st.done, per_state, &opts);
+                bool any = false;
+                for (const auto& o : opts) {
+                    std::vector<size_t> picked;
+                    const Scan sc = scan(st.done, o.second, (size_t)-1, &picked);
+                    if (picked.empty()) continue;
+                    any = true;
+                    State ns;
+                    ns.done = st.done;
+                    for (size_t i : picked) ns.done[i] = 1;
+                    ns.n_done = st.n_done + picked.size();
+                    ns.passes = st.passes;
+                    ns.passes.push_back(make_pass(sc.high, sc.nh, std::move(picked)));
+                    next.push_back(std::move(ns));
+                }
+                if (!any) {   // the first remaining gate cannot go through the tile kernel: a pass of its own
+                    State ns = st;
+                    size_t first = 0;
+                    while (ns.done[first]) ++first;
+                    PlannedPass pass;
+                    pass.unfused = true;
+                    pass.gate_idx.push_back(first);
+                    ns.done[first] = 1;
+                    ns.n_done++;
+                    ns.passes.push_back(std::move(pass));
+                    next.push_back(std::move(ns));
+                }
+            }
+            std::sort(next.begin(), next.end(), [](const State& a, const State& b) { return a.n_done > b.n_done; });
+            std::vector<State> kept;
+            for (State& ns : next) {
+                bool dup = false;
+                for (const State& k : kept) if (k.n_done == ns.n_done && k.done == ns.done) { dup = true; break; }
+                if (!dup) kept.push_back(std::move(ns));
+                if (kept.size() >= beam) break;
+            }
+            states.swap(kept);
+            if (states.empty()) return false;
+            if (getenv("QB_PLAN_BEAM_TRACE")) {
+                fprintf(stderr, "beam depth %zu:", depth + 1);
+                for (const State& k : states) fprintf(stderr, " %zu", k.n_done);
+                fprintf(stderr, "\n");
+            }
+        }
+        return false;
+    }
+};
+
+// ---- plan cache: gate-list hash -> passes (process-wide; plans carry gate INDICES, so they fit any list with the same hash) ----
+struct CachedPlan {
+    std::vector<PlannedPass> passes;
+    size_t n_gates = 0;
+    int tier = 0;        // 0: the streaming planner's plan; 1: the beam search has looked at it
+    uint64_t seen = 0;
+};
+std::mutex& g_plan_mu = *new std::mutex;
+std::unordered_map<uint64_t, CachedPlan>& g_plans = *new std::unordered_map<uint64_t, CachedPlan>;
+
+uint64_t plan_key(const std::vector<Gate>& gates, uint32_t n_local, uint32_t tile_bits) {
+    uint64_t h = 0xcbf29ce484222325ull ^ ((uint64_t)n_local << 32) ^ tile_bits;
+    auto mix = [&](const void* p, size_t n) {
+        const unsigned char* b = (const unsigned char*)p;
+        for (size_t i = 0; i < n; ++i) h = (h ^ b[i]) * 0x100000001b3ull;
+    };
+    for (const char* name : {"QB_PLAN_LOOKAHEAD", "QB_PLAN_MIN_LC", "QB_PLAN_BEAM"}) {   // the planner's switches are part of the key
+        const char* v = getenv(name);
+        mix(v ? v : "-", v ? strlen(v) + 1 : 2);
+    }
+    for (const Gate& g : gates) {
+        mix(&g.k, sizeof g.k);
+        mix(&g.kind, sizeof g.kind);
+        mix(&g.ctrl_mask, sizeof g.ctrl_mask);
+        mix(g.targets.data(), g.targets.size() * sizeof(uint32_t));
+        mix(g.matrix.data(), g.matrix.size() * sizeof(c64));
+    }
+    return h;
+}
+}  // namespace
+
 template <class Prog>
 static bool encode_pass(const std::vector<Gate>& gates, const PlannedPass& pass, Prog* prog) {
     const uint32_t T = (uint32_t)pass.tile_pos.size();
@@ -420,7 +659,9 @@ int run_fused(Reg* r, std::vector<Gate>& gates, std::vector<Gate>* hold) {
     const int max_ops = (int)(sizeof(PassLarge::ops) / sizeof(TileOp));
     const int max_mats = (int)(sizeof(PassLarge::mats) / sizeof(c64));
     static thread_local PassLarge large;  // host staging; thread_local: different handles may run on different threads
-    auto launch = [&](const PlannedPass& p) -> int {
+    // A pass neither encoder can take (the second-tier planner is allowed more gates per pass than the shared-memory kernel's
+    // program holds, counting on the register-blocked encoder's merging) is cut in two: same tile, same order, two sweeps.
+    std::function<int(const PlannedPass&)> launch = [&](const PlannedPass& p) -> int {
         if (p.unfused) return k_apply_gate_unfused(r, gates[p.gate_idx[0]]);
         // a pass with a single gate is cheaper through the streaming kernels (they skip untouched halves)
         if (p.gate_idx.size() == 1 && r->force_path != 2 && r->force_path != 4) {
@@ -439,17 +680,80 @@ int run_fused(Reg* r, std::vector<Gate>& gates, std::vector<Gate>* hold) {
             if (!encode_pass(gates, p, &small)) return set_error(QB_ERR_UNSUPPORTED, -1, "internal: pass encoding failed");
             return launch_pass(r, small);
         }
-        if (!encode_pass(gates, p, &large)) return set_error(QB_ERR_UNSUPPORTED, -1, "internal: pass encoding failed");
-        return launch_pass(r, large);
+        if (p.gate_idx.size() <= sizeof(PassLarge::ops) / sizeof(TileOp) && mats <= sizeof(PassLarge::mats) / sizeof(c64)) {
+            if (!encode_pass(gates, p, &large)) return set_error(QB_ERR_UNSUPPORTED, -1, "internal: pass encoding failed");
+            return launch_pass(r, large);
+        }
+        if (p.gate_idx.size() < 2) return set_error(QB_ERR_UNSUPPORTED, -1, "internal: pass encoding failed");
+        PlannedPass a = p, b = p;
+        const size_t half = p.gate_idx.size() / 2;
+        a.gate_idx.assign(p.gate_idx.begin(), p.gate_idx.begin() + (long)half);
+        b.gate_idx.assign(p.gate_idx.begin() + (long)half, p.gate_idx.end());
+        const bool last = r->xchg_last_pass;   // only the second half may carry an exchange
+        r->xchg_last_pass = false;
+        QB_TRY(launch(a));
+        r->xchg_last_pass = last;
+        return launch(b);
     };
+    // Plan cache.  A gate list that has been planned before (same gates, same register shape) is not planned again: its passes
+    // are launched straight from the cache.  The second time a list is seen -- it is evidently being re-applied -- the beam
+    // search above looks for a shorter plan, once, and the cache keeps the better one.  QB_PLAN_BEAM=0 disables the search,
+    // QB_PLAN_BEAM=k sets the beam width (default 4).
+    const char* cache_env = getenv("QB_PLAN_CACHE");
+    const bool cacheable = !hold && gates.size() >= 32 && !(cache_env && cache_env[0] == '0');
+    uint64_t key = 0;
+    if (cacheable) {
+        key = plan_key(gates, r->n_local, r->tile_bits);
+        std::vector<PlannedPass> plan;
+        bool found = false, upgrade = false;
+        {
+            std::lock_guard<std::mutex> lk(g_plan_mu);
+            auto it = g_plans.find(key);
+            if (it != g_plans.end() && it->second.n_gates == gates.size()) {
+                found = true;
+                it->second.seen++;
+                const char* be = getenv("QB_PLAN_BEAM");
+                const char* bm = getenv("QB_PLAN_BEAM_MIN_QUBITS");   // tests lower it to sizes the oracle can follow
+                const uint32_t beam_min = bm ? (uint32_t)atoi(bm) : 28u;
+                upgrade = it->second.tier == 0 && it->second.seen >= 2 && r->n_local >= beam_min && gates.size() >= 64 && !(be && be[0] == '0');
+                if (upgrade) it->second.tier = 1;   // one attempt, whoever gets here first
+                plan = it->second.passes;
+            }
+        }
+        if (found) {
+            if (upgrade) {
+                const char* be = getenv("QB_PLAN_BEAM");
+                const size_t beam = be && atoi(be) > 0 ? (size_t)atoi(be) : 4;
+                // more gates per pass than the shared-memory kernel's program holds: the register-blocked encoder merges the
+                // phase cascades of a QFT pass (hundreds of gates) into a handful of ops; what it cannot take is cut in two
+                const bool big = r->tile_bits == 12 && r->n_local >= 12 && r->force_path == 0;
+                BeamPlanner bp(gates, r->n_local, r->tile_bits, big ? 320 : max_ops, big ? 1000 : max_mats);
+                std::vector<PlannedPass> better;
+                if (bp.run(beam, beam, &better) && better.size() < plan.size()) {
+                    plan = better;
+                    std::lock_guard<std::mutex> lk(g_plan_mu);
+                    g_plans[key].passes = plan;
+                }
+            }
+            for (size_t i = 0; i < plan.size(); ++i) {
+                r->xchg_last_pass = i + 1 == plan.size() && r->xchg_request != nullptr;
+                const int rc = launch(plan[i]);
+                r->xchg_last_pass = false;
+                QB_TRY(rc);
+            }
+            return QB_OK;
+        }
+    }
     // Every pass is launched as soon as the NEXT one has been planned: the GPU starts after one pass's worth of planning instead
     // of the whole queue's (0.26 s per 4096 gates on big registers), and the last pass is known when planning ends -- with `hold`
     // (the queue overflowed, more gates are coming) its gates go back to the queue instead, unless it is the only pass.
     int rc = QB_OK;
     bool have_prev = false, launched_any = false;
     PlannedPass prev;
+    std::vector<PlannedPass> record;
     plan_passes(gates, r->n_local, r->tile_bits, max_ops, max_mats, [&](PlannedPass&& p) {
         if (rc == QB_OK && have_prev) { rc = launch(prev); launched_any = true; }
+        if (cacheable && have_prev) record.push_back(prev);
         prev = std::move(p);
         have_prev = true;
     });
@@ -458,6 +762,16 @@ int run_fused(Reg* r, std::vector<Gate>& gates, std::vector<Gate>* hold) {
         if (hold && launched_any) {
             for (size_t gi : prev.gate_idx) hold->push_back(gates[gi]);
         } else {
+            if (cacheable) {
+                record.push_back(prev);
+                std::lock_guard<std::mutex> lk(g_plan_mu);
+                if (g_plans.size() > 4096) g_plans.clear();   // bound the cache: plans are cheap to recompute
+                CachedPlan& c = g_plans[key];
+                c.passes = record;
+                c.n_gates = gates.size();
+                c.tier = 0;
+                c.seen = 1;
+            }
             r->xchg_last_pass = r->xchg_request != nullptr;   // sharded registers: this pass may carry the exchange that follows it
             const int rc_last = launch(prev);
             r->xchg_last_pass = false;
@@ -467,6 +781,20 @@ int run_fused(Reg* r, std::vector<Gate>& gates, std::vector<Gate>* hold) {
     return QB_OK;
 }
 
+// Introspection entry points plan with the streaming planner, or -- QB_PLAN_DEBUG_BEAM=k -- with the beam search of width k, so
+// that the CPU tests can replay second-tier plans against the oracle too.
+static void plan_for_debug(const std::vector<Gate>& gates, uint32_t n, uint32_t tile_bits, std::vector<PlannedPass>* passes) {
+    const int max_ops = (int)(sizeof(PassLarge::ops) / sizeof(TileOp)), max_mats = (int)(sizeof(PassLarge::mats) / sizeof(c64));
+    const char* be = getenv("QB_PLAN_DEBUG_BEAM");
+    if (be && atoi(be) > 0) {
+        const bool big = tile_bits == 12 && n >= 12;
+        BeamPlanner bp(gates, n, tile_bits, big ? 320 : max_ops, big ? 1000 : max_mats);
+        if (bp.run((size_t)atoi(be), (size_t)atoi(be), passes)) return;
+        passes->clear();
+    }
+    plan_passes(gates, n, tile_bits, max_ops, max_mats, passes);
+}
+
 // The plan for a register of n index bits with 2^12 tiles (qb_shard.cu plans the virtual register of all shards with it).
 void plan_register_passes(const std::vector<Gate>& gates, uint32_t n, std::vector<PlannedPass>* out) {
     plan_passes(gates, n, 12, (int)(sizeof(PassLarge::ops) / sizeof(TileOp)), (int)(sizeof(PassLarge::mats) / sizeof(c64)), out);
@@ -474,8 +802,7 @@ void plan_register_passes(const std::vector<Gate>& gates, uint32_t n, std::vecto
 
 int64_t plan_debug(uint32_t n, std::vector<Gate>& gates, uint32_t tile_bits, int32_t* pass_of_gate, int32_t* order_in_pass) {
     std::vector<PlannedPass> passes;
-    plan_passes(gates, n, tile_bits, (int)(sizeof(PassLarge::ops) / sizeof(TileOp)),
-                (int)(sizeof(PassLarge::mats) / sizeof(c64)), &passes);
+    plan_for_debug(gates, n, tile_bits, &passes);
     for (size_t p = 0; p < passes.size(); ++p)
         for (size_t o = 0; o < passes[p].gate_idx.size(); ++o) {
             const Gate& g = gates[passes[p].gate_idx[o]];
@@ -489,7 +816,7 @@ int64_t plan_debug(uint32_t n, std::vector<Gate>& gates, uint32_t tile_bits, int
 //   u32 n_gates, i64 tags[n_gates], u8 tile_pos[12] (kind 0), then the round program (encode_rounds_debug).
 int64_t rounds_debug(uint32_t n, std::vector<Gate>& gates, unsigned char* out, uint64_t cap) {
     std::vector<PlannedPass> passes;
-    plan_passes(gates, n, 12, (int)(sizeof(PassLarge::ops) / sizeof(TileOp)), (int)(sizeof(PassLarge::mats) / sizeof(c64)), &passes);
+    plan_for_debug(gates, n, 12, &passes);
     unsigned char* w = out;
     auto room = [&](uint64_t bytes) { return (uint64_t)(w - out) + bytes <= cap; };
     for (const PlannedPass& p : passes) {

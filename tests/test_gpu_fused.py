@@ -146,3 +146,31 @@ def test_thorough_planning_forced_on_small_registers(engine, n, kind, monkeypatc
     ops = {"layers": circuits.random_circuit(n, 8, seed=n), "qft": circuits.qft_circuit(n), "mixed": circuits.mixed_circuit(n, 150, n)}[kind]
     reg, ora = _run(engine, n, ops, 4000 + n)
     assert_close(reg.state, ora.state, f"thorough planning n={n} {kind}")
+
+
+@pytest.mark.parametrize("n,kind", [(16, "qft_layers"), (18, "layers"), (17, "mixed")])
+def test_plan_cache_and_second_tier_planner_on_repeated_circuits(engine, n, kind, monkeypatch):
+    """A gate list that comes back is launched from the plan cache; the second time it is seen the beam-search planner looks for
+    a shorter plan (forced on at this size with QB_PLAN_BEAM_MIN_QUBITS).  Four applications on one register against the oracle:
+    the state must match after every one, and the later applications never need more sweeps than the first."""
+    monkeypatch.setenv("QB_PLAN_BEAM_MIN_QUBITS", "12")
+    monkeypatch.setenv("QB_PLAN_LOOKAHEAD", "1")
+    ops = {"qft_layers": circuits.qft_circuit(n) + circuits.random_circuit(n, 4, seed=n), "layers": circuits.random_circuit(n, 8, seed=n),
+           "mixed": [o for o in circuits.mixed_circuit(n, 200, n) if len(o[1]) <= 2]}[kind]
+    s = random_state(n, 4100 + n)
+    reg = engine.Register.new([False] * n)
+    reg.set_option(6, 2)      # specialised kernels, synchronous
+    reg.set_option(7, 12)
+    reg.set_state(s)
+    ora = OracleRegister(s.copy(), n)
+    eops = [engine.Operation(m, t) for m, t in ops]
+    sweeps = []
+    for rep in range(4):
+        p0 = reg.stat(2)
+        reg.apply_batch(eops)
+        reg.sync()
+        sweeps.append(reg.stat(2) - p0)
+        for o in ops:
+            ora.apply(o)
+        assert_close(reg.state, ora.state, f"application {rep + 1}, {kind} n={n}")
+    assert sweeps[2] <= sweeps[0] and sweeps[3] == sweeps[2], sweeps

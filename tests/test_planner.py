@@ -109,3 +109,31 @@ def test_lookahead_over_the_tile_bits_needs_fewer_sweeps(n, depth, monkeypatch):
     small = circuits.mixed_circuit(16, 300, 4)
     _, pass_of, order = _plan(16, small)
     _check_order(small, pass_of, order)
+
+
+@pytest.mark.parametrize("n,kind", [(14, "layers"), (15, "qft"), (13, "mixed"), (28, "layers")])
+def test_beam_planner_keeps_the_ordering_guarantees(n, kind, monkeypatch):
+    """The second-tier planner (beam search over the passes' high tile bits, qb_tile.cu; used when a gate list comes back) obeys
+    the same commutation rule as the streaming planner: every pair of non-commuting gates keeps its program order."""
+    monkeypatch.setenv("QB_PLAN_DEBUG_BEAM", "4")
+    ops = {"layers": circuits.random_circuit(n, 6, seed=n), "qft": circuits.qft_circuit(n), "mixed": circuits.mixed_circuit(n, 200, n)}[kind]
+    _, pass_of, order = _plan(n, ops)
+    _check_order(ops, pass_of, order)
+
+
+def test_beam_planner_needs_fewer_sweeps_on_the_baseline_circuit(monkeypatch):
+    """BASELINE circuit at 33 qubits (QFT + 20 layers, SWAPs absorbed into the qubit names as the API layer does): the streaming
+    planner needs 21 sweeps over the 137 GB state, the beam search 19."""
+    import bench
+    n = 33
+    label, ops = list(range(n)), []
+    for m, t in bench.build_circuit(n):
+        if m.shape == (4, 4) and np.array_equal(m, bench._SWAP):
+            label[t[0]], label[t[1]] = label[t[1]], label[t[0]]
+            continue
+        ops.append((m, [label[q] for q in t]))
+    streaming, pass_of, order = _plan(n, ops)
+    monkeypatch.setenv("QB_PLAN_DEBUG_BEAM", "4")
+    beam, pass_of, order = _plan(n, ops)
+    _check_order(ops, pass_of, order)
+    assert beam < streaming and beam <= 19, (beam, streaming)

@@ -166,3 +166,18 @@ def test_unconditional_phases_on_one_bit_are_multiplied_on_the_host():
     assert em.RC_PH_R not in codes and em.RC_PH_NEG not in codes
     got, want, seen, st = _replay(n, ops, 32)
     assert_close(got, want)
+
+
+@pytest.mark.parametrize("kind,n,seed", [("layers", 14, 21), ("qft", 16, 22), ("mixed", 15, 23), ("qft_layers", 16, 24)])
+def test_second_tier_plans_replay_to_the_oracle(kind, n, seed, monkeypatch):
+    """The beam-search planner (used when a gate list comes back; it is allowed more gates per pass than the streaming planner,
+    counting on the encoder's merging of phase cascades) through the encoder and the program emulator: every gate exactly
+    once, amplitudes as the oracle's."""
+    monkeypatch.setenv("QB_PLAN_DEBUG_BEAM", "4")
+    monkeypatch.setenv("QB_PLAN_LOOKAHEAD", "1")
+    ops = {"layers": circuits.random_circuit(n, 8, seed=seed), "qft": circuits.qft_circuit(n), "mixed": circuits.mixed_circuit(n, 150, seed),
+           "qft_layers": circuits.qft_circuit(n) + circuits.random_circuit(n, 4, seed=seed)}[kind]
+    got, want, seen, st = _replay(n, ops, 500 + seed)
+    identities = [i for i, (m, t) in enumerate(ops) if np.array_equal(np.asarray(m), np.eye(len(m)))]
+    assert sorted(seen + identities) == list(range(len(ops)))
+    assert_close(got, want, f"second-tier plan {kind} n={n}")
