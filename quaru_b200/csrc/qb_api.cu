@@ -60,6 +60,7 @@ static int alloc_common(Reg* r) {
     if (const char* j = getenv("QB_JIT_VARIANT")) {
         const int v = atoi(j);
         r->jit_min_blocks = (v & 15) ? (v & 15) : 2; r->jit_persistent = (v >> 4) & 1; r->jit_prefetch = (v >> 5) & 1;
+        r->jit_pipelined = (v >> 6) & 1;
     }
     return QB_OK;
 }
@@ -339,7 +340,7 @@ int qb_clone(qb_reg* src_, qb_reg** out) try {
     Reg* dst = REG(*out);
     dst->fusion = src->fusion; dst->tile_bits = src->tile_bits; dst->max_queue = src->max_queue; dst->force_path = src->force_path;
     dst->jit = src->jit; dst->jit_min_qubits = src->jit_min_qubits; dst->jit_min_blocks = src->jit_min_blocks;
-    dst->jit_persistent = src->jit_persistent; dst->jit_prefetch = src->jit_prefetch;
+    dst->jit_persistent = src->jit_persistent; dst->jit_prefetch = src->jit_prefetch; dst->jit_pipelined = src->jit_pipelined;
     dst->relabel = src->relabel; dst->label = src->label;   // same amplitudes, same qubit names
     // create_impl queued dst's initialisation (memset + the single 1) on dst->stream, a different non-blocking stream: the copy
     // is ordered after both streams' work by issuing it on dst->stream once src->stream has drained
@@ -650,8 +651,9 @@ int qb_set_option(qb_reg* reg, int32_t option, int64_t value) try {
             return QB_OK;
         case QB_OPT_JIT_MIN_QUBITS: r->jit_min_qubits = (uint32_t)std::max<int64_t>(value, 12); return QB_OK;
         case QB_OPT_JIT_VARIANT:
-            if ((value & 15) < 1 || (value & 15) > 4 || value > 63) return set_error(QB_ERR_INVALID_ARGUMENT, value, "bad jit variant");
+            if ((value & 15) < 1 || (value & 15) > 4 || value > 127) return set_error(QB_ERR_INVALID_ARGUMENT, value, "bad jit variant");
             r->jit_min_blocks = (int)(value & 15); r->jit_persistent = (int)((value >> 4) & 1); r->jit_prefetch = (int)((value >> 5) & 1);
+            r->jit_pipelined = (int)((value >> 6) & 1);
             return QB_OK;
         case QB_OPT_FORCE_PATH:
             if (value < 0 || value > 4) return set_error(QB_ERR_INVALID_ARGUMENT, value, "force path must be in [0, 4]");

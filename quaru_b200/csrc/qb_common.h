@@ -110,7 +110,7 @@ struct Reg {
     // specialised kernel is ready), 2 synchronous (wait for the compiler; failures are errors)
     int jit = 1;
     uint32_t jit_min_qubits = 26;   // local qubits from which a pass is worth a compile (its sweeps take >= ~1 ms)
-    int jit_min_blocks = 2, jit_persistent = 0, jit_prefetch = 0;
+    int jit_min_blocks = 2, jit_persistent = 0, jit_prefetch = 0, jit_pipelined = 0;
     // stats
     int64_t st_launches = 0, st_passes = 0, st_gates = 0, st_bytes = 0, st_swap_bytes = 0, st_swaps = 0;
     int64_t st_tile_launches = 0, st_tile_ns = 0, st_rounds = 0, st_p2p = 0, st_remote_passes = 0;

@@ -130,7 +130,7 @@ void fnv(const void* data, size_t len, uint64_t* a, uint64_t* b) {
 Key key_of(const ProgView& p, const JitOpts& o) {
     uint64_t a = 0xcbf29ce484222325ull, b = 0x84222325cbf29ce4ull;
     const uint32_t hdr[12] = {p.lc, p.h, p.n_rounds, p.n_mats, p.n_ops, (uint32_t)o.min_blocks, (uint32_t)o.persistent, (uint32_t)o.prefetch,
-                              (uint32_t)o.remote, (uint32_t)o.xchg_bits,
+                              (uint32_t)o.remote | ((uint32_t)o.pipelined << 8), (uint32_t)o.xchg_bits,
                               (uint32_t)o.xchg_V[0] | ((uint32_t)o.xchg_V[1] << 8) | ((uint32_t)o.xchg_V[2] << 16),
                               (uint32_t)o.xchg_J[0] | ((uint32_t)o.xchg_J[1] << 8) | ((uint32_t)o.xchg_J[2] << 16)};
     fnv(hdr, sizeof(hdr), &a, &b);
@@ -236,10 +236,13 @@ int load_on_device(Entry* e, int device) {
     CUfunction fn = nullptr;
     rc = d->ModuleGetFunction(&fn, mod, "qb_jit_pass");
     if (rc) return fail_cu(rc, "cuModuleGetFunction(qb_jit_pass)");
-    rc = d->FuncSetAttribute(fn, 8 /* CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES */, (int)(sizeof(c64) << RT));
+    // the pipelined shape: a ring of three tile buffers + six mbarriers, 544 threads
+    const unsigned smem = e->opts.pipelined ? 3u * 65536u + 128u : (unsigned)(sizeof(c64) << RT);
+    const int threads = e->opts.pipelined ? 544 : RTHREADS;
+    rc = d->FuncSetAttribute(fn, 8 /* CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES */, (int)smem);
     if (rc) return fail_cu(rc, "cuFuncSetAttribute(max dynamic shared memory)");
     int per_sm = 0;
-    rc = d->OccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, RTHREADS, sizeof(c64) << RT);
+    rc = d->OccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, smem);
     if (rc) return fail_cu(rc, "cuOccupancyMaxActiveBlocksPerMultiprocessor");
     e->per_sm[device] = per_sm < 1 ? 1 : per_sm;
     e->fn[device] = fn;
@@ -269,6 +272,8 @@ int jit_try_launch(Reg* r, const ProgView& p, const RemoteArgs* remote, bool* la
     o.persistent = r->jit_persistent;
     o.prefetch = r->jit_persistent ? r->jit_prefetch : 0;
     o.remote = remote != nullptr;
+    o.pipelined = (r->jit_pipelined && !remote && !xchg) ? 1 : 0;
+    if (o.pipelined) o.persistent = o.prefetch = 0;
     if (xchg) {
         o.xchg_bits = xchg->gp;
         for (int i = 0; i < xchg->gp; ++i) { o.xchg_V[i] = xchg->V[i]; o.xchg_J[i] = xchg->J[i]; }
@@ -300,7 +305,7 @@ int jit_try_launch(Reg* r, const ProgView& p, const RemoteArgs* remote, bool* la
     if (tiles > 0x7fffffffull) return set_error(QB_ERR_UNSUPPORTED, (int64_t)tiles, "too many tiles for one grid");
     uint32_t tile_or = 0, n_tiles = (uint32_t)tiles;
     unsigned grid = (unsigned)tiles;
-    if (o.persistent) {
+    if (o.persistent || o.pipelined) {
         int sms = 148;
         QB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, r->device));
         grid = (unsigned)std::min<uint64_t>(tiles, (uint64_t)sms * (uint64_t)e->per_sm[r->device]);
@@ -331,7 +336,9 @@ int jit_try_launch(Reg* r, const ProgView& p, const RemoteArgs* remote, bool* la
         args[2] = &n_tiles;
     }
     if (r->profile) QB_TRY(tile_profile_begin(r));
-    rc = driver()->LaunchKernel(e->fn[r->device], grid, 1, 1, RTHREADS, 1, 1, (unsigned)(sizeof(c64) << RT), (void*)r->stream, args, nullptr);
+    const unsigned block = o.pipelined ? 544u : (unsigned)RTHREADS;
+    const unsigned smem = o.pipelined ? 3u * 65536u + 128u : (unsigned)(sizeof(c64) << RT);
+    rc = driver()->LaunchKernel(e->fn[r->device], grid, 1, 1, block, 1, 1, smem, (void*)r->stream, args, nullptr);
     if (rc) return fail_cu(rc, "cuLaunchKernel(qb_jit_pass)");
     if (r->profile) QB_TRY(tile_profile_end(r));
     r->st_jit_launches++;
@@ -381,7 +388,8 @@ int64_t qb_jit_source_debug(const void* program, uint64_t len, int32_t min_block
     if (!deserialise((const unsigned char*)program, len, &prog, &n_ops)) return set_error(QB_ERR_INVALID_ARGUMENT, -1, "not a serialised round program");
     JitOpts o;
     o.min_blocks = min_blocks;
-    o.persistent = persistent;
+    o.persistent = persistent == 1;
+    o.pipelined = persistent == 2;   // `persistent` = 2 selects the pipelined shape (producer warp + bulk-async tile ring)
     o.prefetch = prefetch;
     o.remote = remote;
     if (xchg_bits < 0 || xchg_bits > 3 || (xchg_bits && !xchg_vj)) return set_error(QB_ERR_INVALID_ARGUMENT, xchg_bits, "0..3 exchanged bits");

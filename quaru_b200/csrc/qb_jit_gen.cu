@@ -39,6 +39,23 @@ typedef unsigned long long u64;
 struct QbRemote { double2* base[8]; u32 n_local; u32 pad; };
 #define QB_KERNEL(name, minb) extern "C" __global__ void __launch_bounds__(256, minb) name(double2* __restrict__ st, u32 tile_or, u32 n_tiles)
 #define QB_KERNEL_REMOTE(name, minb) extern "C" __global__ void __launch_bounds__(256, minb) name(const __grid_constant__ QbRemote ra, u32 tile_or, u32 n_tiles)
+#define QB_KERNEL_PIPE(name) extern "C" __global__ void __launch_bounds__(544, 1) name(double2* __restrict__ st, u32 tile_or, u32 n_tiles)
+#define QB_SMEM_RAW(t) extern __shared__ __align__(128) unsigned char t[]
+typedef u64 QB_MBAR_T;
+static __device__ __forceinline__ u32 qb_saddr(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+#define QB_MBAR_INIT(B, C) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(qb_saddr(B)), "r"((u32)(C)) : "memory")
+#define QB_MBAR_INIT_FENCE() asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory")
+#define QB_MBAR_EXPECT_TX(B, N) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(qb_saddr(B)), "r"((u32)(N)) : "memory")
+#define QB_MBAR_ARRIVE(B) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(qb_saddr(B)) : "memory")
+#define QB_MBAR_WAIT(B, P) do { u32 done_; do { asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done_) : "r"(qb_saddr(B)), "r"((u32)(P)) : "memory"); } while (!done_); } while (0)
+#define QB_BULK_G2S(D, S, N, B) asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(qb_saddr(D)), "l"(S), "r"((u32)(N)), "r"(qb_saddr(B)) : "memory")
+#define QB_BULK_S2G(D, S, N) asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(D), "r"(qb_saddr(S)), "r"((u32)(N)) : "memory")
+#define QB_BULK_COMMIT() asm volatile("cp.async.bulk.commit_group;" ::: "memory")
+#define QB_BULK_WAIT_READ() asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory")
+#define QB_FENCE_ASYNC() asm volatile("fence.proxy.async.shared::cta;" ::: "memory")
+#define QB_GROUP_SYNC(G) asm volatile("bar.sync %0, 256;" ::"r"(1u + (G)) : "memory")
+#define QB_SYNCWARP() __syncwarp()
+#define QB_BLOCK_SYNC() __syncthreads()
 #define QB_KERNEL_XCHG(name, minb) extern "C" __global__ void __launch_bounds__(256, minb) name(const double2* __restrict__ st, const __grid_constant__ QbRemote out, u32 rank, u32 tile_or, u32 n_tiles)
 )QB";
 
@@ -382,7 +399,111 @@ struct Gen {
         }
     }
 
+    // tile-local offset of register j in a round whose register bits are R[0..3]
+    static uint32_t reg_local(const RoundDesc& rd, int j) {
+        uint32_t l = 0;
+        for (int i = 0; i < 4; ++i)
+            if ((j >> i) & 1) l |= 1u << rd.R[i];
+        return l;
+    }
+
+    // ---- the pipelined shape -----------------------------------------------------------------------------------------------
+    // One persistent CTA per SM: a producer warp streams tiles from HBM into a ring of three 64 KB shared-memory buffers with
+    // bulk-async copies (cp.async.bulk, one per contiguous segment of the tile, completion counted on an mbarrier); two
+    // consumer groups of 256 threads take alternate tiles: wait for the buffer, registers <- buffer, the rounds (transposes
+    // through the same buffer, named barriers per group), registers -> buffer, bulk-async store back to HBM, buffer released
+    // through a second mbarrier.  HBM latency never sits in a consumer's critical path, and while one group is at a barrier or
+    // in a transpose the other one has the FP64 pipe.
+    std::string run_pipelined() {
+        const uint32_t nseg = 1u << (RT - p.lc), seg_amps = 1u << p.lc;
+        s += "QB_KERNEL_PIPE(qb_jit_pass)\n{\n";
+        s += "    QB_SMEM_RAW(smem_raw);\n";
+        s += "    double2* const bufs = reinterpret_cast<double2*>(smem_raw);\n";
+        s += "    QB_MBAR_T* const full = reinterpret_cast<QB_MBAR_T*>(smem_raw + 3u * 65536u);\n";
+        s += "    QB_MBAR_T* const empty = full + 3;\n";
+        s += "    const u32 tid_all = QB_TID;\n";
+        s += "    if (tid_all == 0) { for (int i_ = 0; i_ < 3; ++i_) { QB_MBAR_INIT(&full[i_], 1); QB_MBAR_INIT(&empty[i_], 1); } QB_MBAR_INIT_FENCE(); }\n";
+        s += "    QB_BLOCK_SYNC();\n";
+        s += "    const u32 n_mine = QB_BID < n_tiles ? (n_tiles - QB_BID + QB_GRID - 1u) / QB_GRID : 0u;\n";
+        // segment index -> offset from the tile base
+        std::string segoff;
+        {
+            char buf[128];
+            for (uint32_t i = 0; i < p.h;) {
+                uint32_t len = 1;
+                while (i + len < p.h && p.hp[i + len] == p.hp[i] + len) ++len;
+                snprintf(buf, sizeof(buf), "%s((u64)((sg_ >> %u) & 0x%xu) << %u)", segoff.empty() ? "" : " | ", i, (1u << len) - 1u, p.hp[i]);
+                segoff += buf;
+                i += len;
+            }
+            if (segoff.empty()) segoff = "0ull";
+        }
+        // ---- producer ----
+        s += "    if (tid_all >= 512u) {\n      const u32 lane = tid_all - 512u;\n";
+        s += "      for (u32 k = 0; k < n_mine; ++k) {\n        const u32 stage = k % 3u, par = (k / 3u) & 1u;\n";
+        s += "        QB_MBAR_WAIT(&empty[stage], par ^ 1u);\n";
+        s += "        const u32 tix = (QB_BID + k * QB_GRID) | tile_or;\n";
+        f("        const u64 base = %s;\n", base_expr("tix").c_str());
+        s += "        if (lane == 0) QB_MBAR_EXPECT_TX(&full[stage], 65536u);\n        QB_SYNCWARP();\n";
+        f("        for (u32 sg_ = lane; sg_ < %uu; sg_ += 32u)\n", nseg);
+        f("          QB_BULK_G2S(bufs + stage * 4096u + sg_ * %uu, st + (base + (%s)), %uu, &full[stage]);\n", seg_amps, segoff.c_str(), seg_amps * 16u);
+        s += "      }\n      return;\n    }\n";
+        // ---- consumers ----
+        s += "    const u32 grp = tid_all >> 8, tid = tid_all & 255u;\n";
+        s += "    for (u32 k = grp; k < n_mine; k += 2u) {\n";
+        s += "    const u32 stage = k % 3u, par = (k / 3u) & 1u;\n";
+        s += "    double2* const tile = bufs + stage * 4096u;\n";
+        s += "    const u32 tix = (QB_BID + k * QB_GRID) | tile_or;\n";
+        f("    const u64 base = %s;\n", base_expr("tix").c_str());
+        s += "    double";
+        for (int j = 0; j < 16; ++j) f(" x%d, y%d%s", j, j, j == 15 ? ";\n" : ",");
+        s += "    double px = 1.0, py = 0.0;\n    u32 tl;\n";
+        for (int j = 0; j < 16; ++j) nm[j] = j;
+        emit_tl(p.rounds[0]);
+        s += "    QB_MBAR_WAIT(&full[stage], par);\n";
+        for (int j = 0; j < 16; ++j)
+            f("    { const double2 t_ = tile[tl | 0x%xu]; x%d = t_.x; y%d = t_.y; }\n", reg_local(p.rounds[0], j), j, j);
+        s += "    QB_GROUP_SYNC(grp);\n";   // everybody has its amplitudes: the buffer is the transposes' scratch from here on
+        for (uint32_t r = 0; r < p.n_rounds; ++r) {
+            const RoundDesc& rd = p.rounds[r];
+            f("    // ---- round %u: register bits %u %u %u %u ----\n", r, rd.R[0], rd.R[1], rd.R[2], rd.R[3]);
+            if (r > 0) {
+                const RoundDesc& prev = p.rounds[r - 1];
+                s += "    {\n      const u32 s_t = qb_swz(tl);\n";
+                for (int j = 0; j < 16; ++j) f("      tile[s_t ^ 0x%xu] = make_double2(%s, %s);\n", prev.sro[j], X(j).c_str(), Y(j).c_str());
+                s += "    }\n    QB_GROUP_SYNC(grp);\n";
+                emit_tl(rd);
+                s += "    {\n      const u32 s_n = qb_swz(tl);\n";
+                for (int j = 0; j < 16; ++j) {
+                    nm[j] = j;
+                    f("      { const double2 t_ = tile[s_n ^ 0x%xu]; x%d = t_.x; y%d = t_.y; }\n", rd.sro[j], j, j);
+                }
+                s += "    }\n    QB_GROUP_SYNC(grp);\n";   // the buffer is written again (next transpose, or the store staging below)
+            }
+            s += "    px = 1.0; py = 0.0;\n";
+            tph_one = true;
+            for (uint32_t oi = rd.op_begin; oi < rd.op_end; ++oi) emit_op(p.ops[oi]);
+            if (rd.has_tph && !tph_one) {
+                s += "    {\n";
+                for (int j = 0; j < 16; ++j) cmul_reg_expr(j, "px", "py");
+                close();
+            }
+        }
+        // registers -> buffer (tile-local order = the order of the tile's segments in HBM), then bulk-async stores
+        const RoundDesc& last = p.rounds[p.n_rounds - 1];
+        for (int j = 0; j < 16; ++j) f("    tile[tl | 0x%xu] = make_double2(%s, %s);\n", reg_local(last, j), X(j).c_str(), Y(j).c_str());
+        s += "    QB_FENCE_ASYNC();\n    QB_GROUP_SYNC(grp);\n";
+        s += "    if (tid < 32u) {\n";
+        f("      for (u32 sg_ = tid; sg_ < %uu; sg_ += 32u)\n", nseg);
+        f("        QB_BULK_S2G(st + (base + (%s)), tile + sg_ * %uu, %uu);\n", segoff.c_str(), seg_amps, seg_amps * 16u);
+        s += "      QB_BULK_COMMIT();\n      QB_BULK_WAIT_READ();\n      QB_SYNCWARP();\n";
+        s += "      if (tid == 0) QB_MBAR_ARRIVE(&empty[stage]);\n    }\n";
+        s += "    }\n}\n";
+        return finish();
+    }
+
     std::string run() {
+        if (o.pipelined && !o.remote && o.xchg_bits == 0) return run_pipelined();
         // ---- kernel body ----
         f("%s(qb_jit_pass, %d)\n{\n", o.xchg_bits > 0 ? "QB_KERNEL_XCHG" : o.remote ? "QB_KERNEL_REMOTE" : "QB_KERNEL", o.min_blocks);
         s += "    QB_SMEM(tile);\n    const u32 tid = QB_TID;\n";
@@ -467,7 +588,11 @@ struct Gen {
         s += "    }\n";
         if (o.persistent) s += "    }\n";
         s += "}\n";
-        // ---- prelude + tables in front ----
+        return finish();
+    }
+
+    // ---- prelude + tables in front of the kernel text ----
+    std::string finish() {
         std::string head = "// generated by quaru_b200 (qb_jit_gen.cu): one fused tile pass, specialised\n#ifdef QB_HOST_EMU\n#include \"qb_jit_emu.h\"\n#else\n";
         head += kDevicePrelude;
         head += "#endif\nstatic __device__ __forceinline__ u32 qb_swz(u32 l) { return l ^ (((l >> 3) ^ (l >> 6) ^ (l >> 9)) & 7u); }\n";

@@ -10,8 +10,10 @@
 thread_local qb_emu_dim3 qb_emu_thread, qb_emu_block;
 qb_emu_dim3 qb_emu_grid;
 pthread_barrier_t qb_emu_barrier;
-alignas(32) static double2 g_shared[4096];
-double2* qb_emu_shared = g_shared;
+alignas(128) static unsigned char g_shared_raw[3 * 65536 + 1024];
+double2* qb_emu_shared = reinterpret_cast<double2*>(g_shared_raw);
+unsigned char* qb_emu_shared_raw = g_shared_raw;
+pthread_barrier_t qb_emu_group_barrier[2], qb_emu_block_barrier, qb_emu_warp_barrier[17];
 
 #include QB_JIT_SRC
 
@@ -20,6 +22,31 @@ double2* qb_emu_shared = g_shared;
 // `tile_or` carries the rank.
 extern "C" int jit_host_run(double* state, unsigned n_tiles, unsigned grid, unsigned tile_or, void* const* bases, unsigned world,
                             unsigned n_local) {
+#ifdef QB_JIT_PIPE
+    // pipelined shape: `grid` persistent CTAs of 544 threads (2 consumer groups of 256 + the producer warp), one after the other
+    (void)bases; (void)world; (void)n_local;
+    const unsigned ctas_p = grid ? grid : 1;
+    qb_emu_grid = {ctas_p, 1, 1};
+    for (unsigned b = 0; b < ctas_p; ++b) {
+        pthread_barrier_init(&qb_emu_block_barrier, nullptr, 544);
+        pthread_barrier_init(&qb_emu_group_barrier[0], nullptr, 256);
+        pthread_barrier_init(&qb_emu_group_barrier[1], nullptr, 256);
+        for (int w = 0; w < 17; ++w) pthread_barrier_init(&qb_emu_warp_barrier[w], nullptr, 32);
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < 544; ++t)
+            th.emplace_back([=]() {
+                qb_emu_thread = {t, 0, 0};
+                qb_emu_block = {b, 0, 0};
+                qb_jit_pass(reinterpret_cast<double2*>(state), tile_or, n_tiles);
+            });
+        for (std::thread& x : th) x.join();
+        pthread_barrier_destroy(&qb_emu_block_barrier);
+        pthread_barrier_destroy(&qb_emu_group_barrier[0]);
+        pthread_barrier_destroy(&qb_emu_group_barrier[1]);
+        for (int w = 0; w < 17; ++w) pthread_barrier_destroy(&qb_emu_warp_barrier[w]);
+    }
+    return 0;
+#else
     const unsigned ctas = grid ? grid : n_tiles;
     qb_emu_grid = {ctas, 1, 1};
     pthread_barrier_init(&qb_emu_barrier, nullptr, 256);
@@ -51,4 +78,5 @@ extern "C" int jit_host_run(double* state, unsigned n_tiles, unsigned grid, unsi
     for (std::thread& th : threads) th.join();
     pthread_barrier_destroy(&qb_emu_barrier);
     return 0;
+#endif
 }

@@ -7,6 +7,8 @@ Every configuration runs in its own process (a faulting variant cannot take the 
 timeout:
   * `interpreter`: the interpreter kernel k2r_tile_pass (QB_JIT=0) -- the round-1 kernel;
   * `jit`: the specialised kernels (K2j, qb_jit_gen.cu), default shape: one CTA per tile, 128 registers, 2 CTAs / SM;
+  * `jit_pipelined`: one persistent CTA per SM, a producer warp streaming tiles into a ring of three shared-memory buffers with
+    bulk-async copies (cp.async.bulk + mbarrier), two consumer groups of 256 threads, bulk-async stores;
   * `jit_3cta` (80 registers, 3 CTAs / SM), `jit_persistent`, `jit_persistent_prefetch`: the other kernel shapes;
   * `jit_lc4`: the planner allowed 256-byte contiguous segments (QB_PLAN_MIN_LC=4: eight arbitrary high tile bits instead of 7);
   * `jit_no_lookahead`, `jit_no_swap_relabel`: planner switches.
@@ -27,6 +29,7 @@ sys.path.insert(0, ROOT)
 CONFIGS = [  # (label, jit mode, jit variant, extra environment); most informative first, the time budget may cut the tail
     ("jit", 2, 2, {}),
     ("interpreter", 0, 2, {}),
+    ("jit_pipelined", 2, 2 | 64, {}),
     ("jit_lc4", 2, 2, {"QB_PLAN_MIN_LC": "4"}),
     ("jit_3cta", 2, 3, {}),
     ("jit_persistent", 2, 2 | 16, {}),

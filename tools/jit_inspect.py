@@ -45,7 +45,8 @@ def main():
         pb = p[3]["bytes"]
         cap = 16 << 20
         buf = ctypes.create_string_buffer(cap)
-        got = L.qb_jit_source_debug(pb, len(pb), variant & 15, (variant >> 4) & 1, (variant >> 5) & 1, 0, 0, None, buf, cap)
+        persistent = 2 if (variant >> 6) & 1 else (variant >> 4) & 1      # bit 6: the pipelined shape
+        got = L.qb_jit_source_debug(pb, len(pb), variant & 15, persistent, (variant >> 5) & 1, 0, 0, None, buf, cap)
         assert got > 0, _ffi.last_error()
         src = buf.raw[:got]
         ms = ctypes.c_double(0)
