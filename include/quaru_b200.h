@@ -166,7 +166,8 @@ int qb_timer_stop(qb_reg* reg, float* ms);
 #define QB_OPT_FUSION 1        /* 1 (default): buffer gates and fuse into tile passes; 0: one pass per gate */
 #define QB_OPT_TILE_BITS 2     /* log2 amplitudes per shared-memory tile (default 12) */
 #define QB_OPT_MAX_QUEUE 3     /* auto-flush after this many buffered gates (default 4096) */
-#define QB_OPT_FORCE_PATH 4    /* tests only: 0 auto, 1 generic kernel, 2 shared-memory tile kernel, 4 tile kernels even for single gates */
+#define QB_OPT_FORCE_PATH 4    /* tests only: 0 auto, 1 generic kernel (in place), 2 shared-memory tile kernel, 4 tile kernels even for single gates,
+                                  5 generic kernel out of place (the k > 13 path: needs a second state buffer) */
 #define QB_OPT_PROFILE 5       /* 1: bracket every tile-pass launch with CUDA events (QB_STAT_TILE_NS) */
 #define QB_OPT_JIT 6           /* specialised tile kernels (one NVRTC-compiled kernel per distinct pass program, cached by program hash):
                                   0 off; 1 (default, env QB_JIT) asynchronous -- a pass runs through the interpreter kernel until its

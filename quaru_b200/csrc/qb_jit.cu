@@ -236,9 +236,9 @@ int load_on_device(Entry* e, int device) {
     CUfunction fn = nullptr;
     rc = d->ModuleGetFunction(&fn, mod, "qb_jit_pass");
     if (rc) return fail_cu(rc, "cuModuleGetFunction(qb_jit_pass)");
-    // the pipelined shape: a ring of three tile buffers + six mbarriers, 544 threads
+    // the pipelined shapes: a ring of three tile buffers + mbarriers; 544 threads with the producer warp, 512 without
     const unsigned smem = e->opts.pipelined ? 3u * 65536u + 128u : (unsigned)(sizeof(c64) << RT);
-    const int threads = e->opts.pipelined ? 544 : RTHREADS;
+    const int threads = e->opts.pipelined == 1 ? 544 : e->opts.pipelined == 2 ? 512 : RTHREADS;
     rc = d->FuncSetAttribute(fn, 8 /* CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES */, (int)smem);
     if (rc) return fail_cu(rc, "cuFuncSetAttribute(max dynamic shared memory)");
     int per_sm = 0;
@@ -272,7 +272,7 @@ int jit_try_launch(Reg* r, const ProgView& p, const RemoteArgs* remote, bool* la
     o.persistent = r->jit_persistent;
     o.prefetch = r->jit_persistent ? r->jit_prefetch : 0;
     o.remote = remote != nullptr;
-    o.pipelined = (r->jit_pipelined && !remote && !xchg) ? 1 : 0;
+    o.pipelined = (r->jit_pipelined && !remote && !xchg) ? r->jit_pipelined : 0;
     if (o.pipelined) o.persistent = o.prefetch = 0;
     if (xchg) {
         o.xchg_bits = xchg->gp;
@@ -336,7 +336,7 @@ int jit_try_launch(Reg* r, const ProgView& p, const RemoteArgs* remote, bool* la
         args[2] = &n_tiles;
     }
     if (r->profile) QB_TRY(tile_profile_begin(r));
-    const unsigned block = o.pipelined ? 544u : (unsigned)RTHREADS;
+    const unsigned block = o.pipelined == 1 ? 544u : o.pipelined == 2 ? 512u : (unsigned)RTHREADS;
     const unsigned smem = o.pipelined ? 3u * 65536u + 128u : (unsigned)(sizeof(c64) << RT);
     rc = driver()->LaunchKernel(e->fn[r->device], grid, 1, 1, block, 1, 1, smem, (void*)r->stream, args, nullptr);
     if (rc) return fail_cu(rc, "cuLaunchKernel(qb_jit_pass)");
@@ -389,7 +389,7 @@ int64_t qb_jit_source_debug(const void* program, uint64_t len, int32_t min_block
     JitOpts o;
     o.min_blocks = min_blocks;
     o.persistent = persistent == 1;
-    o.pipelined = persistent == 2;   // `persistent` = 2 selects the pipelined shape (producer warp + bulk-async tile ring)
+    o.pipelined = persistent >= 2 ? persistent - 1 : 0;   // `persistent` = 2 / 3 select the pipelined shapes (producer warp / self-fed ring)
     o.prefetch = prefetch;
     o.remote = remote;
     if (xchg_bits < 0 || xchg_bits > 3 || (xchg_bits && !xchg_vj)) return set_error(QB_ERR_INVALID_ARGUMENT, xchg_bits, "0..3 exchanged bits");

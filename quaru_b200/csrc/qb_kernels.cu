@@ -210,6 +210,51 @@ __global__ void __launch_bounds__(256) k3_apply_general(const c64* __restrict__ 
 }
 
 // ================================================================================================
+// K3i: the same gate IN PLACE, for k <= 13 -- no second state buffer, so a dense 3+-qubit gate (hadamard_transform on three
+// targets, Shor's to_quantum_gate, an unfused dense 2-qubit gate) works on a register that fills the GPU.
+// A chunk = 2^gl amplitude groups (a group = the 2^k amplitudes that differ only in the target bits; only groups whose control
+// bits are all 1 are enumerated).  A CTA stages a chunk in shared memory (group index fastest across threads, so loads follow
+// the non-target low bits), then LANES lanes cooperate on each output exactly as K3 does (same per-lane strided partial sums,
+// same xor tree: bit-identical results) and write it straight back: every input of the chunk is already in shared memory.
+// ================================================================================================
+template <int LANES>
+__global__ void __launch_bounds__(256) k3_apply_general_inplace(c64* __restrict__ st, uint64_t n_chunks, uint32_t gl,
+                                                                const c64* __restrict__ M, const uint64_t* __restrict__ offs,
+                                                                uint32_t k, uint64_t ctrl_mask, InsertList ins) {
+    extern __shared__ __align__(16) c64 k3_sh[];   // [group][c]
+    constexpr uint32_t SLICES = 256 / LANES;
+    const uint32_t dim = 1u << k, gpc = 1u << gl, ch = dim << gl;
+    const uint32_t sub = threadIdx.x % LANES, slice = threadIdx.x / LANES;
+    const uint32_t iters = (ch + SLICES - 1) / SLICES;   // same trip count for every thread (shuffles below)
+    for (uint64_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+        for (uint32_t e = threadIdx.x; e < ch; e += 256) {
+            const uint32_t g = e & (gpc - 1u), c = e >> gl;
+            const uint64_t base = expand_index((chunk << gl) | g, ins) | ctrl_mask;
+            k3_sh[(g << k) | c] = st[base | offs[c]];
+        }
+        __syncthreads();
+        for (uint32_t it = 0; it < iters; ++it) {
+            const uint32_t e = it * SLICES + slice;
+            const bool valid = e < ch;
+            const uint32_t g = e & (gpc - 1u), row = e >> gl;
+            c64 acc = make_double2(0.0, 0.0);
+            if (valid) {
+                const c64* Mr = M + (uint64_t)row * dim;
+                const c64* in = k3_sh + ((uint64_t)g << k);
+                for (uint32_t c = sub; c < dim; c += LANES) acc = cfma(Mr[c], in[c], acc);
+            }
+#pragma unroll
+            for (int sft = LANES / 2; sft >= 1; sft >>= 1) {
+                acc.x += __shfl_xor_sync(0xffffffffu, acc.x, sft);
+                acc.y += __shfl_xor_sync(0xffffffffu, acc.y, sft);
+            }
+            if (valid && sub == 0) st[(expand_index((chunk << gl) | g, ins) | ctrl_mask) | offs[row]] = acc;
+        }
+        __syncthreads();   // the next chunk's staging overwrites the shared-memory copy
+    }
+}
+
+// ================================================================================================
 // K6: measurement probabilities -- first loop of try_measure (register.rs:303-315).
 // The sum is an exact balanced ADJACENT-PAIR binary tree over the amplitude index (leaves are
 // |a|^2 = rn(rn(re*re) + rn(im*im)) put into bucket bit_t(i); missing leaves are +0.0), so the
@@ -433,10 +478,13 @@ int k_init_product(Reg* r, const double* q) {
     return QB_OK;
 }
 
+constexpr uint32_t K3I_MAX_K = 13;   // 2^13 amplitudes = 128 KB of shared memory per group
+
 static int launch_general(Reg* r, const Gate& g) {
-    // out-of-place: needs a second state-sized buffer (only reachable for gates the tile path cannot take)
     const uint64_t n_amps = 1ull << r->n_local;
-    if (!r->scratch) {
+    const bool in_place = g.k <= K3I_MAX_K && r->force_path != 5;
+    if (!in_place && !r->scratch) {
+        // out-of-place (k > 13, or QB_OPT_FORCE_PATH = 5): needs a second state-sized buffer
         cudaError_t e = cudaMalloc((void**)&r->scratch, n_amps * sizeof(c64));
         if (e != cudaSuccess) {
             cudaGetLastError();
@@ -459,10 +507,37 @@ static int launch_general(Reg* r, const Gate& g) {
     uint64_t* doffs = (uint64_t*)((char*)r->dmat + mat_bytes);
     QB_CUDA(cudaMemcpyAsync(doffs, offs.data(), off_bytes, cudaMemcpyHostToDevice, r->stream));
     QB_CUDA(cudaStreamSynchronize(r->stream));  // `offs` is a pageable local: make sure it has been consumed
+    const uint64_t tmask = g.target_mask();
+    if (in_place) {
+        const uint32_t nc = (uint32_t)__builtin_popcountll(g.ctrl_mask);
+        const uint32_t free_bits = r->n_local - g.k - nc;   // bits of the group index
+        const uint32_t gl = std::min<uint32_t>(free_bits, g.k < 11 ? 11 - g.k : 0);   // chunks of 2048 amplitudes (32 KB)
+        const uint64_t n_chunks = 1ull << (free_bits - gl);
+        const size_t smem = sizeof(c64) << (g.k + gl);
+        const InsertList ins = make_inserts(tmask | g.ctrl_mask);
+        const unsigned grid = (unsigned)std::min<uint64_t>(n_chunks, (uint64_t)num_sms() * 4);
+#define QB_GENI(L)                                                                                                              \
+    do {                                                                                                                        \
+        if (smem > 48 * 1024)                                                                                                   \
+            QB_CUDA(cudaFuncSetAttribute(k3_apply_general_inplace<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        k3_apply_general_inplace<L><<<grid, 256, smem, r->stream>>>(r->state, n_chunks, gl, r->dmat, doffs, g.k, g.ctrl_mask, ins); \
+    } while (0)
+        if (g.k >= 5) QB_GENI(32);
+        else if (g.k == 4) QB_GENI(16);
+        else if (g.k == 3) QB_GENI(8);
+        else if (g.k == 2) QB_GENI(4);
+        else if (g.k == 1) QB_GENI(2);
+        else QB_GENI(1);
+#undef QB_GENI
+        QB_CUDA(cudaGetLastError());
+        r->st_launches++;
+        r->st_passes++;
+        r->st_bytes += (int64_t)((n_amps >> nc) * 32);
+        return QB_OK;
+    }
     TargetList tl;
     tl.k = g.k;
     for (uint32_t j = 0; j < g.k; ++j) tl.t[j] = g.targets[j];
-    const uint64_t tmask = g.target_mask();
 #define QB_GEN(L)                                                                                              \
     k3_apply_general<L><<<grid_for(n_amps * L, 256, 1, 8), 256, 0, r->stream>>>(r->state, r->scratch, n_amps, \
                                                                                 r->dmat, doffs, g.k, tmask,  \
@@ -542,7 +617,7 @@ static int launch_1q(Reg* r, const Gate& g) {
 }
 
 int k_apply_gate_unfused(Reg* r, const Gate& g) {
-    if (r->force_path == 1) {
+    if (r->force_path == 1 || r->force_path == 5) {
         if (g.kind == GK_DIAG) {  // the generic kernel takes dense matrices: expand the diagonal
             Gate d = g;
             d.kind = GK_DENSE;

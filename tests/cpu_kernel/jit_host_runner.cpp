@@ -23,17 +23,18 @@ pthread_barrier_t qb_emu_group_barrier[2], qb_emu_block_barrier, qb_emu_warp_bar
 extern "C" int jit_host_run(double* state, unsigned n_tiles, unsigned grid, unsigned tile_or, void* const* bases, unsigned world,
                             unsigned n_local) {
 #ifdef QB_JIT_PIPE
-    // pipelined shape: `grid` persistent CTAs of 544 threads (2 consumer groups of 256 + the producer warp), one after the other
+    // pipelined shapes: `grid` persistent CTAs of QB_JIT_PIPE threads (2 consumer groups of 256, + the producer warp when 544),
+    // one after the other
     (void)bases; (void)world; (void)n_local;
     const unsigned ctas_p = grid ? grid : 1;
     qb_emu_grid = {ctas_p, 1, 1};
     for (unsigned b = 0; b < ctas_p; ++b) {
-        pthread_barrier_init(&qb_emu_block_barrier, nullptr, 544);
+        pthread_barrier_init(&qb_emu_block_barrier, nullptr, QB_JIT_PIPE);
         pthread_barrier_init(&qb_emu_group_barrier[0], nullptr, 256);
         pthread_barrier_init(&qb_emu_group_barrier[1], nullptr, 256);
         for (int w = 0; w < 17; ++w) pthread_barrier_init(&qb_emu_warp_barrier[w], nullptr, 32);
         std::vector<std::thread> th;
-        for (unsigned t = 0; t < 544; ++t)
+        for (unsigned t = 0; t < QB_JIT_PIPE; ++t)
             th.emplace_back([=]() {
                 qb_emu_thread = {t, 0, 0};
                 qb_emu_block = {b, 0, 0};

@@ -79,6 +79,7 @@ static inline void qb_emu_mbar_wait(QB_MBAR_T* b, unsigned parity) {   // return
 extern pthread_barrier_t qb_emu_group_barrier[2], qb_emu_block_barrier, qb_emu_warp_barrier[17];
 extern unsigned char* qb_emu_shared_raw;
 #define QB_KERNEL_PIPE(name) extern "C" void name(double2* st, u32 tile_or, u32 n_tiles)
+#define QB_KERNEL_RING(name) extern "C" void name(double2* st, u32 tile_or, u32 n_tiles)
 #define QB_SMEM_RAW(t) unsigned char* t = qb_emu_shared_raw
 #define QB_MBAR_INIT(B, C) qb_emu_mbar_init((B), (C))
 #define QB_MBAR_INIT_FENCE() ((void)0)

@@ -101,7 +101,7 @@ def test_error_payloads_and_options(engine):
     with pytest.raises(OperationError):
         reg.try_measure(7, u=0.5)
     with pytest.raises(Exception):
-        reg.set_option(_ffi.QB_OPT_FORCE_PATH, 5)
+        reg.set_option(_ffi.QB_OPT_FORCE_PATH, 6)
     reg.set_option(_ffi.QB_OPT_FORCE_PATH, 0)
     with pytest.raises(Exception):
         reg.set_option(_ffi.QB_OPT_JIT, 3)

@@ -11,6 +11,7 @@ from tests.util import assert_close, random_matrix, random_state, tree_probabili
 pytestmark = pytest.mark.gpu
 
 FORCE_GENERIC, FORCE_TILE, FORCE_STREAM = 1, 2, 3
+FORCE_GENERIC_OUT_OF_PLACE = 5
 OPT_FUSION, OPT_TILE_BITS, OPT_FORCE = 1, 2, 4
 
 
@@ -100,10 +101,12 @@ def test_dense_k_scrambled_targets(engine, n, k):
 
 
 @pytest.mark.parametrize("n", [1, 3, 6, 11])
-def test_generic_kernel_matches_specialised(engine, n):
-    """The out-of-place generic kernel (K3) forced for every gate shape gives the oracle's result too."""
+@pytest.mark.parametrize("force", [FORCE_GENERIC, FORCE_GENERIC_OUT_OF_PLACE])
+def test_generic_kernel_matches_specialised(engine, n, force):
+    """The generic kernel forced for every gate shape -- in place (K3i, the default for dense gates the tile path does not
+    take) and out of place (K3, the k > 13 path) -- gives the oracle's result too."""
     rng = np.random.default_rng(n)
-    reg, ora = _pair(engine, n, 600 + n, force=FORCE_GENERIC)
+    reg, ora = _pair(engine, n, 600 + n, force=force)
     for t in range(n):
         _both(engine, reg, ora, random_matrix(1, t), [t])
         _both(engine, reg, ora, *og.rz(0.3 + t, t))
@@ -112,6 +115,23 @@ def test_generic_kernel_matches_specialised(engine, n):
             _both(engine, reg, ora, *og.cnot(c, t))
             _both(engine, reg, ora, *og.cz(c, t))
     assert_close(reg.state, ora.state, f"n={n}")
+
+
+@pytest.mark.parametrize("n,k", [(14, 9), (14, 12), (13, 13), (18, 3), (20, 5)])
+def test_wide_dense_gates_in_place(engine, n, k):
+    """Dense k-qubit gates beyond the tile path go through the in-place kernel K3i (no second state buffer): scattered and
+    low/high targets, with and without controls, chunks of several groups (k < 11) and of one group (k >= 11)."""
+    rng = np.random.default_rng(100 * n + k)
+    reg, ora = _pair(engine, n, 900 + n)
+    for i in range(1 if k >= 12 else 3):
+        qs = [int(x) for x in rng.permutation(n)[:k]]
+        m = random_matrix(k, 17 * n + k + i)
+        _both(engine, reg, ora, m, qs)
+        if k <= 9 and i == 0:
+            rest = [q for q in range(n) if q not in qs]
+            op = og.to_controlled(og.to_controlled((m, qs), rest[0]), rest[-1])
+            _both(engine, reg, ora, *op)
+    assert_close(reg.state, ora.state, f"in-place dense gate n={n} k={k}")
 
 
 def test_shor_and_swap_gates(engine):
