@@ -57,6 +57,12 @@ static __device__ __forceinline__ u32 qb_saddr(const void* p) { return (u32)__cv
 #define QB_GROUP_SYNC(G) asm volatile("bar.sync %0, 256;" ::"r"(1u + (G)) : "memory")
 #define QB_SYNCWARP() __syncwarp()
 #define QB_BLOCK_SYNC() __syncthreads()
+#define QB_CP_ASYNC16(D, S) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(qb_saddr(D)), "l"(S) : "memory")
+#define QB_CP_ASYNC_COMMIT() asm volatile("cp.async.commit_group;" ::: "memory")
+#define QB_CP_ASYNC_WAIT_ALL() asm volatile("cp.async.wait_group 0;" ::: "memory")
+#define QB_SPIN() __nanosleep(20)
+#define QB_FLAG_LD(P) (*(volatile u32*)(P))
+#define QB_FLAG_ST(P, V) do { __threadfence_block(); *(volatile u32*)(P) = (V); } while (0)
 #define QB_KERNEL_XCHG(name, minb) extern "C" __global__ void __launch_bounds__(256, minb) name(const double2* __restrict__ st, const __grid_constant__ QbRemote out, u32 rank, u32 tile_or, u32 n_tiles)
 )QB";
 
@@ -550,7 +556,94 @@ struct Gen {
         return finish();
     }
 
+    // ---- the prefetching ring (pipelined = 3) ------------------------------------------------------------------------------
+    // One persistent CTA of 512 threads per SM, two groups of 256 threads on alternate tiles, three 64 KB buffers: tile k lives
+    // in buffer k % 3.  Every thread fetches ITS OWN 16 amplitudes of its group's next tile (k + 2) with 16-byte cp.async
+    // (LDGSTS: HBM -> shared memory without passing through registers) while it computes tile k, and reads them back with
+    // cp.async.wait_group + 16 LDS at the top of tile k + 2: a per-thread prefetch queue in shared memory, so no cross-thread
+    // completion tracking is needed -- no mbarrier, no bulk copies.  Buffer (k + 2) % 3 is the buffer of the OTHER group's tile
+    // k - 1; that group publishes "my shared-memory use of tile t is over" (after the last transpose read) in done[group], and
+    // the prefetch is issued at the first round boundary at which done[other] >= k holds (at the latest before the stores,
+    // spinning).  Results go from registers straight to HBM as in the default shape.
+    void emit_prefetch_lambda() {
+        s += "    auto prefetch = [&](u32 kk) {\n";
+        s += "      const u32 ntix = (QB_BID + kk * QB_GRID) | tile_or;\n";
+        f("      const u64 ngt = (%s) + goff0;\n", base_expr("ntix").c_str());
+        s += "      double2* const nt = bufs + (kk % 3u) * 4096u + tl0;\n";
+        for (int j = 0; j < 16; ++j)
+            f("      QB_CP_ASYNC16(nt + 0x%xu, st + (ngt + 0x%llxull));\n", reg_local(p.rounds[0], j), (unsigned long long)p.gro_first[j]);
+        s += "      QB_CP_ASYNC_COMMIT();\n    };\n";
+    }
+    std::string run_ring() {
+        s += "QB_KERNEL_RING(qb_jit_pass)\n{\n";
+        s += "    QB_SMEM_RAW(smem_raw);\n";
+        s += "    double2* const bufs = reinterpret_cast<double2*>(smem_raw);\n";
+        s += "    u32* const done = reinterpret_cast<u32*>(smem_raw + 3u * 65536u);\n";
+        s += "    const u32 tid_all = QB_TID, grp = tid_all >> 8, tid = tid_all & 255u;\n";
+        s += "    if (tid_all < 2u) QB_FLAG_ST(&done[tid_all], 0u);\n";
+        s += "    QB_BLOCK_SYNC();\n";
+        s += "    const u32 n_mine = QB_BID < n_tiles ? (n_tiles - QB_BID + QB_GRID - 1u) / QB_GRID : 0u;\n";
+        s += "    u32 tl;\n";
+        emit_tl(p.rounds[0]);
+        s += "    const u32 tl0 = tl;\n";
+        f("    const u64 goff0 = %s;\n", goff_expr().c_str());
+        emit_prefetch_lambda();
+        s += "    if (grp < n_mine) prefetch(grp);\n";
+        s += "    for (u32 k = grp; k < n_mine; k += 2u) {\n";
+        s += "    double2* const tile = bufs + (k % 3u) * 4096u;\n";
+        s += "    const u32 tix = (QB_BID + k * QB_GRID) | tile_or;\n";
+        f("    const u64 base = %s;\n", base_expr("tix").c_str());
+        s += "    bool pf = k + 2u >= n_mine;   // true: tile k + 2 has been requested (or does not exist)\n";
+        s += "    double";
+        for (int j = 0; j < 16; ++j) f(" x%d, y%d%s", j, j, j == 15 ? ";\n" : ",");
+        s += "    double px = 1.0, py = 0.0;\n    tl = tl0;\n";
+        for (int j = 0; j < 16; ++j) nm[j] = j;
+        s += "    QB_CP_ASYNC_WAIT_ALL();\n";   // the only copies in flight are this thread's amplitudes of tile k
+        for (int j = 0; j < 16; ++j)
+            f("    { const double2 t_ = tile[tl0 | 0x%xu]; x%d = t_.x; y%d = t_.y; }\n", reg_local(p.rounds[0], j), j, j);
+        const char* publish = "    if (tid == 0u) QB_FLAG_ST(&done[grp], k + 1u);\n";
+        const char* try_pf = "    if (!pf && QB_FLAG_LD(&done[grp ^ 1u]) >= k) { prefetch(k + 2u); pf = true; }\n";
+        if (p.n_rounds > 1) s += "    QB_GROUP_SYNC(grp);\n";   // everybody has its amplitudes: the buffer is the transposes' scratch from here on
+        else { s += "    QB_GROUP_SYNC(grp);\n"; s += publish; }
+        s += try_pf;
+        for (uint32_t r = 0; r < p.n_rounds; ++r) {
+            const RoundDesc& rd = p.rounds[r];
+            f("    // ---- round %u: register bits %u %u %u %u ----\n", r, rd.R[0], rd.R[1], rd.R[2], rd.R[3]);
+            if (r > 0) {
+                const RoundDesc& prev = p.rounds[r - 1];
+                s += "    {\n      const u32 s_t = qb_swz(tl);\n";
+                for (int j = 0; j < 16; ++j) f("      tile[s_t ^ 0x%xu] = make_double2(%s, %s);\n", prev.sro[j], X(j).c_str(), Y(j).c_str());
+                s += "    }\n    QB_GROUP_SYNC(grp);\n";
+                emit_tl(rd);
+                s += "    {\n      const u32 s_n = qb_swz(tl);\n";
+                for (int j = 0; j < 16; ++j) {
+                    nm[j] = j;
+                    f("      { const double2 t_ = tile[s_n ^ 0x%xu]; x%d = t_.x; y%d = t_.y; }\n", rd.sro[j], j, j);
+                }
+                s += "    }\n    QB_GROUP_SYNC(grp);\n";   // the buffer is written again by the next transpose, or handed to the other group
+                if (r + 1 == p.n_rounds) s += publish;
+                s += try_pf;
+            }
+            s += "    px = 1.0; py = 0.0;\n";
+            tph_one = true;
+            for (uint32_t oi = rd.op_begin; oi < rd.op_end; ++oi) emit_op(p.ops[oi]);
+            if (rd.has_tph && !tph_one) {
+                s += "    {\n";
+                for (int j = 0; j < 16; ++j) cmul_reg_expr(j, "px", "py");
+                close();
+            }
+        }
+        // the other group may still be transposing in the buffer tile k + 2 goes to: wait for it here at the latest
+        s += "    if (!pf) { while (QB_FLAG_LD(&done[grp ^ 1u]) < k) QB_SPIN(); prefetch(k + 2u); }\n";
+        f("    {\n      const u64 gt = base + (%s);\n", goff_expr().c_str());
+        for (int j = 0; j < 16; ++j)
+            f("      QB_ST(st + (gt + 0x%llxull), %s, %s);\n", (unsigned long long)p.gro_last[j], X(j).c_str(), Y(j).c_str());
+        s += "    }\n    }\n}\n";
+        return finish();
+    }
+
     std::string run() {
+        if (o.pipelined == 3 && !o.remote && o.xchg_bits == 0) return run_ring();
         if (o.pipelined && !o.remote && o.xchg_bits == 0) return run_pipelined();
         // ---- kernel body ----
         f("%s(qb_jit_pass, %d)\n{\n", o.xchg_bits > 0 ? "QB_KERNEL_XCHG" : o.remote ? "QB_KERNEL_REMOTE" : "QB_KERNEL", o.min_blocks);
@@ -643,6 +736,10 @@ struct Gen {
     std::string finish() {
         std::string head = "// generated by quaru_b200 (qb_jit_gen.cu): one fused tile pass, specialised\n#ifdef QB_HOST_EMU\n#include \"qb_jit_emu.h\"\n#else\n";
         head += kDevicePrelude;
+        // experiments on the bulk-async shapes' rare trap (QB_RING_DBG, read when the source is generated): 1 = mbarrier.test_wait
+        // (no hardware suspend) instead of try_wait, 2 = one polling lane per warp
+        if (o.dbg & 1) head += "#undef QB_MBAR_WAIT\n#define QB_MBAR_WAIT(B, P) do { u32 done_; do { asm volatile(\"{\\n\\t.reg .pred p;\\n\\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\\n\\tselp.u32 %0, 1, 0, p;\\n\\t}\" : \"=r\"(done_) : \"r\"(qb_saddr(B)), \"r\"((u32)(P)) : \"memory\"); } while (!done_); } while (0)\n";
+        if (o.dbg & 2) head += "#define QB_MBAR_WAIT_ALL(B, P) QB_MBAR_WAIT(B, P)\n#undef QB_MBAR_WAIT\n#define QB_MBAR_WAIT(B, P) do { if ((QB_TID & 31u) == 0u) { u32 done_; do { asm volatile(\"{\\n\\t.reg .pred p;\\n\\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\\n\\tselp.u32 %0, 1, 0, p;\\n\\t}\" : \"=r\"(done_) : \"r\"(qb_saddr(B)), \"r\"((u32)(P)) : \"memory\"); } while (!done_); } __syncwarp(); } while (0)\n";
         head += "#endif\nstatic __device__ __forceinline__ u32 qb_swz(u32 l) { return l ^ (((l >> 3) ^ (l >> 6) ^ (l >> 9)) & 7u); }\n";
         if (uses_table) {
             head += "QB_TABLE_DECL = {\n";

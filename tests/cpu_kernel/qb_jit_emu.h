@@ -59,15 +59,24 @@ static inline void qb_emu_mbar_check(QB_MBAR_T* b) {   // b->mu held
     if (b->pending == 0 && b->tx == 0) { b->phase++; b->pending = b->count; }
 }
 static inline void qb_emu_mbar_init(QB_MBAR_T* b, int c) { new (b) QB_MBAR_T(); b->count = b->pending = c; }
+#include <stdio.h>
+#include <stdlib.h>
+static inline void qb_emu_mbar_fail(const char* what) {   // what the hardware answers with a trap ("Warp Illegal Instruction")
+    fprintf(stderr, "qb_jit_emu: mbarrier protocol error: %s\n", what);
+    abort();
+}
 static inline void qb_emu_mbar_arrive(QB_MBAR_T* b, long long expect) {
     std::lock_guard<std::mutex> lk(b->mu);
+    if (b->pending <= 0) qb_emu_mbar_fail("arrival on a phase whose arrivals are complete (pending count underflow)");
     b->tx += expect;
+    if (b->tx > 1048575 || b->tx < -1048575) qb_emu_mbar_fail("tx-count out of range");
     b->pending--;
     qb_emu_mbar_check(b);
 }
 static inline void qb_emu_mbar_complete(QB_MBAR_T* b, long long bytes) {
     std::lock_guard<std::mutex> lk(b->mu);
     b->tx -= bytes;
+    if (b->tx > 1048575 || b->tx < -1048575) qb_emu_mbar_fail("tx-count out of range");
     qb_emu_mbar_check(b);
 }
 static inline void qb_emu_mbar_wait(QB_MBAR_T* b, unsigned parity) {   // returns once the phase of that parity has completed
@@ -94,3 +103,10 @@ extern unsigned char* qb_emu_shared_raw;
 #define QB_GROUP_SYNC(G) pthread_barrier_wait(&qb_emu_group_barrier[(G)])
 #define QB_SYNCWARP() pthread_barrier_wait(&qb_emu_warp_barrier[QB_TID >> 5])   /* lanes are OS threads here: a real barrier */
 #define QB_BLOCK_SYNC() pthread_barrier_wait(&qb_emu_block_barrier)
+// the prefetching ring (pipelined = 3): cp.async is an immediate copy here; the done[] flags are atomics
+#define QB_CP_ASYNC16(D, S) memcpy((void*)(D), (const void*)(S), 16)
+#define QB_CP_ASYNC_COMMIT() ((void)0)
+#define QB_CP_ASYNC_WAIT_ALL() ((void)0)
+#define QB_FLAG_LD(P) __atomic_load_n((P), __ATOMIC_ACQUIRE)
+#define QB_FLAG_ST(P, V) __atomic_store_n((P), (V), __ATOMIC_RELEASE)
+#define QB_SPIN() sched_yield()

@@ -75,7 +75,7 @@ def run_circuit(n, ops, seed, grid=0, **gen):
             dev[:] = tmp.state
             continue
         n_prog += 1
-        lib = build_host(jit_source(p[3]["bytes"], **gen), pipe={2: 544, 3: 512}.get(gen.get("persistent"), 0))
+        lib = build_host(jit_source(p[3]["bytes"], **gen), pipe={2: 544, 3: 512, 4: 512}.get(gen.get("persistent"), 0))
         assert lib.jit_host_run(dev.ctypes.data, 1 << (n - 12), grid, 0, None, 0, 0) == 0
     return dev, ora.state, n_prog
 
@@ -233,11 +233,12 @@ def test_exchanging_pass_stores_into_the_post_exchange_placement(world, n, kind,
 
 
 @pytest.mark.parametrize("n,grid,kind", [(14, 1, "layers"), (15, 2, "mixed"), (15, 3, "qft"), (13, 1, "mixed"), (16, 5, "layers"), (12, 1, "qft")])
-@pytest.mark.parametrize("shape", [2, 3])
+@pytest.mark.parametrize("shape", [2, 3, 4])
 def test_pipelined_shape(n, grid, kind, shape):
     """The pipelined kernel shapes (one persistent CTA per SM: tiles stream into a ring of three shared-memory buffers with
     bulk-async copies counted on mbarriers, two consumer groups of 256 threads take alternate tiles, results go back through
-    the buffer with bulk-async stores; shape 2 = a producer warp feeds the ring, shape 3 = the storing warp refills its buffer)
+    the buffer with bulk-async stores; shape 2 = a producer warp feeds the ring, shape 3 = the storing warp refills its buffer;
+    shape 4 = the prefetching ring: per-thread cp.async of the group's next tile, done[] flags between the groups, direct stores)
     with the mbarrier / bulk-copy / named-barrier protocol emulated on CPU threads: tile counts that are smaller than, equal to
     and not a multiple of the ring and the grid."""
     ops = {"layers": circuits.random_circuit(n, 4, seed=2 * n), "qft": circuits.qft_circuit(n), "mixed": circuits.mixed_circuit(n, 100, 3 * n)}[kind]
