@@ -60,7 +60,7 @@ static int alloc_common(Reg* r) {
     if (const char* j = getenv("QB_JIT_VARIANT")) {
         const int v = atoi(j);
         r->jit_min_blocks = (v & 15) ? (v & 15) : 2; r->jit_persistent = (v >> 4) & 1; r->jit_prefetch = (v >> 5) & 1;
-        r->jit_pipelined = (v >> 6) & 3;
+        r->jit_pipelined = (v >> 6) & 1;
     }
     return QB_OK;
 }
@@ -651,9 +651,9 @@ int qb_set_option(qb_reg* reg, int32_t option, int64_t value) try {
             return QB_OK;
         case QB_OPT_JIT_MIN_QUBITS: r->jit_min_qubits = (uint32_t)std::max<int64_t>(value, 12); return QB_OK;
         case QB_OPT_JIT_VARIANT:
-            if ((value & 15) < 1 || (value & 15) > 4 || value > 255) return set_error(QB_ERR_INVALID_ARGUMENT, value, "bad jit variant");
+            if ((value & 15) < 1 || (value & 15) > 4 || value > 127) return set_error(QB_ERR_INVALID_ARGUMENT, value, "bad jit variant");
             r->jit_min_blocks = (int)(value & 15); r->jit_persistent = (int)((value >> 4) & 1); r->jit_prefetch = (int)((value >> 5) & 1);
-            r->jit_pipelined = (int)((value >> 6) & 3);
+            r->jit_pipelined = (int)((value >> 6) & 1);
             return QB_OK;
         case QB_OPT_FORCE_PATH:
             if (value < 0 || value > 5) return set_error(QB_ERR_INVALID_ARGUMENT, value, "force path must be in [0, 5]");

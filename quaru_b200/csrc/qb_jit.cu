@@ -130,7 +130,7 @@ void fnv(const void* data, size_t len, uint64_t* a, uint64_t* b) {
 Key key_of(const ProgView& p, const JitOpts& o) {
     uint64_t a = 0xcbf29ce484222325ull, b = 0x84222325cbf29ce4ull;
     const uint32_t hdr[12] = {p.lc, p.h, p.n_rounds, p.n_mats, p.n_ops, (uint32_t)o.min_blocks, (uint32_t)o.persistent, (uint32_t)o.prefetch,
-                              (uint32_t)o.remote | ((uint32_t)o.pipelined << 8) | ((uint32_t)o.dbg << 16), (uint32_t)o.xchg_bits,
+                              (uint32_t)o.remote | ((uint32_t)o.pipelined << 8), (uint32_t)o.xchg_bits,
                               (uint32_t)o.xchg_V[0] | ((uint32_t)o.xchg_V[1] << 8) | ((uint32_t)o.xchg_V[2] << 16),
                               (uint32_t)o.xchg_J[0] | ((uint32_t)o.xchg_J[1] << 8) | ((uint32_t)o.xchg_J[2] << 16)};
     fnv(hdr, sizeof(hdr), &a, &b);
@@ -236,9 +236,9 @@ int load_on_device(Entry* e, int device) {
     CUfunction fn = nullptr;
     rc = d->ModuleGetFunction(&fn, mod, "qb_jit_pass");
     if (rc) return fail_cu(rc, "cuModuleGetFunction(qb_jit_pass)");
-    // the pipelined shapes: a ring of three tile buffers + mbarriers; 544 threads with the producer warp, 512 without
+    // the prefetching ring: three tile buffers + the two done[] flags, 512 threads
     const unsigned smem = e->opts.pipelined ? 3u * 65536u + 128u : (unsigned)(sizeof(c64) << RT);
-    const int threads = e->opts.pipelined == 1 ? 544 : e->opts.pipelined >= 2 ? 512 : RTHREADS;
+    const int threads = e->opts.pipelined ? 512 : RTHREADS;
     rc = d->FuncSetAttribute(fn, 8 /* CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES */, (int)smem);
     if (rc) return fail_cu(rc, "cuFuncSetAttribute(max dynamic shared memory)");
     int per_sm = 0;
@@ -272,9 +272,8 @@ int jit_try_launch(Reg* r, const ProgView& p, const RemoteArgs* remote, bool* la
     o.persistent = r->jit_persistent;
     o.prefetch = r->jit_persistent ? r->jit_prefetch : 0;
     o.remote = remote != nullptr;
-    o.pipelined = (r->jit_pipelined && !remote && !xchg) ? r->jit_pipelined : 0;
+    o.pipelined = (r->jit_pipelined && !remote && !xchg) ? 1 : 0;
     if (o.pipelined) o.persistent = o.prefetch = 0;
-    if (o.pipelined) { const char* d = getenv("QB_RING_DBG"); o.dbg = d ? atoi(d) : 0; }
     if (xchg) {
         o.xchg_bits = xchg->gp;
         for (int i = 0; i < xchg->gp; ++i) { o.xchg_V[i] = xchg->V[i]; o.xchg_J[i] = xchg->J[i]; }
@@ -337,7 +336,7 @@ int jit_try_launch(Reg* r, const ProgView& p, const RemoteArgs* remote, bool* la
         args[2] = &n_tiles;
     }
     if (r->profile) QB_TRY(tile_profile_begin(r));
-    const unsigned block = o.pipelined == 1 ? 544u : o.pipelined >= 2 ? 512u : (unsigned)RTHREADS;
+    const unsigned block = o.pipelined ? 512u : (unsigned)RTHREADS;
     const unsigned smem = o.pipelined ? 3u * 65536u + 128u : (unsigned)(sizeof(c64) << RT);
     rc = driver()->LaunchKernel(e->fn[r->device], grid, 1, 1, block, 1, 1, smem, (void*)r->stream, args, nullptr);
     if (rc) return fail_cu(rc, "cuLaunchKernel(qb_jit_pass)");
@@ -390,9 +389,8 @@ int64_t qb_jit_source_debug(const void* program, uint64_t len, int32_t min_block
     JitOpts o;
     o.min_blocks = min_blocks;
     o.persistent = persistent == 1;
-    o.pipelined = persistent >= 2 ? persistent - 1 : 0;   // `persistent` = 2 / 3 / 4 select the pipelined shapes (producer warp / self-fed ring / prefetching ring)
+    o.pipelined = persistent == 2;   // `persistent` = 2 selects the prefetching ring
     o.prefetch = prefetch;
-    if (o.pipelined) { const char* d = getenv("QB_RING_DBG"); o.dbg = d ? atoi(d) : 0; }
     o.remote = remote;
     if (xchg_bits < 0 || xchg_bits > 3 || (xchg_bits && !xchg_vj)) return set_error(QB_ERR_INVALID_ARGUMENT, xchg_bits, "0..3 exchanged bits");
     o.xchg_bits = xchg_bits;

@@ -28,9 +28,8 @@ struct JitOpts {
     int min_blocks = 2;   // __launch_bounds__(256, min_blocks): 2 -> 128 registers, 3 -> 80
     int persistent = 0;   // CTAs walk the tiles (grid = resident CTAs) instead of one CTA per tile
     int prefetch = 0;     // persistent only: prefetch.global.L2 of the next tile after the current tile's loads were issued
-    int pipelined = 0;    // one persistent CTA per SM, bulk-async (cp.async.bulk / mbarrier) ring of three tile buffers, two consumer
-                          // groups: 1 = a 17th warp is the producer, 2 = the storing warp refills the buffer (512 threads)
-    int dbg = 0;          // QB_RING_DBG: experiments on the bulk-async shapes (see qb_jit_gen.cu)
+    int pipelined = 0;    // the prefetching ring: one persistent CTA of 512 threads per SM, two groups on alternate tiles, every thread
+                          // fetches its amplitudes of the group's next tile with cp.async into a ring of three tile buffers
     int remote = 0;       // sharded registers: amplitudes addressed through the table of peer-mapped shards
     // sharded registers, the exchanging epilogue: the pass stores every amplitude where it lives after the exchange of local
     // bits xchg_V[i] with rank bits xchg_J[i], into the destination rank's other state buffer (0 = an ordinary pass)

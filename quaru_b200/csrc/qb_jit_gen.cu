@@ -39,23 +39,10 @@ typedef unsigned long long u64;
 struct QbRemote { double2* base[8]; u32 n_local; u32 pad; };
 #define QB_KERNEL(name, minb) extern "C" __global__ void __launch_bounds__(256, minb) name(double2* __restrict__ st, u32 tile_or, u32 n_tiles)
 #define QB_KERNEL_REMOTE(name, minb) extern "C" __global__ void __launch_bounds__(256, minb) name(const __grid_constant__ QbRemote ra, u32 tile_or, u32 n_tiles)
-#define QB_KERNEL_PIPE(name) extern "C" __global__ void __launch_bounds__(544, 1) name(double2* __restrict__ st, u32 tile_or, u32 n_tiles)
 #define QB_KERNEL_RING(name) extern "C" __global__ void __launch_bounds__(512, 1) name(double2* __restrict__ st, u32 tile_or, u32 n_tiles)
 #define QB_SMEM_RAW(t) extern __shared__ __align__(128) unsigned char t[]
-typedef u64 QB_MBAR_T;
 static __device__ __forceinline__ u32 qb_saddr(const void* p) { return (u32)__cvta_generic_to_shared(p); }
-#define QB_MBAR_INIT(B, C) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(qb_saddr(B)), "r"((u32)(C)) : "memory")
-#define QB_MBAR_INIT_FENCE() asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory")
-#define QB_MBAR_EXPECT_TX(B, N) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(qb_saddr(B)), "r"((u32)(N)) : "memory")
-#define QB_MBAR_ARRIVE(B) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(qb_saddr(B)) : "memory")
-#define QB_MBAR_WAIT(B, P) do { u32 done_; do { asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done_) : "r"(qb_saddr(B)), "r"((u32)(P)) : "memory"); } while (!done_); } while (0)
-#define QB_BULK_G2S(D, S, N, B) asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(qb_saddr(D)), "l"(S), "r"((u32)(N)), "r"(qb_saddr(B)) : "memory")
-#define QB_BULK_S2G(D, S, N) asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(D), "r"(qb_saddr(S)), "r"((u32)(N)) : "memory")
-#define QB_BULK_COMMIT() asm volatile("cp.async.bulk.commit_group;" ::: "memory")
-#define QB_BULK_WAIT_READ() asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory")
-#define QB_FENCE_ASYNC() asm volatile("fence.proxy.async.shared::cta;" ::: "memory")
 #define QB_GROUP_SYNC(G) asm volatile("bar.sync %0, 256;" ::"r"(1u + (G)) : "memory")
-#define QB_SYNCWARP() __syncwarp()
 #define QB_BLOCK_SYNC() __syncthreads()
 #define QB_CP_ASYNC16(D, S) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(qb_saddr(D)), "l"(S) : "memory")
 #define QB_CP_ASYNC_COMMIT() asm volatile("cp.async.commit_group;" ::: "memory")
@@ -414,149 +401,7 @@ struct Gen {
         return l;
     }
 
-    // ---- the pipelined shapes ----------------------------------------------------------------------------------------------
-    // One persistent CTA per SM; tiles travel HBM -> shared memory -> HBM as bulk-async copies (cp.async.bulk, one per
-    // contiguous segment of the tile, completion counted on an mbarrier) through a ring of three 64 KB buffers, and two
-    // consumer groups of 256 threads take alternate tiles: wait for the buffer, registers <- buffer, the rounds (transposes
-    // through the same buffer, named barriers per group), registers -> buffer, bulk-async store back to HBM.  HBM latency never
-    // sits in a consumer's critical path, and while one group is at a barrier or in a transpose the other one has the FP64 pipe.
-    //   pipelined = 1: a 17th warp is the producer; buffers come back to it through a second set of mbarriers.  544 threads
-    //                  leave 96 registers per thread (5 warps on one SM sub-partition), so the larger programs spill.
-    //   pipelined = 2: no producer warp.  The thread that has just stored a segment of tile k out of a buffer (and waited until
-    //                  the copy engine has read it) refills those bytes with the same segment of tile k + 3 itself: the buffer's
-    //                  next user is the OTHER group, half a tile period later.  512 threads, 128 registers, one set of
-    //                  mbarriers, the copies issued by all eight warps of the group.
-    void emit_fill(const char* ind, const char* lane, const char* tix_expr) {   // one warp: arm full[stage_f], issue the segment copies
-        const uint32_t nseg = 1u << (RT - p.lc), seg_amps = 1u << p.lc;
-        std::string segoff;
-        char buf[128];
-        for (uint32_t i = 0; i < p.h;) {
-            uint32_t len = 1;
-            while (i + len < p.h && p.hp[i + len] == p.hp[i] + len) ++len;
-            snprintf(buf, sizeof(buf), "%s((u64)((sg_ >> %u) & 0x%xu) << %u)", segoff.empty() ? "" : " | ", i, (1u << len) - 1u, p.hp[i]);
-            segoff += buf;
-            i += len;
-        }
-        if (segoff.empty()) segoff = "0ull";
-        f("%sconst u32 ftix = %s;\n", ind, tix_expr);
-        f("%sconst u64 fbase = %s;\n", ind, base_expr("ftix").c_str());
-        f("%sif (%s == 0) QB_MBAR_EXPECT_TX(&full[stage_f], 65536u);\n%sQB_SYNCWARP();\n", ind, lane, ind);
-        f("%sfor (u32 sg_ = %s; sg_ < %uu; sg_ += 32u)\n", ind, lane, nseg);
-        f("%s  QB_BULK_G2S(bufs + stage_f * 4096u + sg_ * %uu, st + (fbase + (%s)), %uu, &full[stage_f]);\n", ind, seg_amps, segoff.c_str(), seg_amps * 16u);
-    }
-    std::string segoff_expr() const {
-        std::string segoff;
-        char buf[128];
-        for (uint32_t i = 0; i < p.h;) {
-            uint32_t len = 1;
-            while (i + len < p.h && p.hp[i + len] == p.hp[i] + len) ++len;
-            snprintf(buf, sizeof(buf), "%s((u64)((sg_ >> %u) & 0x%xu) << %u)", segoff.empty() ? "" : " | ", i, (1u << len) - 1u, p.hp[i]);
-            segoff += buf;
-            i += len;
-        }
-        return segoff.empty() ? "0ull" : segoff;
-    }
-    std::string run_pipelined() {
-        const bool self_fed = o.pipelined == 2;
-        const uint32_t nseg = 1u << (RT - p.lc), seg_amps = 1u << p.lc;
-        s += self_fed ? "QB_KERNEL_RING(qb_jit_pass)\n{\n" : "QB_KERNEL_PIPE(qb_jit_pass)\n{\n";
-        s += "    QB_SMEM_RAW(smem_raw);\n";
-        s += "    double2* const bufs = reinterpret_cast<double2*>(smem_raw);\n";
-        s += "    QB_MBAR_T* const full = reinterpret_cast<QB_MBAR_T*>(smem_raw + 3u * 65536u);\n";
-        if (!self_fed) s += "    QB_MBAR_T* const empty = full + 3;\n";
-        s += "    const u32 tid_all = QB_TID;\n";
-        if (self_fed) s += "    if (tid_all == 0) { for (int i_ = 0; i_ < 3; ++i_) QB_MBAR_INIT(&full[i_], 1); QB_MBAR_INIT_FENCE(); }\n";
-        else s += "    if (tid_all == 0) { for (int i_ = 0; i_ < 3; ++i_) { QB_MBAR_INIT(&full[i_], 1); QB_MBAR_INIT(&empty[i_], 1); } QB_MBAR_INIT_FENCE(); }\n";
-        s += "    QB_BLOCK_SYNC();\n";
-        s += "    const u32 n_mine = QB_BID < n_tiles ? (n_tiles - QB_BID + QB_GRID - 1u) / QB_GRID : 0u;\n";
-        const std::string segoff = segoff_expr();
-        if (self_fed) {
-            // ---- prologue: the first warp fills the ring ----
-            s += "    if (tid_all < 32u) {\n      for (u32 k = 0; k < 3u && k < n_mine; ++k) {\n        const u32 stage_f = k;\n";
-            emit_fill("        ", "tid_all", "(QB_BID + k * QB_GRID) | tile_or");
-            s += "      }\n    }\n";
-        } else {
-            // ---- producer ----
-            s += "    if (tid_all >= 512u) {\n      const u32 lane = tid_all - 512u;\n";
-            s += "      for (u32 k = 0; k < n_mine; ++k) {\n        const u32 stage_f = k % 3u, par = (k / 3u) & 1u;\n";
-            s += "        QB_MBAR_WAIT(&empty[stage_f], par ^ 1u);\n";
-            emit_fill("        ", "lane", "(QB_BID + k * QB_GRID) | tile_or");
-            s += "      }\n      return;\n    }\n";
-        }
-        // ---- consumers ----
-        s += "    const u32 grp = tid_all >> 8, tid = tid_all & 255u;\n";
-        s += "    for (u32 k = grp; k < n_mine; k += 2u) {\n";
-        s += "    const u32 stage = k % 3u, par = (k / 3u) & 1u;\n";
-        s += "    double2* const tile = bufs + stage * 4096u;\n";
-        s += "    const u32 tix = (QB_BID + k * QB_GRID) | tile_or;\n";
-        f("    const u64 base = %s;\n", base_expr("tix").c_str());
-        s += "    double";
-        for (int j = 0; j < 16; ++j) f(" x%d, y%d%s", j, j, j == 15 ? ";\n" : ",");
-        s += "    double px = 1.0, py = 0.0;\n    u32 tl;\n";
-        for (int j = 0; j < 16; ++j) nm[j] = j;
-        emit_tl(p.rounds[0]);
-        s += "    QB_MBAR_WAIT(&full[stage], par);\n";
-        for (int j = 0; j < 16; ++j)
-            f("    { const double2 t_ = tile[tl | 0x%xu]; x%d = t_.x; y%d = t_.y; }\n", reg_local(p.rounds[0], j), j, j);
-        s += "    QB_GROUP_SYNC(grp);\n";   // everybody has its amplitudes: the buffer is the transposes' scratch from here on
-        for (uint32_t r = 0; r < p.n_rounds; ++r) {
-            const RoundDesc& rd = p.rounds[r];
-            f("    // ---- round %u: register bits %u %u %u %u ----\n", r, rd.R[0], rd.R[1], rd.R[2], rd.R[3]);
-            if (r > 0) {
-                const RoundDesc& prev = p.rounds[r - 1];
-                s += "    {\n      const u32 s_t = qb_swz(tl);\n";
-                for (int j = 0; j < 16; ++j) f("      tile[s_t ^ 0x%xu] = make_double2(%s, %s);\n", prev.sro[j], X(j).c_str(), Y(j).c_str());
-                s += "    }\n    QB_GROUP_SYNC(grp);\n";
-                emit_tl(rd);
-                s += "    {\n      const u32 s_n = qb_swz(tl);\n";
-                for (int j = 0; j < 16; ++j) {
-                    nm[j] = j;
-                    f("      { const double2 t_ = tile[s_n ^ 0x%xu]; x%d = t_.x; y%d = t_.y; }\n", rd.sro[j], j, j);
-                }
-                s += "    }\n    QB_GROUP_SYNC(grp);\n";   // the buffer is written again (next transpose, or the store staging below)
-            }
-            s += "    px = 1.0; py = 0.0;\n";
-            tph_one = true;
-            for (uint32_t oi = rd.op_begin; oi < rd.op_end; ++oi) emit_op(p.ops[oi]);
-            if (rd.has_tph && !tph_one) {
-                s += "    {\n";
-                for (int j = 0; j < 16; ++j) cmul_reg_expr(j, "px", "py");
-                close();
-            }
-        }
-        // registers -> buffer (tile-local order = the order of the tile's segments in HBM), then bulk-async stores
-        const RoundDesc& last = p.rounds[p.n_rounds - 1];
-        for (int j = 0; j < 16; ++j) f("    tile[tl | 0x%xu] = make_double2(%s, %s);\n", reg_local(last, j), X(j).c_str(), Y(j).c_str());
-        if (self_fed) {
-            // Every thread of the group is past its wait on full[stage] (the group barriers above), so the barrier's next phase
-            // can be armed here.  Then the segments are spread over the group's eight warps (a warp issues its lanes' bulk copies
-            // one after the other): the thread that stored a segment waits until the copy engine has read it out of shared
-            // memory and refills the same bytes with the same segment of tile k + 3 -- the buffer's next user is the OTHER group.
-            s += "    const bool refill = k + 3u < n_mine;\n";
-            s += "    if (tid == 0u && refill) QB_MBAR_EXPECT_TX(&full[stage], 65536u);\n";
-            s += "    QB_FENCE_ASYNC();\n    QB_GROUP_SYNC(grp);\n";
-            s += "    {\n      const u32 sg_ = (tid >> 5) + 8u * (tid & 31u);\n";
-            f("      if (sg_ < %uu) {\n", nseg);
-            f("        const u64 so_ = %s;\n", segoff.c_str());
-            f("        QB_BULK_S2G(st + (base + so_), tile + sg_ * %uu, %uu);\n", seg_amps, seg_amps * 16u);
-            s += "        QB_BULK_COMMIT();\n        QB_BULK_WAIT_READ();\n";
-            s += "        if (refill) {\n          const u32 ftix = (QB_BID + (k + 3u) * QB_GRID) | tile_or;\n";
-            f("          const u64 fbase = %s;\n", base_expr("ftix").c_str());
-            f("          QB_BULK_G2S(tile + sg_ * %uu, st + (fbase + so_), %uu, &full[stage]);\n", seg_amps, seg_amps * 16u);
-            s += "        }\n      }\n    }\n";
-        } else {
-            s += "    QB_FENCE_ASYNC();\n    QB_GROUP_SYNC(grp);\n";
-            s += "    if (tid < 32u) {\n";
-            f("      for (u32 sg_ = tid; sg_ < %uu; sg_ += 32u)\n", nseg);
-            f("        QB_BULK_S2G(st + (base + (%s)), tile + sg_ * %uu, %uu);\n", segoff.c_str(), seg_amps, seg_amps * 16u);
-            s += "      QB_BULK_COMMIT();\n      QB_BULK_WAIT_READ();\n      QB_SYNCWARP();\n";
-            s += "      if (tid == 0) QB_MBAR_ARRIVE(&empty[stage]);\n    }\n";
-        }
-        s += "    }\n}\n";
-        return finish();
-    }
-
-    // ---- the prefetching ring (pipelined = 3) ------------------------------------------------------------------------------
+    // ---- the prefetching ring (pipelined = 1) ------------------------------------------------------------------------------
     // One persistent CTA of 512 threads per SM, two groups of 256 threads on alternate tiles, three 64 KB buffers: tile k lives
     // in buffer k % 3.  Every thread fetches ITS OWN 16 amplitudes of its group's next tile (k + 2) with 16-byte cp.async
     // (LDGSTS: HBM -> shared memory without passing through registers) while it computes tile k, and reads them back with
@@ -643,8 +488,7 @@ struct Gen {
     }
 
     std::string run() {
-        if (o.pipelined == 3 && !o.remote && o.xchg_bits == 0) return run_ring();
-        if (o.pipelined && !o.remote && o.xchg_bits == 0) return run_pipelined();
+        if (o.pipelined && !o.remote && o.xchg_bits == 0) return run_ring();
         // ---- kernel body ----
         f("%s(qb_jit_pass, %d)\n{\n", o.xchg_bits > 0 ? "QB_KERNEL_XCHG" : o.remote ? "QB_KERNEL_REMOTE" : "QB_KERNEL", o.min_blocks);
         s += "    QB_SMEM(tile);\n    const u32 tid = QB_TID;\n";
@@ -736,10 +580,6 @@ struct Gen {
     std::string finish() {
         std::string head = "// generated by quaru_b200 (qb_jit_gen.cu): one fused tile pass, specialised\n#ifdef QB_HOST_EMU\n#include \"qb_jit_emu.h\"\n#else\n";
         head += kDevicePrelude;
-        // experiments on the bulk-async shapes' rare trap (QB_RING_DBG, read when the source is generated): 1 = mbarrier.test_wait
-        // (no hardware suspend) instead of try_wait, 2 = one polling lane per warp
-        if (o.dbg & 1) head += "#undef QB_MBAR_WAIT\n#define QB_MBAR_WAIT(B, P) do { u32 done_; do { asm volatile(\"{\\n\\t.reg .pred p;\\n\\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\\n\\tselp.u32 %0, 1, 0, p;\\n\\t}\" : \"=r\"(done_) : \"r\"(qb_saddr(B)), \"r\"((u32)(P)) : \"memory\"); } while (!done_); } while (0)\n";
-        if (o.dbg & 2) head += "#define QB_MBAR_WAIT_ALL(B, P) QB_MBAR_WAIT(B, P)\n#undef QB_MBAR_WAIT\n#define QB_MBAR_WAIT(B, P) do { if ((QB_TID & 31u) == 0u) { u32 done_; do { asm volatile(\"{\\n\\t.reg .pred p;\\n\\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\\n\\tselp.u32 %0, 1, 0, p;\\n\\t}\" : \"=r\"(done_) : \"r\"(qb_saddr(B)), \"r\"((u32)(P)) : \"memory\"); } while (!done_); } __syncwarp(); } while (0)\n";
         head += "#endif\nstatic __device__ __forceinline__ u32 qb_swz(u32 l) { return l ^ (((l >> 3) ^ (l >> 6) ^ (l >> 9)) & 7u); }\n";
         if (uses_table) {
             head += "QB_TABLE_DECL = {\n";

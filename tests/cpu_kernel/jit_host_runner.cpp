@@ -13,7 +13,7 @@ pthread_barrier_t qb_emu_barrier;
 alignas(128) static unsigned char g_shared_raw[3 * 65536 + 1024];
 double2* qb_emu_shared = reinterpret_cast<double2*>(g_shared_raw);
 unsigned char* qb_emu_shared_raw = g_shared_raw;
-pthread_barrier_t qb_emu_group_barrier[2], qb_emu_block_barrier, qb_emu_warp_barrier[17];
+pthread_barrier_t qb_emu_group_barrier[2], qb_emu_block_barrier;
 
 #include QB_JIT_SRC
 
@@ -23,8 +23,7 @@ pthread_barrier_t qb_emu_group_barrier[2], qb_emu_block_barrier, qb_emu_warp_bar
 extern "C" int jit_host_run(double* state, unsigned n_tiles, unsigned grid, unsigned tile_or, void* const* bases, unsigned world,
                             unsigned n_local) {
 #ifdef QB_JIT_PIPE
-    // pipelined shapes: `grid` persistent CTAs of QB_JIT_PIPE threads (2 consumer groups of 256, + the producer warp when 544),
-    // one after the other
+    // prefetching ring: `grid` persistent CTAs of QB_JIT_PIPE = 512 threads (two groups of 256), one after the other
     (void)bases; (void)world; (void)n_local;
     const unsigned ctas_p = grid ? grid : 1;
     qb_emu_grid = {ctas_p, 1, 1};
@@ -32,7 +31,6 @@ extern "C" int jit_host_run(double* state, unsigned n_tiles, unsigned grid, unsi
         pthread_barrier_init(&qb_emu_block_barrier, nullptr, QB_JIT_PIPE);
         pthread_barrier_init(&qb_emu_group_barrier[0], nullptr, 256);
         pthread_barrier_init(&qb_emu_group_barrier[1], nullptr, 256);
-        for (int w = 0; w < 17; ++w) pthread_barrier_init(&qb_emu_warp_barrier[w], nullptr, 32);
         std::vector<std::thread> th;
         for (unsigned t = 0; t < QB_JIT_PIPE; ++t)
             th.emplace_back([=]() {
@@ -44,7 +42,6 @@ extern "C" int jit_host_run(double* state, unsigned n_tiles, unsigned grid, unsi
         pthread_barrier_destroy(&qb_emu_block_barrier);
         pthread_barrier_destroy(&qb_emu_group_barrier[0]);
         pthread_barrier_destroy(&qb_emu_group_barrier[1]);
-        for (int w = 0; w < 17; ++w) pthread_barrier_destroy(&qb_emu_warp_barrier[w]);
     }
     return 0;
 #else

@@ -52,7 +52,7 @@ def build_host(src, remote=False, xchg=False, pipe=False):
         if xchg:
             cmd.insert(5, "-DQB_JIT_XCHG")
         if pipe:
-            cmd.insert(5, f"-DQB_JIT_PIPE={pipe}")   # CTA size: 544 (producer warp) or 512 (self-fed ring)
+            cmd.insert(5, f"-DQB_JIT_PIPE={pipe}")   # CTA size of the prefetching ring
         subprocess.check_call(cmd)
     lib = ctypes.CDLL(so)
     lib.jit_host_run.restype = ctypes.c_int
@@ -75,7 +75,7 @@ def run_circuit(n, ops, seed, grid=0, **gen):
             dev[:] = tmp.state
             continue
         n_prog += 1
-        lib = build_host(jit_source(p[3]["bytes"], **gen), pipe={2: 544, 3: 512, 4: 512}.get(gen.get("persistent"), 0))
+        lib = build_host(jit_source(p[3]["bytes"], **gen), pipe=512 if gen.get("persistent") == 2 else 0)
         assert lib.jit_host_run(dev.ctypes.data, 1 << (n - 12), grid, 0, None, 0, 0) == 0
     return dev, ora.state, n_prog
 
@@ -232,16 +232,15 @@ def test_exchanging_pass_stores_into_the_post_exchange_placement(world, n, kind,
             assert_close(B[rr][l2[sel]], want_local[r][l[sel]], f"exchanging pass world={world} rank {r} -> {rr}")
 
 
-@pytest.mark.parametrize("n,grid,kind", [(14, 1, "layers"), (15, 2, "mixed"), (15, 3, "qft"), (13, 1, "mixed"), (16, 5, "layers"), (12, 1, "qft")])
-@pytest.mark.parametrize("shape", [2, 3, 4])
-def test_pipelined_shape(n, grid, kind, shape):
-    """The pipelined kernel shapes (one persistent CTA per SM: tiles stream into a ring of three shared-memory buffers with
-    bulk-async copies counted on mbarriers, two consumer groups of 256 threads take alternate tiles, results go back through
-    the buffer with bulk-async stores; shape 2 = a producer warp feeds the ring, shape 3 = the storing warp refills its buffer;
-    shape 4 = the prefetching ring: per-thread cp.async of the group's next tile, done[] flags between the groups, direct stores)
-    with the mbarrier / bulk-copy / named-barrier protocol emulated on CPU threads: tile counts that are smaller than, equal to
-    and not a multiple of the ring and the grid."""
+@pytest.mark.parametrize("n,grid,kind", [(14, 1, "layers"), (15, 2, "mixed"), (15, 3, "qft"), (13, 1, "mixed"), (16, 5, "layers"), (12, 1, "qft"),
+                                         (18, 1, "layers")])
+def test_prefetching_ring(n, grid, kind):
+    """The prefetching ring (one persistent CTA of 512 threads per SM: two groups of 256 threads on alternate tiles, every thread
+    fetches its own amplitudes of the group's next tile with cp.async into a ring of three shared-memory tile buffers; the
+    groups tell each other through done[] flags when a buffer may be overwritten; results go straight from registers to the
+    state) on CPU threads: tile counts that are smaller than, equal to and not a multiple of the ring and the grid, and 64 tiles
+    through one CTA."""
     ops = {"layers": circuits.random_circuit(n, 4, seed=2 * n), "qft": circuits.qft_circuit(n), "mixed": circuits.mixed_circuit(n, 100, 3 * n)}[kind]
-    dev, want, n_prog = run_circuit(n, ops, 900 + n, grid=grid, persistent=shape)
+    dev, want, n_prog = run_circuit(n, ops, 900 + n, grid=grid, persistent=2)
     assert n_prog >= 1
-    assert_close(dev, want, f"pipelined generated kernel vs oracle, {kind} n={n} grid={grid}")
+    assert_close(dev, want, f"prefetching-ring kernel vs oracle, {kind} n={n} grid={grid}")

@@ -45,7 +45,7 @@ def main():
         pb = p[3]["bytes"]
         cap = 16 << 20
         buf = ctypes.create_string_buffer(cap)
-        persistent = 1 + ((variant >> 6) & 3) if (variant >> 6) & 3 else (variant >> 4) & 1      # bits 6-7: the pipelined shapes
+        persistent = 2 if (variant >> 6) & 1 else (variant >> 4) & 1      # bit 6: the prefetching ring
         got = L.qb_jit_source_debug(pb, len(pb), variant & 15, persistent, (variant >> 5) & 1, 0, 0, None, buf, cap)
         assert got > 0, _ffi.last_error()
         src = buf.raw[:got]
