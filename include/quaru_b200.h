@@ -175,8 +175,9 @@ int qb_timer_stop(qb_reg* reg, float* ms);
 #define QB_OPT_JIT_MIN_QUBITS 7 /* local qubits from which passes are specialised (default 26, env QB_JIT_MIN_QUBITS) */
 #define QB_OPT_JIT_VARIANT 8   /* kernel shape: bits 0-3 = CTAs per SM the register budget is set for (2 -> 128 registers, 3 -> 80),
                                   bit 4 = persistent CTAs walking the tiles, bit 5 = with an L2 prefetch of the next tile,
-                                  bit 6 = the pipelined shape: one persistent CTA per SM, a producer warp streaming tiles into a ring of
-                                  three shared-memory buffers with bulk-async copies (mbarrier completion), two consumer groups */
+                                  bit 6 = the prefetching ring: one persistent CTA of 512 threads per SM, two groups on alternate tiles,
+                                  every thread fetches its amplitudes of the group's next tile with cp.async into a ring of three
+                                  shared-memory tile buffers (measured slower than the default shape) */
 int qb_set_option(qb_reg* reg, int32_t option, int64_t value);
 
 #define QB_STAT_KERNEL_LAUNCHES 1 /* kernels launched by this handle since creation */
