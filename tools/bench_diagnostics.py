@@ -29,7 +29,7 @@ sys.path.insert(0, ROOT)
 CONFIGS = [  # (label, jit mode, jit variant, extra environment); most informative first, the time budget may cut the tail
     ("jit", 2, 2, {}),
     ("interpreter", 0, 2, {}),
-    ("jit_pipelined", 2, 2 | 64, {}),
+    ("jit_prefetch_ring", 2, 2 | 64, {}),
     ("jit_lc4", 2, 2, {"QB_PLAN_MIN_LC": "4"}),
     ("jit_3cta", 2, 3, {}),
     ("jit_persistent", 2, 2 | 16, {}),
