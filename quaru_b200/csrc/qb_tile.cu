@@ -529,6 +529,38 @@ struct BeamPlanner {
     }
 };
 
+// The second-tier plan for a gate list, with the encoder in the loop.  The beam search is allowed more gates per pass than the
+// shared-memory kernel's program holds (the register-blocked encoder merges the phase cascades of a QFT pass, hundreds of
+// gates, into a handful of ops); a pass the encoder still refuses is cut in two sweeps at launch.  So the plan's cost is its
+// number of SWEEPS, and when the first plan contains such a pass the search is repeated with smaller caps (the gates that no
+// longer fit move on to the next pass instead of paying a sweep of their own) and the cheapest plan wins.
+size_t plan_sweeps(const std::vector<Gate>& gates, uint32_t n_local, const std::vector<PlannedPass>& plan) {
+    size_t sweeps = 0;
+    for (const PlannedPass& p : plan) {
+        bool one = p.unfused || p.gate_idx.size() == 1 || p.tile_pos.size() != 12;
+        if (!one) one = pass_encodes_v2(n_local, gates, p.gate_idx, p.tile_pos, p.lc);
+        sweeps += one ? 1 : 2;
+    }
+    return sweeps;
+}
+bool beam_plan(const std::vector<Gate>& gates, uint32_t n_local, uint32_t tile_bits, bool big, int max_ops, int max_mats, size_t beam,
+               std::vector<PlannedPass>* out) {
+    const int caps[7][2] = {{big ? 320 : max_ops, big ? 1000 : max_mats}, {288, 900}, {256, 800}, {224, 700}, {192, 600}, {160, 500}, {max_ops, max_mats}};
+    bool have = false;
+    size_t best = 0;
+    for (int c = 0; c < (big ? 7 : 1); ++c) {
+        if (c > 0 && caps[c][0] >= caps[c - 1][0]) continue;
+        BeamPlanner bp(gates, n_local, tile_bits, caps[c][0], caps[c][1]);
+        std::vector<PlannedPass> cand;
+        if (!bp.run(beam, beam, &cand)) continue;
+        const size_t sw = big ? plan_sweeps(gates, n_local, cand) : cand.size();
+        if (getenv("QB_PLAN_BEAM_TRACE")) fprintf(stderr, "beam_plan: caps %d/%d -> %zu passes, %zu sweeps\n", caps[c][0], caps[c][1], cand.size(), sw);
+        if (!have || sw < best) { *out = cand; best = sw; have = true; }
+        if (sw == cand.size()) break;   // every pass of this plan is one sweep: smaller caps cannot do better
+    }
+    return have;
+}
+
 // ---- plan cache: gate-list hash -> passes (process-wide; plans carry gate INDICES, so they fit any list with the same hash) ----
 struct CachedPlan {
     std::vector<PlannedPass> passes;
@@ -727,9 +759,9 @@ int run_fused(Reg* r, std::vector<Gate>& gates, std::vector<Gate>* hold) {
                 // more gates per pass than the shared-memory kernel's program holds: the register-blocked encoder merges the
                 // phase cascades of a QFT pass (hundreds of gates) into a handful of ops; what it cannot take is cut in two
                 const bool big = r->tile_bits == 12 && r->n_local >= 12 && r->force_path == 0;
-                BeamPlanner bp(gates, r->n_local, r->tile_bits, big ? 320 : max_ops, big ? 1000 : max_mats);
                 std::vector<PlannedPass> better;
-                if (bp.run(beam, beam, &better) && better.size() < plan.size()) {
+                if (beam_plan(gates, r->n_local, r->tile_bits, big, max_ops, max_mats, beam, &better) &&
+                    (big ? plan_sweeps(gates, r->n_local, better) < plan_sweeps(gates, r->n_local, plan) : better.size() < plan.size())) {
                     plan = better;
                     std::lock_guard<std::mutex> lk(g_plan_mu);
                     g_plans[key].passes = plan;
@@ -788,8 +820,7 @@ static void plan_for_debug(const std::vector<Gate>& gates, uint32_t n, uint32_t 
     const char* be = getenv("QB_PLAN_DEBUG_BEAM");
     if (be && atoi(be) > 0) {
         const bool big = tile_bits == 12 && n >= 12;
-        BeamPlanner bp(gates, n, tile_bits, big ? 320 : max_ops, big ? 1000 : max_mats);
-        if (bp.run((size_t)atoi(be), (size_t)atoi(be), passes)) return;
+        if (beam_plan(gates, n, tile_bits, big, max_ops, max_mats, (size_t)atoi(be), passes)) return;
         passes->clear();
     }
     plan_passes(gates, n, tile_bits, max_ops, max_mats, passes);

@@ -18,6 +18,9 @@ int run_pass_v2(Reg* r, const std::vector<Gate>& gates, const std::vector<size_t
                 const std::vector<uint32_t>& tile_pos, uint32_t lc, bool* handled);
 int run_pass_remote(Reg* r, uint32_t n_virtual, const std::vector<Gate>& gates, const std::vector<size_t>& gate_idx,
                     const std::vector<uint32_t>& tile_pos, uint32_t lc, c64* const* bases, bool* handled);
+// true if the register-blocked encoder takes the pass as it is (planners: a pass it refuses is cut in two sweeps at launch)
+bool pass_encodes_v2(uint32_t n_local, const std::vector<Gate>& gates, const std::vector<size_t>& gate_idx,
+                     const std::vector<uint32_t>& tile_pos, uint32_t lc);
 int64_t encode_rounds_debug(uint32_t n_local, const std::vector<Gate>& gates, const std::vector<size_t>& gate_idx,
                             const std::vector<uint32_t>& tile_pos, uint32_t lc, unsigned char* out, uint64_t cap);
 int64_t rounds_debug(uint32_t n, std::vector<Gate>& gates, unsigned char* out, uint64_t cap);

@@ -828,6 +828,13 @@ int64_t encode_rounds_debug(uint32_t n_local, const std::vector<Gate>& gates, co
     return (int64_t)(w - out);
 }
 
+bool pass_encodes_v2(uint32_t n_local, const std::vector<Gate>& gates, const std::vector<size_t>& gate_idx,
+                     const std::vector<uint32_t>& tile_pos, uint32_t lc) {
+    if (tile_pos.size() != RT || n_local < RT) return false;
+    static thread_local RProgLarge prog;
+    return encode_rounds(gates, gate_idx, tile_pos, lc, &prog, thorough_encoding(n_local));
+}
+
 // returns QB_OK and *handled = true if the pass went through the register-blocked kernel
 int run_pass_v2(Reg* r, const std::vector<Gate>& gates, const std::vector<size_t>& gate_idx, const std::vector<uint32_t>& tile_pos,
                 uint32_t lc, bool* handled) {
