@@ -36,6 +36,20 @@ def test_shors_21_fast(engine):
     assert "The factors of 21 are" in out
 
 
+def test_shors_working(engine):
+    """The reference's own test of the driver (examples/shors.rs:424-431): every composite number up to 15 through
+    shors(n, fast = true, use_circuit = false); only 15 gets past the classical checks and onto the register."""
+    import numpy as np
+
+    sys.path.insert(0, ROOT)
+    from examples import shors as driver
+
+    rng = np.random.default_rng(15)
+    for n in [4, 6, 8, 9, 10, 12, 14, 15]:
+        r = driver.shors(n, True, False, rng)
+        assert n % r == 0 and 1 < r < n, (n, r)
+
+
 def test_openqasm_example_and_protocols(engine):
     out = _run("examples/openqasm_example.py")
     assert "000: 50" in out.replace("49.99999999999999", "50") or "000: 50.0" in out or "000: 49.9" in out
