@@ -360,6 +360,7 @@ def parity_check(job, n=20):
     reg = job.register(n)
     reg.set_option(_ffi.QB_OPT_JIT, 2)
     reg.set_option(_ffi.QB_OPT_JIT_MIN_QUBITS, 12)
+    reg.set_option(_ffi.QB_OPT_PEEPHOLE, 1)      # on by default only from 28 local qubits: what the timed registers run with
     ora = OracleRegister.new([False] * n)
     reg.apply_batch([Operation(m, t) for m, t in ops_np])
     for m, t in ops_np:
@@ -378,6 +379,7 @@ def parity_check(job, n=20):
            "outcomes_equal": job.maxr(0.0 if outcomes_equal else 1.0) == 0.0,
            "jit_launches": reg.stat(_ffi.QB_STAT_JIT_LAUNCHES), "exchanges": reg.stat(_ffi.QB_STAT_SWAPS),
            "remote_passes": reg.stat(_ffi.QB_STAT_REMOTE_PASSES),
+           "peephole_rewrites": reg.stat(_ffi.QB_STAT_PEEPHOLE_REWRITES),
            "tolerance": {"max_abs_diff": 1e-12, "l2_diff": 1e-10}}
     res["ok"] = bool(res["max_abs_diff"] <= 1e-12 and res["l2_diff"] <= 1e-10 and res["outcomes_equal"])
     reg.close()
@@ -502,7 +504,10 @@ def run_ours(args):
         "config": {"workload": workload_name(n, kind, g), "qubits": n, "gates_per_step": n_gates,
                    "sharding": f"top {g} qubits over {world} GPU(s)",
                    "l2_policy": "inputs (>= 17 GB per GPU) are far larger than the 126 MB L2; no flush needed",
-                   "fusion": "on (tile passes)", "seed": 0},
+                   "fusion": "on (tile passes)", "seed": 0,
+                   "peephole": "on (H ; CX -> CZ ; H and friends on every flushed gate list, QB_OPT_PEEPHOLE; the operator is "
+                               "unchanged, see parity_check; QB_PEEPHOLE=0 python bench.py measures without it)",
+                   "peephole_rewrites_total": reg.stat(_ffi.QB_STAT_PEEPHOLE_REWRITES)},
         "effective_GBps": value * B_gate / 1e9,
         "physical_GBps": m["bytes"] * world / (ms / 1e3) / 1e9,
         "passes_per_step": m["passes"] / args.steps,

@@ -178,6 +178,9 @@ int qb_timer_stop(qb_reg* reg, float* ms);
                                   bit 6 = the prefetching ring: one persistent CTA of 512 threads per SM, two groups on alternate tiles,
                                   every thread fetches its amplitudes of the group's next tile with cp.async into a ring of three
                                   shared-memory tile buffers (measured slower than the default shape) */
+#define QB_OPT_PEEPHOLE 9      /* H / controlled-X / controlled-Z rewriting of every flushed gate list (C^nX = H C^nZ H: H ; CX -> CZ ; H,
+                                  CX ; H -> H ; CZ, H ; CX ; H -> CZ, H ; CZ ; H -> CX, H ; H -> nothing): 0 off, 1 on.  Default: on for
+                                  registers of >= 28 local qubits (env QB_PEEPHOLE=1 / 0 forces it on / off); only with fusion on */
 int qb_set_option(qb_reg* reg, int32_t option, int64_t value);
 
 #define QB_STAT_KERNEL_LAUNCHES 1 /* kernels launched by this handle since creation */
@@ -198,6 +201,7 @@ int qb_set_option(qb_reg* reg, int32_t option, int64_t value);
 #define QB_STAT_JIT_PENDING 16    /* process-wide: compiles queued or running */
 #define QB_STAT_JIT_FAILED 17     /* process-wide: compiles that failed */
 #define QB_STAT_FUSED_EXCHANGES 18 /* sharded registers: exchanges carried by the stores of a tile pass (counted in QB_STAT_SWAPS too) */
+#define QB_STAT_PEEPHOLE_REWRITES 19 /* rewrites of the H / CX / CZ peephole so far */
 int qb_get_stat(qb_reg* reg, int32_t stat, int64_t* value);
 
 /* Blocks until no specialised kernel is being compiled (process-wide).  A driver that is about to time a circuit it has
@@ -275,6 +279,12 @@ const char* qb_version(void);
  * [-3, m, a_0, b_0, ..., a_{m-1}, b_{m-1}]: the engine-qubit pairs that are swapped, in order, before a raw read.
  * Returns the number of int32 written or a negative error (tests/test_relabel.py replays it against the oracle). */
 int64_t qb_relabel_debug(uint32_t n, const qb_gate* gates, uint64_t count, int32_t* out, uint64_t capacity);
+
+/* Dry run of the H / CX / CZ peephole (QB_OPT_PEEPHOLE) on a gate list: out[0] = number of rewrites, then one record per gate
+ * of the rewritten list: [kind (0 dense, 1 diagonal), k, control mask, targets[0..k), m, re/im of the m matrix (dense: 2^k x 2^k
+ * row-major; diagonal: 2^k) entries] -- the engine's classified form (controls extracted).  Returns the number of doubles
+ * written or a negative error (tests/test_peephole.py applies both lists with the oracle). */
+int64_t qb_peephole_debug(uint32_t n, const qb_gate* gates, uint64_t count, double* out, uint64_t capacity);
 
 #ifdef __cplusplus
 }

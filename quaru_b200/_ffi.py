@@ -22,6 +22,8 @@ QB_OPT_JIT, QB_OPT_JIT_MIN_QUBITS, QB_OPT_JIT_VARIANT = 6, 7, 8
 (QB_STAT_JIT_LAUNCHES, QB_STAT_JIT_COMPILES, QB_STAT_JIT_MISSES, QB_STAT_JIT_COMPILE_MS, QB_STAT_JIT_PENDING,
  QB_STAT_JIT_FAILED) = 12, 13, 14, 15, 16, 17
 QB_STAT_FUSED_EXCHANGES = 18
+QB_OPT_PEEPHOLE = 9
+QB_STAT_PEEPHOLE_REWRITES = 19
 (QB_STAT_KERNEL_LAUNCHES, QB_STAT_PASSES, QB_STAT_GATES, QB_STAT_BYTES_MOVED, QB_STAT_SWAP_BYTES,
  QB_STAT_SWAPS, QB_STAT_TILE_LAUNCHES, QB_STAT_TILE_NS, QB_STAT_ROUNDS, QB_STAT_P2P_EXCHANGES,
  QB_STAT_REMOTE_PASSES) = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11
@@ -100,6 +102,7 @@ SIGNATURES = {
     "qb_shard_plan_debug": (ctypes.c_int64, [ctypes.c_uint32, ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(QbGate),
                                              ctypes.c_uint64, _i32p, ctypes.c_uint64, _u32p]),
     "qb_relabel_debug": (ctypes.c_int64, [ctypes.c_uint32, ctypes.POINTER(QbGate), ctypes.c_uint64, _i32p, ctypes.c_uint64]),
+    "qb_peephole_debug": (ctypes.c_int64, [ctypes.c_uint32, ctypes.POINTER(QbGate), ctypes.c_uint64, ctypes.POINTER(ctypes.c_double), ctypes.c_uint64]),
     "qb_plan_debug": (ctypes.c_int64, [ctypes.c_uint32, ctypes.POINTER(QbGate), ctypes.c_uint64, ctypes.c_uint32,
                                        _i32p, _i32p]),
     "qb_jit_source_debug": (ctypes.c_int64, [ctypes.c_char_p, ctypes.c_uint64, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,

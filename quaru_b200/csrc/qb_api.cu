@@ -55,6 +55,8 @@ static int alloc_common(Reg* r) {
     // SWAP gates as relabelling: for registers whose sweeps are expensive (QB_SWAP_RELABEL=1 / 0 forces it on / off)
     const char* rl = getenv("QB_SWAP_RELABEL");
     r->relabel = rl ? rl[0] == '1' : r->n_local >= 28;
+    const char* ph = getenv("QB_PEEPHOLE");   // H ; CX -> CZ ; H and friends: same policy, QB_PEEPHOLE=1 / 0 forces it on / off
+    r->peephole = ph ? ph[0] == '1' : r->n_local >= 28;
     if (const char* j = getenv("QB_JIT")) r->jit = (j[0] >= '0' && j[0] <= '2') ? j[0] - '0' : 1;
     if (const char* j = getenv("QB_JIT_MIN_QUBITS")) r->jit_min_qubits = (uint32_t)atoi(j);
     if (const char* j = getenv("QB_JIT_VARIANT")) {
@@ -166,6 +168,7 @@ static int flush(Reg* r, bool more_coming = false) {
     std::vector<Gate> gates;
     gates.swap(r->queue);
     r->held = 0;
+    if (r->peephole && r->fusion) r->st_peephole += (int64_t)peephole_h_cx(&gates);
     if (r->world > 1) return shard_run(r, gates);
     if (r->fusion && more_coming) {
         std::vector<Gate> hold;
@@ -342,6 +345,7 @@ int qb_clone(qb_reg* src_, qb_reg** out) try {
     dst->jit = src->jit; dst->jit_min_qubits = src->jit_min_qubits; dst->jit_min_blocks = src->jit_min_blocks;
     dst->jit_persistent = src->jit_persistent; dst->jit_prefetch = src->jit_prefetch; dst->jit_pipelined = src->jit_pipelined;
     dst->relabel = src->relabel; dst->label = src->label;   // same amplitudes, same qubit names
+    dst->peephole = src->peephole;
     // create_impl queued dst's initialisation (memset + the single 1) on dst->stream, a different non-blocking stream: the copy
     // is ordered after both streams' work by issuing it on dst->stream once src->stream has drained
     cudaError_t e = cudaStreamSynchronize(src->stream);
@@ -645,6 +649,7 @@ int qb_set_option(qb_reg* reg, int32_t option, int64_t value) try {
             r->max_queue = (uint64_t)value;
             return QB_OK;
         case QB_OPT_PROFILE: r->profile = value != 0; return QB_OK;
+        case QB_OPT_PEEPHOLE: r->peephole = value != 0; return QB_OK;
         case QB_OPT_JIT:
             if (value < 0 || value > 2) return set_error(QB_ERR_INVALID_ARGUMENT, value, "jit must be 0, 1 or 2");
             r->jit = (int)value;
@@ -689,6 +694,7 @@ int qb_get_stat(qb_reg* reg, int32_t stat, int64_t* value) try {
         case QB_STAT_JIT_COMPILES: *value = r->st_jit_compiles; return QB_OK;
         case QB_STAT_JIT_MISSES: *value = r->st_jit_misses; return QB_OK;
         case QB_STAT_FUSED_EXCHANGES: *value = r->st_fused_exchanges; return QB_OK;
+        case QB_STAT_PEEPHOLE_REWRITES: *value = r->st_peephole; return QB_OK;
         case QB_STAT_JIT_COMPILE_MS:
         case QB_STAT_JIT_PENDING:
         case QB_STAT_JIT_FAILED: {
@@ -734,6 +740,33 @@ int64_t qb_relabel_debug(uint32_t n, const qb_gate* gates, uint64_t count, int32
     rec.push_back(-3);
     rec.push_back((int32_t)(pairs.size() / 2));
     for (uint32_t p : pairs) rec.push_back((int32_t)p);
+    if (rec.size() > capacity) return set_error(QB_ERR_INVALID_ARGUMENT, (int64_t)rec.size(), "buffer too small");
+    for (size_t i = 0; i < rec.size(); ++i) out[i] = rec[i];
+    return (int64_t)rec.size();
+} QB_CATCH_ALL
+
+int64_t qb_peephole_debug(uint32_t n, const qb_gate* gates, uint64_t count, double* out, uint64_t capacity) try {
+    if ((count && !gates) || !out) return set_error(QB_ERR_INVALID_ARGUMENT, -1, "NULL argument");
+    if (n == 0 || n > 40) return set_error(QB_ERR_INVALID_ARGUMENT, n, "1..40 qubits");
+    std::vector<Gate> gs;
+    for (uint64_t i = 0; i < count; ++i) {
+        QB_TRY(validate_targets(n, gates[i].targets, gates[i].k));
+        Gate g;
+        if (!classify_gate(gates[i].matrix, gates[i].targets, gates[i].k, &g)) continue;
+        g.tag = (int64_t)i;
+        gs.push_back(std::move(g));
+    }
+    const size_t rewrites = peephole_h_cx(&gs);
+    std::vector<double> rec;
+    rec.push_back((double)rewrites);
+    for (const Gate& g : gs) {
+        rec.push_back(g.kind == GK_DIAG ? 1.0 : 0.0);
+        rec.push_back((double)g.k);
+        rec.push_back((double)g.ctrl_mask);   // n <= 40: exact in a double
+        for (uint32_t t : g.targets) rec.push_back((double)t);
+        rec.push_back((double)g.matrix.size());
+        for (const c64& e : g.matrix) { rec.push_back(e.x); rec.push_back(e.y); }
+    }
     if (rec.size() > capacity) return set_error(QB_ERR_INVALID_ARGUMENT, (int64_t)rec.size(), "buffer too small");
     for (size_t i = 0; i < rec.size(); ++i) out[i] = rec[i];
     return (int64_t)rec.size();

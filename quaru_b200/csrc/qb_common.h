@@ -77,6 +77,15 @@ void canonical_swaps(std::vector<uint32_t>* label, std::vector<uint32_t>* pairs)
                                                                                    // in order, to make the map the identity again
 void make_swap_gate(uint32_t a, uint32_t b, Gate* out);
 
+// ---- H / controlled-X / controlled-Z peephole over a gate list (qb_gate.cu; pure host logic, checked on CPU through
+// qb_peephole_debug).  C^nX(t) = H(t) C^nZ H(t), so on the qubit t of a (multi-)controlled X
+//     H ; CX      ->  CZ ; H          CX ; H   ->  H ; CZ          H ; CX ; H  ->  CZ          H ; CZ ; H  ->  CX      H ; H  ->  (nothing)
+// where ";" is program order and "adjacent" means adjacent among the gates that touch t.  A Hadamard costs a tile pass 32
+// FP64 instructions per thread, a CX whose control is a thread bit 64 selects, a CZ next to nothing (a sign in a per-thread
+// phase table), so every rule removes work; the unitary is unchanged up to the rounding of 2 * (1/sqrt 2)^2.
+// Returns the number of rewrites.
+size_t peephole_h_cx(std::vector<Gate>* gates);
+
 // ---- the handle ----------------------------------------------------------------------------------
 struct Shard;  // multi-GPU state (qb_shard.cu)
 struct XchgArgs;  // an exchange carried by the stores of a tile pass (qb_jit.h)
@@ -130,6 +139,9 @@ struct Reg {
     // SWAP relabelling (above the placement): caller's qubit q is engine ("logical") qubit label[q]
     bool relabel = false;
     std::vector<uint32_t> label;
+    // H / CX / CZ peephole over every flushed gate list (qb_gate.cu); default: registers whose sweeps are expensive
+    bool peephole = false;
+    int64_t st_peephole = 0;
 };
 
 // ---- kernels' host launchers (qb_kernels.cu) -------------------------------------------------------

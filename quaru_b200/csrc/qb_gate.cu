@@ -14,6 +14,8 @@
 #include <exception>
 #include <new>
 
+#include <math.h>
+
 #include "qb_common.h"
 
 namespace qb {
@@ -162,6 +164,125 @@ void canonical_swaps(std::vector<uint32_t>* label, std::vector<uint32_t>* pairs)
 void make_swap_gate(uint32_t a, uint32_t b, Gate* out) {
     const uint32_t t[2] = {a, b};
     classify_gate(kSwap, t, 2, out);
+}
+
+// ---- H / CX / CZ peephole --------------------------------------------------------------------------------------------------
+namespace {
+bool ph_is_h(const Gate& g, double* s) {
+    if (g.kind != GK_DENSE || g.k != 1 || g.ctrl_mask != 0 || g.matrix.size() != 4) return false;
+    for (const c64& e : g.matrix) if (e.y != 0.0) return false;
+    const double v = g.matrix[0].x;
+    if (!(g.matrix[1].x == v && g.matrix[2].x == v && g.matrix[3].x == -v)) return false;
+    if (fabs(2.0 * v * v - 1.0) > 1e-15) return false;   // the normalised Hadamard (operation.rs:350), to the last bit or two
+    *s = v;
+    return true;
+}
+bool ph_is_cx(const Gate& g) {   // X on one target under >= 1 controls
+    if (g.kind != GK_DENSE || g.k != 1 || g.ctrl_mask == 0 || g.matrix.size() != 4) return false;
+    return g.matrix[0].x == 0.0 && g.matrix[0].y == 0.0 && g.matrix[1].x == 1.0 && g.matrix[1].y == 0.0 && g.matrix[2].x == 1.0 &&
+           g.matrix[2].y == 0.0 && g.matrix[3].x == 0.0 && g.matrix[3].y == 0.0;
+}
+bool ph_is_cz(const Gate& g) {   // the phase -1 where >= 2 qubits are all 1 (what classify_gate makes of CZ / cnz)
+    return g.kind == GK_DIAG && g.k == 0 && g.matrix.size() == 1 && g.matrix[0].x == -1.0 && g.matrix[0].y == 0.0 &&
+           __builtin_popcountll(g.ctrl_mask) >= 2;
+}
+inline bool ph_touches(const Gate& g, uint32_t t) { return (g.qubit_mask() >> t) & 1ull; }
+long ph_last_touching(const std::vector<Gate>& v, long before, uint32_t t) {
+    for (long i = before - 1; i >= 0; --i)
+        if (ph_touches(v[(size_t)i], t)) return i;
+    return -1;
+}
+Gate ph_make_cz(uint64_t qubits, int64_t tag) {
+    Gate z;
+    z.k = 0;
+    z.kind = GK_DIAG;
+    z.matrix.assign(1, make_double2(-1.0, 0.0));
+    z.ctrl_mask = qubits;
+    z.tag = tag;
+    return z;
+}
+Gate ph_make_cx(uint64_t ctrl, uint32_t t, int64_t tag) {
+    Gate x;
+    x.k = 1;
+    x.kind = GK_DENSE;
+    x.targets.assign(1, t);
+    x.matrix = {make_double2(0, 0), make_double2(1, 0), make_double2(1, 0), make_double2(0, 0)};
+    x.ctrl_mask = ctrl;
+    x.tag = tag;
+    return x;
+}
+}  // namespace
+
+size_t peephole_h_cx(std::vector<Gate>* gates) {
+    std::vector<Gate> out;
+    out.reserve(gates->size() + 8);
+    size_t rewrites = 0;
+    // the Hadamard at out[i] (on t) meets what precedes it on t: H -> both vanish; CX on t -> the H moves in front of it, the
+    // CX becomes a CZ, and the H goes on looking
+    auto settle_h = [&](long i, uint32_t t) {
+        for (;;) {
+            double s_i = 0, s_p = 0;
+            ph_is_h(out[(size_t)i], &s_i);
+            const long p = ph_last_touching(out, i, t);
+            if (p < 0) return;
+            const Gate& prev = out[(size_t)p];
+            if (ph_is_h(prev, &s_p) && fabs(2.0 * s_i * s_p - 1.0) <= 1e-15) {
+                out.erase(out.begin() + i);
+                out.erase(out.begin() + p);
+                ++rewrites;
+                return;
+            }
+            if (ph_is_cx(prev) && prev.targets[0] == t) {          // CX ; H  ->  H ; CZ   (gates between them do not touch t)
+                Gate h = out[(size_t)i];
+                out.erase(out.begin() + i);
+                const Gate z = ph_make_cz(prev.ctrl_mask | (1ull << t), prev.tag);
+                out[(size_t)p] = z;
+                out.insert(out.begin() + p, h);
+                ++rewrites;
+                i = p;
+                continue;
+            }
+            if (ph_is_cz(prev) && ((prev.ctrl_mask >> t) & 1ull)) {   // H ; CZ ; H  ->  CX
+                const long q = ph_last_touching(out, p, t);
+                double s_q = 0;
+                if (q >= 0 && ph_is_h(out[(size_t)q], &s_q) && fabs(2.0 * s_i * s_q - 1.0) <= 1e-15) {
+                    const Gate x = ph_make_cx(prev.ctrl_mask & ~(1ull << t), t, prev.tag);
+                    out[(size_t)p] = x;
+                    out.erase(out.begin() + i);
+                    out.erase(out.begin() + q);
+                    ++rewrites;
+                }
+            }
+            return;
+        }
+    };
+    for (Gate& g : *gates) {
+        double s = 0;
+        if (ph_is_cx(g)) {
+            const uint32_t t = g.targets[0];
+            const long p = ph_last_touching(out, (long)out.size(), t);
+            double s_p = 0;
+            if (p >= 0 && ph_is_h(out[(size_t)p], &s_p)) {           // H ; CX  ->  CZ ; H
+                Gate h = out[(size_t)p];
+                out.erase(out.begin() + p);
+                out.push_back(ph_make_cz(g.ctrl_mask | (1ull << t), g.tag));
+                out.push_back(std::move(h));
+                ++rewrites;
+                continue;
+            }
+            out.push_back(std::move(g));
+            continue;
+        }
+        if (ph_is_h(g, &s)) {
+            const uint32_t t = g.targets[0];
+            out.push_back(std::move(g));
+            settle_h((long)out.size() - 1, t);
+            continue;
+        }
+        out.push_back(std::move(g));
+    }
+    gates->swap(out);
+    return rewrites;
 }
 
 }  // namespace qb

@@ -36,6 +36,11 @@ def main():
         ops = bench.build_circuit(n)
     os.environ.setdefault("QB_SWAP_RELABEL", "1")
     L = _ffi.lib()
+    if os.environ.get("QB_PEEPHOLE", "1") != "0":      # what flush() does for registers of >= 28 local qubits
+        from tests.test_peephole import _rewrite
+        before = len(ops)
+        rewrites, ops = _rewrite(n, ops)
+        print(f"peephole: {rewrites} rewrites, {before} -> {len(ops)} gates")
     progs = [p for p in em.dump_programs(n, ops) if p[0] == "prog"]
     print(f"{len(ops)} gates, {len(progs)} register-blocked passes")
     tot = collections.Counter()
