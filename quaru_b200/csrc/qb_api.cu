@@ -168,7 +168,10 @@ static int flush(Reg* r, bool more_coming = false) {
     std::vector<Gate> gates;
     gates.swap(r->queue);
     r->held = 0;
-    if (r->peephole && r->fusion) r->st_peephole += (int64_t)peephole_h_cx(&gates);
+    if (r->peephole && r->fusion) {
+        r->st_peephole += (int64_t)peephole_h_cx(&gates);
+        if (gates.empty()) return QB_OK;   // everything cancelled
+    }
     if (r->world > 1) return shard_run(r, gates);
     if (r->fusion && more_coming) {
         std::vector<Gate> hold;
