@@ -29,6 +29,7 @@ sys.path.insert(0, ROOT)
 CONFIGS = [  # (label, jit mode, jit variant, extra environment); most informative first, the time budget may cut the tail
     ("jit", 2, 2, {}),
     ("interpreter", 0, 2, {}),
+    ("jit_no_peephole", 2, 2, {"QB_PEEPHOLE": "0"}),
     ("jit_prefetch_ring", 2, 2 | 64, {}),
     ("jit_lc4", 2, 2, {"QB_PLAN_MIN_LC": "4"}),
     ("jit_3cta", 2, 3, {}),
@@ -120,7 +121,7 @@ def main():
             out["rows"].append({"label": label, "skipped": "time budget"})
             continue
         e = dict(os.environ)
-        for k in ("QB_PLAN_LOOKAHEAD", "QB_SWAP_RELABEL", "QB_TILE_IO_LOW", "QB_PLAN_MIN_LC", "QB_JIT", "QB_JIT_VARIANT", "QB_JIT_MIN_QUBITS"):
+        for k in ("QB_PLAN_LOOKAHEAD", "QB_SWAP_RELABEL", "QB_TILE_IO_LOW", "QB_PLAN_MIN_LC", "QB_JIT", "QB_JIT_VARIANT", "QB_JIT_MIN_QUBITS", "QB_PEEPHOLE"):
             e.pop(k, None)
         e.update(env)
         try:
