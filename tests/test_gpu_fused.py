@@ -174,3 +174,36 @@ def test_plan_cache_and_second_tier_planner_on_repeated_circuits(engine, n, kind
             ora.apply(o)
         assert_close(reg.state, ora.state, f"application {rep + 1}, {kind} n={n}")
     assert sweeps[2] <= sweeps[0] and sweeps[3] == sweeps[2], sweeps
+
+
+@pytest.mark.parametrize("n,kind,max_queue", [(12, "layers", None), (14, "qft+layers", None), (16, "mixed", None), (15, "layers", 9), (18, "layers", None)])
+def test_peephole_rewritten_lists_match_the_oracle(engine, n, kind, max_queue):
+    """QB_OPT_PEEPHOLE (on by default only from 28 local qubits): every flushed gate list is rewritten with C^nX = H C^nZ H before
+    it is planned (quaru_b200/csrc/qb_gate.cu, peephole_h_cx); the state and the measured outcomes still are the oracle's
+    (try_apply_fast / try_measure, /root/reference/src/register.rs:140-191, 297-342) -- also when the queue overflows in the
+    middle of the gate stream and held gates meet new ones."""
+    ops = {"layers": lambda: circuits.random_circuit(n, 10, seed=40 + n), "mixed": lambda: circuits.mixed_circuit(n, 150, 50 + n),
+           "qft+layers": lambda: circuits.qft_circuit(n) + circuits.random_circuit(n, 4, seed=n)}[kind]()
+    s = random_state(n, 4100 + n)
+    reg = engine.Register.new([False] * n)
+    reg.set_option(9, 1)                       # QB_OPT_PEEPHOLE
+    if max_queue:
+        reg.set_option(OPT_MAX_QUEUE, max_queue)
+    reg.set_state(s)
+    ora = OracleRegister(s.copy(), n)
+    eops = [engine.Operation(m, t) for m, t in ops]
+    if max_queue:
+        for o in eops:
+            reg.apply(o)
+    else:
+        reg.apply_batch(eops)
+    for o in ops:
+        ora.apply(o)
+    assert_close(reg.state, ora.state, f"peephole on, {kind} n={n}")
+    if kind != "mixed":
+        assert reg.stat(19) > 0, "the layer circuits have Hadamards next to CNOT targets"      # QB_STAT_PEEPHOLE_REWRITES
+    rng = np.random.default_rng(n)
+    for q in (0, n - 1, n // 2):
+        u = float(rng.random())
+        assert reg.try_measure(q, u) == ora.measure(q, u)
+    assert_close(reg.state, ora.state, "collapse after peephole-rewritten passes")
